@@ -1,0 +1,95 @@
+"""Generate golden fixtures from the UNMODIFIED reference modules.
+
+    python tests/golden/make_golden.py          (build container only: needs /root/reference)
+
+For every variant the reference's own SequenceGenerator / SequenceDiscriminator /
+losses.gradient_penalty / utils.slice_audio_batch are executed on CPU (torch fp32)
+for one critic iteration and one generator update from two states (seed-0 init,
+and a deterministic RNG-free perturbation of it), and the outputs are stored as
+small digests: scalars, the generated poses, per-tensor (sum, l2, max, 64 strided
+samples) of every gradient / BN buffer, and the windowing of a short signal.
+The fixtures travel to the GPU box; the reference does not.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import phase3_oracle as O          # noqa: E402
+from oracle import reference_harness as R      # noqa: E402
+
+VARIANTS = {"default": {}, "wavegan": {"enc_type": "wavegan"}, "unet": {"enc_type": "unet"},
+            "ablated": {"ablated": True}, "tanh": {"activ": "tanh"}}
+B = 2
+ALPHA_SEED = 77
+DATA_SEED = 1234
+
+
+def put(out, prefix, d):
+    for k in ("sum", "l2", "maxabs"):
+        out[f"{prefix}/{k}"] = np.float64(d[k])
+    out[f"{prefix}/samples"] = d["samples"].numpy()
+
+
+def one_state(cfg, state, out):
+    gen, critic = R.build_models(cfg, seed=0)
+    if state == "perturbed":
+        sg, sd = gen.state_dict(), critic.state_dict()
+        O.perturb_params(sg)
+        O.perturb_params(sd)
+        gen.load_state_dict(sg)
+        critic.load_state_dict(sd)
+    for k, v in list(gen.state_dict().items()) + list(critic.state_dict().items()):
+        put(out, f"{state}/init/{k}", O.tensor_digest(v))
+    real, audio, noise, _, noise_g = O.synthetic_batch(cfg, B, DATA_SEED)
+    r = R.critic_iteration(gen, critic, cfg, real, audio, noise, ALPHA_SEED, None)
+    for k in ("loss_critic", "gp", "w_dist", "err_real", "err_fake"):
+        out[f"{state}/critic/{k}"] = np.float64(r[k])
+    out[f"{state}/critic/fake"] = r["fake"].numpy()
+    for k, g in r["grads"].items():
+        put(out, f"{state}/critic/grad/{k}", O.tensor_digest(g))
+    for k, v in gen.state_dict().items():
+        if "running" in k or "num_batches" in k:
+            put(out, f"{state}/critic/genbuf/{k}", O.tensor_digest(v))
+    r = R.generator_update(gen, critic, cfg, real, audio, noise_g, None)
+    for k in ("loss_gen", "l1", "tv", "err_real", "err_fake"):
+        out[f"{state}/gen/{k}"] = np.float64(r[k])
+    out[f"{state}/gen/fake"] = r["fake"].contiguous().numpy()
+    for k, g in r["grads"].items():
+        if g is None:
+            out[f"{state}/gen/nograd/{k}"] = np.int8(1)
+        else:
+            put(out, f"{state}/gen/grad/{k}", O.tensor_digest(g))
+
+
+def windowing(out):
+    _, _, utils = R.import_reference()
+    g = torch.Generator().manual_seed(5)
+    for name, (n, win, stride) in {"a": (76800, 3200, 640), "b": (6400, 3200, 640),
+                                   "c": (5000, 700, 160), "d": (3200, 3200, 640)}.items():
+        x = torch.rand(2, n, generator=g)
+        s = utils.slice_audio_batch(x, win, stride, win - stride)
+        out[f"window/{name}/shape"] = np.array(s.shape)
+        out[f"window/{name}/args"] = np.array([n, win, stride])
+        put(out, f"window/{name}", O.tensor_digest(s, 256))
+        s1 = utils.slice_audio_batch(x[0], win, stride, win - stride)
+        assert torch.equal(s1, s[0])
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    here = os.path.dirname(os.path.abspath(__file__))
+    for name, over in VARIANTS.items():
+        cfg = O.make_cfg(**over)
+        out = {}
+        for state in ("init", "perturbed"):
+            one_state(cfg, state, out)
+        if name == "default":
+            windowing(out)
+        np.savez_compressed(os.path.join(here, f"phase3_{name}.npz"), **out)
+        print(name, len(out), "entries", os.path.getsize(os.path.join(here, f"phase3_{name}.npz")) // 1024, "KiB")
