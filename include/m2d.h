@@ -1,0 +1,220 @@
+/*
+ * m2d.h — C ABI of libm2d_b200.so: hand-written sm_100a kernels for the phase3
+ * audio-to-dance WGAN-GP training step of clementabary/music2dance.
+ *
+ * The reference has no native layer: every operation below is, in the reference,
+ * a PyTorch library call (ATen -> cuDNN/cuBLAS/MKL-DNN).  Each entry point cites
+ * the reference call site(s) (relative to the reference root) it replaces.
+ *
+ * Conventions
+ *   - plain C types only; device pointers are `float*` / `const float*`;
+ *     `stream` is a cudaStream_t passed as void* (NULL = legacy default stream)
+ *   - all work is enqueued on `stream`; no host synchronisation, no allocation:
+ *     the caller (PyTorch caching allocator) owns every buffer and workspace
+ *   - return 0 on success, negative m2d_status otherwise; m2d_last_error() gives
+ *     a thread-local message.  No C++ exceptions cross the boundary.
+ *   - activations are CHANNELS-LAST row matrices: element (batch b, row l, col c)
+ *     lives at  ptr[b*bs + l*ld + c]   (bs = batch stride, ld = row stride, floats)
+ *   - the library refuses to run on anything but compute capability 10.x.
+ */
+#ifndef M2D_H
+#define M2D_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    M2D_OK = 0,
+    M2D_ERR_BAD_ARG = -1,
+    M2D_ERR_CUDA = -2,
+    M2D_ERR_ARCH = -3,
+    M2D_ERR_WORKSPACE = -4
+} m2d_status;
+
+enum { M2D_ACT_NONE = 0, M2D_ACT_RELU = 1, M2D_ACT_LEAKY = 2, M2D_ACT_TANH = 3 };
+/* derivative masks: value v is multiplied by act'(.) evaluated from the stored
+ * post-activation tensor `mask`:  RELU: mask>0 ? 1 : 0;  LEAKY: mask>0 ? 1 : 0.2;
+ * TANH: 1 - mask^2 */
+enum { M2D_MASK_NONE = 0, M2D_MASK_RELU = 1, M2D_MASK_LEAKY = 2, M2D_MASK_TANH = 3 };
+
+const char* m2d_last_error(void);
+int m2d_version(void);
+/* 0 if device `dev` is sm_100-class, M2D_ERR_ARCH otherwise. */
+int m2d_check_device(int dev);
+
+/* ------------------------------------------------------------------------
+ * Row-convolution GEMM: the one contraction that serves Conv1d forward,
+ * Conv1d backward-data (per stride residue), the WGAN-GP tangent pass and
+ * every Linear layer.
+ *
+ *   y[b,i,n] = epi( sum_{t<T} sum_{c<Cc}  x[b, i*sr + roff0 + t*droff, c] * w[n, t*Cc + c] )
+ *
+ * rows outside [0, x_rows) read as zero (= Conv1d zero padding).
+ * Windowed mode (win_T > 0, Cc == 1): x is raw audio [nseq, win_seq_len]; batch
+ * b = seq*win_T + f addresses window f of sequence seq, i.e. sample
+ * f*win_stride - win_pad + r, zero outside the sequence — utils.py:329-353
+ * (slice_audio_batch) fused into the first encoder convolution.
+ *
+ * epi(v): v += bias[n]; v = act(v); [v += add  if add_before_mask]; [y2 = v];
+ *         v *= act'(mask); [v += add  otherwise]; y = v
+ *
+ * Replaces: nn.Conv1d.forward in phase3/archis/default.py:64-70,90-97,117-127,
+ * 202-210,217,298-303,326-333; nn.Linear.forward :153,161,175-176,256-257,280-281;
+ * conv/linear backward-data and the double-backward "ggO" pass reached through
+ * losses.py:40-44 and phase3/train.py:215,236.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+    const float* x; long long x_bs; int x_ld; int x_rows;
+    int nb;
+    int win_T, win_stride, win_pad, win_seq_len;
+    const float* w; int w_ld;
+    int N, T, Cc;
+    int sr, roff0, droff;
+    float* y; long long y_bs; int y_ld; int y_rows;
+    float* y2;                           /* optional: value before the mask / post-add (same geometry as y) */
+    const float* bias;
+    int act;
+    const float* mask; long long m_bs; int m_ld; int mask_mode;
+    const float* add; long long a_bs; int a_ld; int add_before_mask;
+    float* ws; long long ws_floats;      /* split-K workspace (may be NULL) */
+} m2d_rowconv_args;
+int m2d_rowconv(const m2d_rowconv_args* a, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Weight gradient of a row convolution, written in the PyTorch parameter
+ * layout (Cout, Cc, T):
+ *   dw[co,c,t] = beta*dw[co,c,t] + scale * sum_{b,l} dy[b,l,co] * x[b, l*sr + roff0 + t*droff, c]
+ * Two-stage deterministic split-K through `ws`.
+ * Replaces: conv/linear backward-weight and the double-backward "gW" pass
+ * (autograd of default.py layers; train.py:215,236; losses.py:40-44).
+ * ---------------------------------------------------------------------- */
+typedef struct {
+    const float* dy; long long dy_bs; int dy_ld; int dy_rows;
+    int nb;
+    const float* x; long long x_bs; int x_ld; int x_rows;
+    int win_T, win_stride, win_pad, win_seq_len;
+    int Cout, T, Cc;
+    int sr, roff0, droff;
+    float* dw;
+    float scale, beta;
+    float* ws; long long ws_floats;
+} m2d_wgrad_args;
+int m2d_wgrad(const m2d_wgrad_args* a, void* stream);
+/* minimum workspace (floats) m2d_wgrad needs for these shapes */
+long long m2d_wgrad_min_ws(int Cout, int T, int Cc);
+
+/* Re-layout of PyTorch Conv1d weights (Cout, Cin, k):
+ *   fwd : wp[co, t*Cin + ci]            = w[co, ci, t]
+ *   bwd : wd_rho[ci, q*Cout + co]       = w[co, ci, stride*q + rho],  rho = 0..stride-1,
+ *         blocks stored back to back, block rho has T_rho = ceil((k-rho)/stride) taps. */
+int m2d_pack_conv_fwd(const float* w, float* wp, int Cout, int Cin, int k, void* stream);
+int m2d_pack_conv_bwd(const float* w, float* wd, int Cout, int Cin, int k, int stride, void* stream);
+
+/* Backward-data of a Conv1d with ONE input channel (AudioDiscriminator.l1,
+ * default.py:298): dx[b,i] = sum_{co,j} dy[b,(i+pad-j)/stride,co] * w[co,0,j]. */
+int m2d_conv_dgrad_c1(const float* dy, int nb, int Lout, int Cout, const float* w, int k,
+                      int stride, int pad, float* dx, int Lin, void* stream);
+
+/* ------------------------------------------------------------------------
+ * GRU (torch.nn.GRU, batch_first, h0 = 0, gates [r|z|n]) — default.py:349-355,
+ * used at :19-20,35-38.  gi = W_ih x + b_ih is precomputed with m2d_rowconv.
+ * Persistent kernel: one thread-block cluster per batch group, W_hh rows sharded
+ * across the cluster's CTAs in shared memory, h exchanged through DSMEM.
+ *   h_out[b,t,:H] (row stride ldh)   save[b,t,4H] = r|z|n|(W_hn h + b_hn)
+ * ---------------------------------------------------------------------- */
+int m2d_gru_forward(const float* gi, const float* w_hh, const float* b_hh,
+                    float* h_out, int ldh, float* save, int B, int T, int H, void* stream);
+/* BPTT: dh_out[b,t,:H] (row stride ldd) upstream gradient; writes dgi, dgh [B,T,3H]. */
+int m2d_gru_backward(const float* dh_out, int ldd, const float* h_out, int ldh,
+                     const float* save, const float* w_hh,
+                     float* dgi, float* dgh, int B, int T, int H, void* stream);
+
+/* ------------------------------------------------------------------------
+ * BatchNorm1d (train mode, eps, momentum) over the rows of a channels-last matrix —
+ * default.py:65,68,91,94,118-127,154,179-180,217.
+ *   stats   : acc[0:C] += column sums, acc[C:2C] += column sums of squares (fp64)
+ *   apply   : y = act(gamma*(x-mean)*rstd + beta); block 0 also writes mean/rstd
+ *             to `mr` (2C floats) and updates running_mean/var (unbiased var);
+ *             y == NULL: statistics / running-stat update only
+ *   eval    : y = act(gamma*(x-rm)/sqrt(rv+eps)+beta)
+ *   bwd_red : acc[0:C] += sum dyy, acc[C:2C] += sum dyy*xhat, dyy = dy*act'(y)
+ *   bwd_app : dx = gamma*rstd*(dyy - acc0/M - xhat*acc1/M); also dgamma = acc1, dbeta = acc0
+ * ---------------------------------------------------------------------- */
+int m2d_colstats(const float* x, int ld, long long M, int C, double* acc, void* stream);
+int m2d_bn_apply(const float* x, int ldx, float* y, int ldy, long long M, int C,
+                 const double* acc, const float* gamma, const float* beta,
+                 float* running_mean, float* running_var, float momentum, float eps,
+                 float* mr, int act, void* stream);
+int m2d_bn_eval(const float* x, int ldx, float* y, int ldy, long long M, int C,
+                const float* gamma, const float* beta, const float* running_mean,
+                const float* running_var, float eps, int act, void* stream);
+int m2d_bn_bwd_reduce(const float* dy, int lddy, const float* y, int ldy, const float* x, int ldx,
+                      long long M, int C, const float* mr, int act, double* acc, void* stream);
+int m2d_bn_bwd_apply(const float* dy, int lddy, const float* y, int ldy, const float* x, int ldx,
+                     float* dx, int lddx, long long M, int C, const float* mr, const float* gamma,
+                     int act, const double* acc, float* dgamma, float* dbeta, void* stream);
+
+/* column sums (bias gradients): out[c] = beta*out[c] + scale * sum_m x[m,c] */
+int m2d_colsum(const float* x, int ld, long long M, int C, float* out, float scale, float beta,
+               double* acc, void* stream);
+
+/* ------------------------------------------------------------------------
+ * element-wise / reductions
+ * ---------------------------------------------------------------------- */
+/* y = a*x (+ b*z if z) */
+int m2d_axpby(const float* x, const float* z, float* y, long long n, float a, float b, void* stream);
+int m2d_fill(float* y, long long n, float v, void* stream);
+/* y[b,:] = s[b]*x[b,:] */
+int m2d_scale_rows(const float* x, const float* s, float* y, int nb, long long per, void* stream);
+/* losses.py:15-20: xi[b,:] = alpha[b]*real[b,:] + (1-alpha[b])*fake[b,:] */
+int m2d_interp(const float* real, const float* fake, const float* alpha, float* xi,
+               int nb, long long per, void* stream);
+/* out[b] += sum x[b,:]^2  (fp64 accumulators) */
+int m2d_rows_sumsq(const float* x, int nb, long long per, double* out, void* stream);
+/* out[0] += sum x  (fp64) */
+int m2d_sum(const float* x, long long n, double* out, void* stream);
+/* losses.py:55-60.  ss0/ss1 [B] sums of squares (ss1 NULL when ablated):
+ * scal[0] = gp, kappa0[b] = dGP/d||.|| chain factor (2/B)(n-1)/n, same for kappa1 */
+int m2d_gp_finalize(const double* ss0, const double* ss1, int B, float* gp, float* kappa0,
+                    float* kappa1, void* stream);
+/* train.py:226,233 + losses.py:76-82 on channels-last poses [B,T,C]:
+ * acc[0] += sum|real-fake|, acc[1] += sum|f[t+1]-f[t]|;
+ * dfake = (+= if accumulate) beta*dL1/dfake + eta*dTV/dfake */
+int m2d_pose_losses(const float* real, const float* fake, float* dfake, int B, int T, int C,
+                    float beta, float eta, int accumulate, double* acc, void* stream);
+/* relu / leaky / tanh derivative applied in place from stored activations */
+int m2d_act_bwd(float* d, const float* y, long long n, int mask_mode, void* stream);
+/* MaxPool1d(2,2) and Upsample(x2, linear, align_corners=False) on channels-last rows
+ * (default.py:236-237) */
+int m2d_maxpool2(const float* x, int ldx, float* y, int ldy, int nb, int Lin, int C, void* stream);
+int m2d_maxpool2_bwd(const float* x, int ldx, const float* dy, int lddy, float* dx, int lddx,
+                     int nb, int Lin, int C, int accumulate, void* stream);
+int m2d_upsample2(const float* x, int ldx, float* y, int ldy, int nb, int Lin, int C, void* stream);
+int m2d_upsample2_bwd(const float* dy, int lddy, float* dx, int lddx, int nb, int Lin, int C,
+                      int accumulate, void* stream);
+/* strided 2-D copy / transpose helpers for the (B,C,L) <-> channels-last boundary */
+int m2d_copy2d(const float* x, int ldx, float* y, int ldy, long long M, int C, int accumulate, void* stream);
+int m2d_transpose_bcl(const float* x, float* y, int nb, int R, int C, void* stream); /* [b,R,C]->[b,C,R] */
+
+/* Scalar losses (train.py:207-214 critic, :226-235 generator).  sums = fp64 {sum D(real),
+ * sum D(fake), sum|real-fake|, sum|tv diffs|}.  mode 0: out = {err_fake-err_real+c0*gp, gp,
+ * w_dist, err_real, err_fake};  mode 1: out = {err_real-err_fake+c0*l1+c1*tv, l1, tv, err_real, err_fake} */
+int m2d_wgan_scalars(const double* sums, const float* gp, int B, long long n_l1, long long n_tv,
+                     float c0, float c1, int mode, float* out, void* stream);
+
+/* utils.py:329-353 (slice_audio_batch / slice_audio_sequence): out[seq,f,j] =
+ * audio[seq, f*stride - pad_left + j], zero outside [0,A).  Pure indexing, bit-exact. */
+int m2d_slice_audio(const float* audio, float* out, int nseq, int A, int nwin, int W, int stride,
+                    int pad_left, void* stream);
+
+/* torch.optim.Adam (train.py:102-103,216,237): flat fused step over n floats.
+ * `step` is a device int32 counter incremented by the call (graph-replay safe);
+ * gradients are multiplied by `gscale` first (1/world_size after a sum all-reduce). */
+int m2d_adam(float* p, const float* g, float* m, float* v, long long n, int* step,
+             float lr, float beta1, float beta2, float eps, float gscale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* M2D_H */

@@ -1,0 +1,30 @@
+// Library-level entry points: error reporting, version, device check.
+#include "common.cuh"
+#include <cstring>
+
+namespace m2d {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace m2d
+
+extern "C" const char* m2d_last_error(void) { return m2d::g_err; }
+extern "C" int m2d_version(void) { return 100; }
+
+extern "C" int m2d_check_device(int dev) {
+    cudaDeviceProp p;
+    cudaError_t e = cudaGetDeviceProperties(&p, dev);
+    if (e != cudaSuccess) {
+        m2d::set_error("check_device: %s", cudaGetErrorString(e));
+        return M2D_ERR_CUDA;
+    }
+    if (p.major != 10) {
+        m2d::set_error("libm2d_b200 is built for sm_100a only; device %d is sm_%d%d", dev, p.major, p.minor);
+        return M2D_ERR_ARCH;
+    }
+    return M2D_OK;
+}

@@ -1,0 +1,60 @@
+// Shared helpers for libm2d_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdint>
+#include "../../include/m2d.h"
+
+namespace m2d {
+
+void set_error(const char* fmt, ...);
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return M2D_ERR_CUDA;
+    }
+    return M2D_OK;
+}
+
+#define M2D_REQUIRE(cond, ...)                      \
+    do {                                            \
+        if (!(cond)) {                              \
+            m2d::set_error(__VA_ARGS__);            \
+            return M2D_ERR_BAD_ARG;                 \
+        }                                           \
+    } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
+
+constexpr int kNumSMs = 148;   // B200
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == M2D_ACT_RELU) return v > 0.f ? v : 0.f;
+    if (act == M2D_ACT_LEAKY) return v > 0.f ? v : 0.2f * v;
+    if (act == M2D_ACT_TANH) return tanhf(v);
+    return v;
+}
+// derivative of the activation evaluated from the stored post-activation value y
+__device__ __forceinline__ float act_deriv(float y, int mode) {
+    if (mode == M2D_MASK_RELU) return y > 0.f ? 1.f : 0.f;
+    if (mode == M2D_MASK_LEAKY) return y > 0.f ? 1.f : 0.2f;
+    if (mode == M2D_MASK_TANH) return 1.f - y * y;
+    return 1.f;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace m2d

@@ -1,0 +1,658 @@
+// HBM-bound kernels: train-mode BatchNorm (stats / apply / backward), column sums,
+// WGAN-GP reductions, pose losses, pooling / upsampling, Adam.  All operate on
+// channels-last row matrices; column reductions accumulate in fp64.
+#include "common.cuh"
+
+namespace m2d {
+
+static inline int grid1d(long long n, int threads = 256, int waves = 8) {
+    long long b = cdiv(n, threads);
+    long long cap = (long long)waves * kNumSMs;
+    return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+// ---------------------------------------------------------------- column tiles
+// CTA = 32 columns x 8 row lanes; grid.x = column strips, grid.y = row chunks.
+struct ColGrid { dim3 grid; long long rows_per; };
+static ColGrid col_grid(long long M, int C) {
+    int gx = (int)cdiv(C, 32);
+    long long want = cdiv(4 * kNumSMs, gx);
+    long long gy = cdiv(M, 64);
+    if (gy > want) gy = want;
+    if (gy < 1) gy = 1;
+    ColGrid g;
+    g.rows_per = cdiv(M, gy);
+    g.grid = dim3((unsigned)gx, (unsigned)cdiv(M, g.rows_per));
+    return g;
+}
+
+template <int NQ, typename F>
+__device__ __forceinline__ void col_reduce(long long M, int C, long long rows_per, double* acc, F f) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ry = threadIdx.x >> 5;
+    const long long r0 = blockIdx.y * rows_per;
+    const long long r1 = r0 + rows_per < M ? r0 + rows_per : M;
+    double s[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) s[q] = 0.0;
+    if (c < C) {
+        for (long long r = r0 + ry; r < r1; r += 8) {
+            float v[NQ];
+            f(r, c, v);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) s[q] += (double)v[q];
+        }
+    }
+    __shared__ double sh[NQ][8][33];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) sh[q][ry][threadIdx.x & 31] = s[q];
+    __syncthreads();
+    if (ry == 0 && c < C) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            double t = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t += sh[q][j][threadIdx.x];
+            atomicAdd(acc + (long long)q * C + c, t);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+colstats_kernel(const float* __restrict__ x, int ld, long long M, int C, long long rows_per, double* acc) {
+    col_reduce<2>(M, C, rows_per, acc, [&](long long r, int c, float* v) {
+        float t = x[r * ld + c];
+        v[0] = t;
+        v[1] = t * t;
+    });
+}
+
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ x, int ld, long long M, int C, long long rows_per, double* acc) {
+    col_reduce<1>(M, C, rows_per, acc, [&](long long r, int c, float* v) { v[0] = x[r * ld + c]; });
+}
+
+__global__ void colsum_finalize_kernel(const double* acc, int C, float* out, float scale, float beta) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) {
+        float v = (float)(acc[c] * (double)scale);
+        out[c] = beta != 0.f ? beta * out[c] + v : v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, long long M, int C,
+                long long rows_per, const double* __restrict__ acc, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float* running_mean, float* running_var, float momentum,
+                float eps, float* mr, int act) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ry = threadIdx.x >> 5;
+    if (c >= C) return;
+    const double mean = acc[c] / (double)M;
+    double var = acc[C + c] / (double)M - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float mu = (float)mean;
+    if (blockIdx.y == 0 && ry == 0) {
+        if (mr) { mr[c] = mu; mr[C + c] = rstd; }
+        if (running_mean) {
+            double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+        }
+    }
+    if (!y) return;      // statistics-only call (dead LinearBlock branch, Q1)
+    const float g = gamma[c], bt = beta[c];
+    const long long r0 = blockIdx.y * rows_per;
+    const long long r1 = r0 + rows_per < M ? r0 + rows_per : M;
+    for (long long r = r0 + ry; r < r1; r += 8) {
+        float v = (x[r * ldx + c] - mu) * rstd * g + bt;
+        y[r * ldy + c] = apply_act(v, act);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bn_eval_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, long long M, int C,
+               long long rows_per, const float* gamma, const float* beta, const float* rm,
+               const float* rv, float eps, int act) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ry = threadIdx.x >> 5;
+    if (c >= C) return;
+    const float rstd = 1.f / sqrtf(rv[c] + eps);
+    const float mu = rm[c], g = gamma[c], bt = beta[c];
+    const long long r0 = blockIdx.y * rows_per;
+    const long long r1 = r0 + rows_per < M ? r0 + rows_per : M;
+    for (long long r = r0 + ry; r < r1; r += 8)
+        y[r * ldy + c] = apply_act((x[r * ldx + c] - mu) * rstd * g + bt, act);
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy,
+                     const float* __restrict__ x, int ldx, long long M, int C, long long rows_per,
+                     const float* __restrict__ mr, int act, double* acc) {
+    col_reduce<2>(M, C, rows_per, acc, [&](long long r, int c, float* v) {
+        float d = dy[r * lddy + c] * act_deriv(y[r * ldy + c], act);
+        float xh = (x[r * ldx + c] - mr[c]) * mr[C + c];
+        v[0] = d;
+        v[1] = d * xh;
+    });
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy,
+                    const float* __restrict__ x, int ldx, float* __restrict__ dx, int lddx, long long M,
+                    int C, long long rows_per, const float* __restrict__ mr,
+                    const float* __restrict__ gamma, int act, const double* __restrict__ acc,
+                    float* dgamma, float* dbeta) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ry = threadIdx.x >> 5;
+    if (c >= C) return;
+    const float s0 = (float)(acc[c] / (double)M), s1 = (float)(acc[C + c] / (double)M);
+    if (blockIdx.y == 0 && ry == 0) {
+        if (dbeta) dbeta[c] = (float)acc[c];
+        if (dgamma) dgamma[c] = (float)acc[C + c];
+    }
+    const float mu = mr[c], rstd = mr[C + c];
+    const float k = gamma[c] * rstd;
+    const long long r0 = blockIdx.y * rows_per;
+    const long long r1 = r0 + rows_per < M ? r0 + rows_per : M;
+    for (long long r = r0 + ry; r < r1; r += 8) {
+        float d = dy[r * lddy + c] * act_deriv(y[r * ldy + c], act);
+        float xh = (x[r * ldx + c] - mu) * rstd;
+        dx[r * lddx + c] = k * (d - s0 - xh * s1);
+    }
+}
+
+// ---------------------------------------------------------------- element-wise
+__global__ void axpby_kernel(const float* __restrict__ x, const float* __restrict__ z, float* y,
+                             long long n, float a, float b) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        y[i] = z ? a * x[i] + b * z[i] : a * x[i];
+}
+
+__global__ void fill_kernel(float* y, long long n, float v) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        y[i] = v;
+}
+
+__global__ void scale_rows_kernel(const float* __restrict__ x, const float* __restrict__ s, float* y,
+                                  long long per) {
+    const float k = s[blockIdx.y];
+    const long long base = blockIdx.y * per;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per;
+         i += (long long)gridDim.x * blockDim.x)
+        y[base + i] = k * x[base + i];
+}
+
+__global__ void interp_kernel(const float* __restrict__ real, const float* __restrict__ fake,
+                              const float* __restrict__ alpha, float* xi, long long per) {
+    const float a = alpha[blockIdx.y];
+    const long long base = blockIdx.y * per;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per;
+         i += (long long)gridDim.x * blockDim.x)
+        xi[base + i] = a * real[base + i] + (1.f - a) * fake[base + i];
+}
+
+__device__ __forceinline__ void block_atomic_add(double v, double* out) {
+    __shared__ double sh[32];
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) atomicAdd(out, t);
+    }
+    __syncthreads();
+}
+
+__global__ void rows_sumsq_kernel(const float* __restrict__ x, long long per, double* out) {
+    const long long base = blockIdx.y * per;
+    double s = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per;
+         i += (long long)gridDim.x * blockDim.x) {
+        float v = x[base + i];
+        s += (double)v * (double)v;
+    }
+    block_atomic_add(s, out + blockIdx.y);
+}
+
+__global__ void sum_kernel(const float* __restrict__ x, long long n, double* out) {
+    double s = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        s += (double)x[i];
+    block_atomic_add(s, out);
+}
+
+__global__ void gp_finalize_kernel(const double* ss0, const double* ss1, int B, float* gp, float* k0,
+                                   float* k1) {
+    // single block; B is a minibatch (<= a few thousand)
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float n0 = sqrtf((float)ss0[b] + 1e-12f);
+        float d0 = n0 - 1.f;
+        acc += (double)(d0 * d0);
+        k0[b] = (2.f / (float)B) * d0 / n0;
+        if (ss1) {
+            float n1 = sqrtf((float)ss1[b] + 1e-12f);
+            float d1 = n1 - 1.f;
+            acc += (double)(d1 * d1);
+            k1[b] = (2.f / (float)B) * d1 / n1;
+        }
+    }
+    __shared__ double total;
+    if (threadIdx.x == 0) total = 0.0;
+    __syncthreads();
+    block_atomic_add(acc, &total);
+    if (threadIdx.x == 0) gp[0] = (float)(total / (double)B);
+}
+
+__device__ __forceinline__ float sgn(float v) { return (v > 0.f) - (v < 0.f); }
+
+__global__ void pose_losses_kernel(const float* __restrict__ real, const float* __restrict__ fake,
+                                   float* dfake, int B, int T, int C, float beta, float eta,
+                                   int accumulate, double* acc) {
+    const long long n = (long long)B * T * C;
+    const float kl1 = beta / (float)n;
+    const float ktv = T > 1 ? eta / (float)((long long)B * (T - 1) * C) : 0.f;
+    double s1 = 0.0, s2 = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        int t = (int)((i / C) % T);
+        float f = fake[i];
+        float d = real[i] - f;
+        s1 += (double)fabsf(d);
+        float g = -kl1 * sgn(d);
+        if (t + 1 < T) {
+            float e = fake[i + C] - f;
+            s2 += (double)fabsf(e);
+            g -= ktv * sgn(e);
+        }
+        if (t > 0) g += ktv * sgn(f - fake[i - C]);
+        if (dfake) dfake[i] = accumulate ? dfake[i] + g : g;
+    }
+    block_atomic_add(s1, acc);
+    block_atomic_add(s2, acc + 1);
+}
+
+__global__ void act_bwd_kernel(float* d, const float* __restrict__ y, long long n, int mode) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        d[i] *= act_deriv(y[i], mode);
+}
+
+// ---------------------------------------------------------------- pool / upsample
+__global__ void maxpool2_kernel(const float* __restrict__ x, int ldx, float* y, int ldy, int Lin,
+                                int Lout, int C, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long long r = i / C;
+        int l = (int)(r % Lout);
+        long long b = r / Lout;
+        const float* p = x + (b * Lin + 2 * l) * (long long)ldx + c;
+        y[(b * Lout + l) * (long long)ldy + c] = fmaxf(p[0], p[ldx]);
+    }
+}
+
+__global__ void maxpool2_bwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ dy,
+                                    int lddy, float* dx, int lddx, int Lin, int Lout, int C,
+                                    long long total, int accumulate) {
+    // one thread per INPUT element
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long long r = i / C;
+        int li = (int)(r % Lin);
+        long long b = r / Lin;
+        int l = li >> 1;
+        float g = 0.f;
+        if (l < Lout) {
+            const float* p = x + (b * Lin + 2 * l) * (long long)ldx + c;
+            bool first = p[0] >= p[ldx];   // ties go to the first element (PyTorch argmax)
+            bool mine = (li & 1) ? !first : first;
+            if (mine) g = dy[(b * Lout + l) * (long long)lddy + c];
+        }
+        float* o = dx + (b * Lin + li) * (long long)lddx + c;
+        *o = accumulate ? *o + g : g;
+    }
+}
+
+// Upsample x2, linear, align_corners=False: src = (i+0.5)/2 - 0.5 clamped at 0
+__global__ void upsample2_kernel(const float* __restrict__ x, int ldx, float* y, int ldy, int Lin, int C,
+                                 long long total) {
+    const int Lout = 2 * Lin;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long long r = i / C;
+        int lo = (int)(r % Lout);
+        long long b = r / Lout;
+        float src = (lo + 0.5f) * 0.5f - 0.5f;
+        if (src < 0.f) src = 0.f;
+        int i0 = (int)src;
+        int i1 = i0 + (i0 < Lin - 1 ? 1 : 0);
+        float l1 = src - (float)i0, l0 = 1.f - l1;
+        const float* p = x + b * Lin * (long long)ldx + c;
+        y[(b * Lout + lo) * (long long)ldy + c] = l0 * p[(long long)i0 * ldx] + l1 * p[(long long)i1 * ldx];
+    }
+}
+
+__global__ void upsample2_bwd_kernel(const float* __restrict__ dy, int lddy, float* dx, int lddx, int Lin,
+                                     int C, long long total, int accumulate) {
+    // one thread per INPUT element m: gathers from outputs 2m-2 .. 2m+2
+    const int Lout = 2 * Lin;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long long r = i / C;
+        int m = (int)(r % Lin);
+        long long b = r / Lin;
+        const float* q = dy + b * Lout * (long long)lddy + c;
+        float g = 0.f;
+        int lo_begin = 2 * m - 2 < 0 ? 0 : 2 * m - 2;
+        int lo_end = 2 * m + 2 >= Lout ? Lout - 1 : 2 * m + 2;
+        for (int lo = lo_begin; lo <= lo_end; ++lo) {
+            float src = (lo + 0.5f) * 0.5f - 0.5f;
+            if (src < 0.f) src = 0.f;
+            int i0 = (int)src;
+            int i1 = i0 + (i0 < Lin - 1 ? 1 : 0);
+            float l1 = src - (float)i0, l0 = 1.f - l1;
+            float w = (i0 == m ? l0 : 0.f) + (i1 == m ? l1 : 0.f);
+            if (w != 0.f) g += w * q[(long long)lo * lddy];
+        }
+        float* o = dx + (b * Lin + m) * (long long)lddx + c;
+        *o = accumulate ? *o + g : g;
+    }
+}
+
+__global__ void copy2d_kernel(const float* __restrict__ x, int ldx, float* y, int ldy, long long M, int C,
+                              int accumulate) {
+    long long total = M * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long long r = i / C;
+        float v = x[r * ldx + c];
+        float* o = y + r * ldy + c;
+        *o = accumulate ? *o + v : v;
+    }
+}
+
+__global__ void transpose_kernel(const float* __restrict__ x, float* y, int R, int C) {
+    __shared__ float tile[32][33];
+    const float* xb = x + (long long)blockIdx.z * R * C;
+    float* yb = y + (long long)blockIdx.z * R * C;
+    int c = blockIdx.x * 32 + threadIdx.x;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        int r = blockIdx.y * 32 + j;
+        if (r < R && c < C) tile[j][threadIdx.x] = xb[(long long)r * C + c];
+    }
+    __syncthreads();
+    int r2 = blockIdx.y * 32 + threadIdx.x;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        int c2 = blockIdx.x * 32 + j;
+        if (r2 < R && c2 < C) yb[(long long)c2 * R + r2] = tile[threadIdx.x][j];
+    }
+}
+
+// train.py:207-214,226-235: scalar losses of one critic iteration / generator update
+__global__ void wgan_scalars_kernel(const double* sums, const float* gp, int B, long long n_l1, long long n_tv,
+                                    float c0, float c1, int mode, float* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const float er = (float)(sums[0] / (double)B), ef = (float)(sums[1] / (double)B);
+    if (mode == 0) {            // critic: err_fake - err_real + gamma*gp
+        const float g = gp[0];
+        out[0] = ef - er + c0 * g; out[1] = g; out[2] = ef - er; out[3] = er; out[4] = ef;
+    } else {                    // generator: err_real - err_fake + beta*l1 + eta*tv
+        const float l1 = (float)(sums[2] / (double)n_l1);
+        const float tv = n_tv > 0 ? (float)(sums[3] / (double)n_tv) : 0.f;
+        out[0] = er - ef + c0 * l1 + c1 * tv; out[1] = l1; out[2] = tv; out[3] = er; out[4] = ef;
+    }
+}
+
+// utils.py:329-353 slice_audio_batch as a standalone gather (bit-exact copy)
+__global__ void slice_audio_kernel(const float* __restrict__ audio, float* __restrict__ out, int A, int nwin,
+                                   int W, int stride, int pad_left) {
+    const long long seq = blockIdx.z;
+    const int f = blockIdx.y;
+    const float* a = audio + seq * A;
+    float* o = out + (seq * nwin + f) * (long long)W;
+    const int start = f * stride - pad_left;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < W; j += gridDim.x * blockDim.x) {
+        int pos = start + j;
+        o[j] = (pos >= 0 && pos < A) ? a[pos] : 0.f;
+    }
+}
+
+// ---------------------------------------------------------------- Adam
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, const int* step, float lr, float b1,
+                            float b2, float eps, float gscale) {
+    // step counter was already incremented for this update
+    const int t = *step;
+    const double bc1 = 1.0 - pow((double)b1, (double)t);
+    const double bc2 = 1.0 - pow((double)b2, (double)t);
+    const float step_size = (float)((double)lr / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        float gi = g[i] * gscale;
+        float mi = m[i] + (gi - m[i]) * (1.f - b1);
+        float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = p[i] - step_size * (mi / denom);
+    }
+}
+__global__ void tick_kernel(int* step) { *step += 1; }
+
+}  // namespace m2d
+
+using namespace m2d;
+
+extern "C" int m2d_colstats(const float* x, int ld, long long M, int C, double* acc, void* stream) {
+    M2D_REQUIRE(x && acc && M > 0 && C > 0, "colstats: bad args");
+    ColGrid g = col_grid(M, C);
+    colstats_kernel<<<g.grid, 256, 0, (cudaStream_t)stream>>>(x, ld, M, C, g.rows_per, acc);
+    return check_launch("colstats");
+}
+
+extern "C" int m2d_bn_apply(const float* x, int ldx, float* y, int ldy, long long M, int C,
+                            const double* acc, const float* gamma, const float* beta,
+                            float* running_mean, float* running_var, float momentum, float eps,
+                            float* mr, int act, void* stream) {
+    M2D_REQUIRE(x && acc && gamma && beta && M > 0 && C > 0, "bn_apply: bad args");
+    ColGrid g = col_grid(M, C);
+    bn_apply_kernel<<<g.grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, M, C, g.rows_per, acc, gamma,
+                                                            beta, running_mean, running_var, momentum,
+                                                            eps, mr, act);
+    return check_launch("bn_apply");
+}
+
+extern "C" int m2d_bn_eval(const float* x, int ldx, float* y, int ldy, long long M, int C,
+                           const float* gamma, const float* beta, const float* running_mean,
+                           const float* running_var, float eps, int act, void* stream) {
+    M2D_REQUIRE(x && y && gamma && beta && running_mean && running_var && M > 0 && C > 0, "bn_eval: bad args");
+    ColGrid g = col_grid(M, C);
+    bn_eval_kernel<<<g.grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, M, C, g.rows_per, gamma, beta,
+                                                           running_mean, running_var, eps, act);
+    return check_launch("bn_eval");
+}
+
+extern "C" int m2d_bn_bwd_reduce(const float* dy, int lddy, const float* y, int ldy, const float* x,
+                                 int ldx, long long M, int C, const float* mr, int act, double* acc,
+                                 void* stream) {
+    M2D_REQUIRE(dy && y && x && mr && acc && M > 0 && C > 0, "bn_bwd_reduce: bad args");
+    ColGrid g = col_grid(M, C);
+    bn_bwd_reduce_kernel<<<g.grid, 256, 0, (cudaStream_t)stream>>>(dy, lddy, y, ldy, x, ldx, M, C,
+                                                                 g.rows_per, mr, act, acc);
+    return check_launch("bn_bwd_reduce");
+}
+
+extern "C" int m2d_bn_bwd_apply(const float* dy, int lddy, const float* y, int ldy, const float* x,
+                                int ldx, float* dx, int lddx, long long M, int C, const float* mr,
+                                const float* gamma, int act, const double* acc, float* dgamma,
+                                float* dbeta, void* stream) {
+    M2D_REQUIRE(dy && y && x && dx && mr && gamma && acc && M > 0 && C > 0, "bn_bwd_apply: bad args");
+    ColGrid g = col_grid(M, C);
+    bn_bwd_apply_kernel<<<g.grid, 256, 0, (cudaStream_t)stream>>>(dy, lddy, y, ldy, x, ldx, dx, lddx, M, C,
+                                                                g.rows_per, mr, gamma, act, acc, dgamma,
+                                                                dbeta);
+    return check_launch("bn_bwd_apply");
+}
+
+extern "C" int m2d_colsum(const float* x, int ld, long long M, int C, float* out, float scale,
+                          float beta, double* acc, void* stream) {
+    M2D_REQUIRE(x && out && acc && M > 0 && C > 0, "colsum: bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(double) * C, st);
+    if (e != cudaSuccess) { set_error("colsum memset: %s", cudaGetErrorString(e)); return M2D_ERR_CUDA; }
+    ColGrid g = col_grid(M, C);
+    colsum_kernel<<<g.grid, 256, 0, st>>>(x, ld, M, C, g.rows_per, acc);
+    colsum_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(acc, C, out, scale, beta);
+    return check_launch("colsum");
+}
+
+extern "C" int m2d_axpby(const float* x, const float* z, float* y, long long n, float a, float b,
+                         void* stream) {
+    M2D_REQUIRE(x && y && n > 0, "axpby: bad args");
+    axpby_kernel<<<grid1d(n), 256, 0, (cudaStream_t)stream>>>(x, z, y, n, a, b);
+    return check_launch("axpby");
+}
+
+extern "C" int m2d_fill(float* y, long long n, float v, void* stream) {
+    M2D_REQUIRE(y && n > 0, "fill: bad args");
+    fill_kernel<<<grid1d(n), 256, 0, (cudaStream_t)stream>>>(y, n, v);
+    return check_launch("fill");
+}
+
+extern "C" int m2d_scale_rows(const float* x, const float* s, float* y, int nb, long long per,
+                              void* stream) {
+    M2D_REQUIRE(x && s && y && nb > 0 && per > 0, "scale_rows: bad args");
+    dim3 grid((unsigned)grid1d(per, 256, 2), (unsigned)nb);
+    scale_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, s, y, per);
+    return check_launch("scale_rows");
+}
+
+extern "C" int m2d_interp(const float* real, const float* fake, const float* alpha, float* xi, int nb,
+                          long long per, void* stream) {
+    M2D_REQUIRE(real && fake && alpha && xi && nb > 0 && per > 0, "interp: bad args");
+    dim3 grid((unsigned)grid1d(per, 256, 2), (unsigned)nb);
+    interp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(real, fake, alpha, xi, per);
+    return check_launch("interp");
+}
+
+extern "C" int m2d_rows_sumsq(const float* x, int nb, long long per, double* out, void* stream) {
+    M2D_REQUIRE(x && out && nb > 0 && per > 0, "rows_sumsq: bad args");
+    dim3 grid((unsigned)grid1d(per, 256, 1), (unsigned)nb);
+    rows_sumsq_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, per, out);
+    return check_launch("rows_sumsq");
+}
+
+extern "C" int m2d_sum(const float* x, long long n, double* out, void* stream) {
+    M2D_REQUIRE(x && out && n > 0, "sum: bad args");
+    sum_kernel<<<grid1d(n, 256, 1), 256, 0, (cudaStream_t)stream>>>(x, n, out);
+    return check_launch("sum");
+}
+
+extern "C" int m2d_gp_finalize(const double* ss0, const double* ss1, int B, float* gp, float* kappa0,
+                               float* kappa1, void* stream) {
+    M2D_REQUIRE(ss0 && gp && kappa0 && B > 0 && (!ss1 || kappa1), "gp_finalize: bad args");
+    gp_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(ss0, ss1, B, gp, kappa0, kappa1);
+    return check_launch("gp_finalize");
+}
+
+extern "C" int m2d_pose_losses(const float* real, const float* fake, float* dfake, int B, int T, int C,
+                               float beta, float eta, int accumulate, double* acc, void* stream) {
+    M2D_REQUIRE(real && fake && acc && B > 0 && T > 0 && C > 0, "pose_losses: bad args");
+    long long n = (long long)B * T * C;
+    pose_losses_kernel<<<grid1d(n, 256, 2), 256, 0, (cudaStream_t)stream>>>(real, fake, dfake, B, T, C, beta,
+                                                                        eta, accumulate, acc);
+    return check_launch("pose_losses");
+}
+
+extern "C" int m2d_act_bwd(float* d, const float* y, long long n, int mask_mode, void* stream) {
+    M2D_REQUIRE(d && y && n > 0, "act_bwd: bad args");
+    act_bwd_kernel<<<grid1d(n), 256, 0, (cudaStream_t)stream>>>(d, y, n, mask_mode);
+    return check_launch("act_bwd");
+}
+
+extern "C" int m2d_maxpool2(const float* x, int ldx, float* y, int ldy, int nb, int Lin, int C,
+                            void* stream) {
+    M2D_REQUIRE(x && y && nb > 0 && Lin > 1 && C > 0, "maxpool2: bad args");
+    int Lout = Lin / 2;
+    long long total = (long long)nb * Lout * C;
+    maxpool2_kernel<<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, Lin, Lout, C, total);
+    return check_launch("maxpool2");
+}
+
+extern "C" int m2d_maxpool2_bwd(const float* x, int ldx, const float* dy, int lddy, float* dx, int lddx,
+                                int nb, int Lin, int C, int accumulate, void* stream) {
+    M2D_REQUIRE(x && dy && dx && nb > 0 && Lin > 1 && C > 0, "maxpool2_bwd: bad args");
+    int Lout = Lin / 2;
+    long long total = (long long)nb * Lin * C;
+    maxpool2_bwd_kernel<<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(x, ldx, dy, lddy, dx, lddx, Lin,
+                                                                       Lout, C, total, accumulate);
+    return check_launch("maxpool2_bwd");
+}
+
+extern "C" int m2d_upsample2(const float* x, int ldx, float* y, int ldy, int nb, int Lin, int C,
+                             void* stream) {
+    M2D_REQUIRE(x && y && nb > 0 && Lin > 0 && C > 0, "upsample2: bad args");
+    long long total = (long long)nb * 2 * Lin * C;
+    upsample2_kernel<<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, Lin, C, total);
+    return check_launch("upsample2");
+}
+
+extern "C" int m2d_upsample2_bwd(const float* dy, int lddy, float* dx, int lddx, int nb, int Lin, int C,
+                                 int accumulate, void* stream) {
+    M2D_REQUIRE(dy && dx && nb > 0 && Lin > 0 && C > 0, "upsample2_bwd: bad args");
+    long long total = (long long)nb * Lin * C;
+    upsample2_bwd_kernel<<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(dy, lddy, dx, lddx, Lin, C, total,
+                                                                        accumulate);
+    return check_launch("upsample2_bwd");
+}
+
+extern "C" int m2d_copy2d(const float* x, int ldx, float* y, int ldy, long long M, int C, int accumulate,
+                          void* stream) {
+    M2D_REQUIRE(x && y && M > 0 && C > 0, "copy2d: bad args");
+    copy2d_kernel<<<grid1d(M * C), 256, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, M, C, accumulate);
+    return check_launch("copy2d");
+}
+
+extern "C" int m2d_transpose_bcl(const float* x, float* y, int nb, int R, int C, void* stream) {
+    M2D_REQUIRE(x && y && nb > 0 && R > 0 && C > 0, "transpose: bad args");
+    dim3 grid((unsigned)cdiv(C, 32), (unsigned)cdiv(R, 32), (unsigned)nb);
+    transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, y, R, C);
+    return check_launch("transpose");
+}
+
+extern "C" int m2d_wgan_scalars(const double* sums, const float* gp, int B, long long n_l1, long long n_tv,
+                                float c0, float c1, int mode, float* out, void* stream) {
+    M2D_REQUIRE(sums && out && B > 0 && (mode == 1 || gp), "wgan_scalars: bad args");
+    wgan_scalars_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, gp, B, n_l1, n_tv, c0, c1, mode, out);
+    return check_launch("wgan_scalars");
+}
+
+extern "C" int m2d_slice_audio(const float* audio, float* out, int nseq, int A, int nwin, int W, int stride,
+                               int pad_left, void* stream) {
+    M2D_REQUIRE(audio && out && nseq > 0 && A > 0 && nwin > 0 && W > 0 && stride >= 0, "slice_audio: bad args");
+    M2D_REQUIRE(nwin <= 65535 && nseq <= 65535, "slice_audio: too many windows/sequences");
+    dim3 grid((unsigned)(cdiv(W, 256) < 8 ? cdiv(W, 256) : 8), (unsigned)nwin, (unsigned)nseq);
+    slice_audio_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(audio, out, A, nwin, W, stride, pad_left);
+    return check_launch("slice_audio");
+}
+
+extern "C" int m2d_adam(float* p, const float* g, float* m, float* v, long long n, int* step, float lr,
+                        float beta1, float beta2, float eps, float gscale, void* stream) {
+    M2D_REQUIRE(p && g && m && v && step && n > 0, "adam: bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    tick_kernel<<<1, 1, 0, st>>>(step);
+    adam_kernel<<<grid1d(n), 256, 0, st>>>(p, g, m, v, n, step, lr, beta1, beta2, eps, gscale);
+    return check_launch("adam");
+}

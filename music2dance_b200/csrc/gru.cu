@@ -1,0 +1,260 @@
+// Persistent GRU recurrence (forward and BPTT) for sm_100a.
+//
+// One thread-block cluster per batch group.  The cluster's CTAs shard the hidden
+// units: CTA `rank` keeps the three gate rows of W_hh (forward) or the matching
+// columns (backward) of its units resident in shared memory for the whole
+// sequence, so W_hh is read from HBM exactly once per launch.  Each step every
+// CTA computes its slice, pushes it into every peer's shared memory through
+// DSMEM, and one cluster barrier publishes the step (buffers are double-buffered,
+// which makes a single barrier per step sufficient).
+#include <cooperative_groups.h>
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace m2d {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+struct GruPlan {
+    int NC;    // CTAs per cluster
+    int nu;    // hidden units per CTA
+    int BG;    // sequences per cluster
+    int HP;    // H padded (multiple of 4, +4 to rotate banks)
+    int HP3;   // 3H padded likewise
+};
+
+static GruPlan make_plan(int H) {
+    GruPlan p;
+    p.NC = H >= 128 ? 8 : (H >= 64 ? 4 : (H >= 32 ? 2 : 1));
+    p.nu = (H + p.NC - 1) / p.NC;
+    p.BG = 256 / p.nu;
+    if (p.BG > 8) p.BG = 8;
+    if (p.BG < 1) p.BG = 1;
+    p.HP = ((H + 3) / 4) * 4 + 4;
+    p.HP3 = ((3 * H + 3) / 4) * 4 + 4;
+    return p;
+}
+
+template <bool SAVE>
+__global__ void __launch_bounds__(256)
+gru_fwd_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh,
+               const float* __restrict__ b_hh, float* __restrict__ h_out, int ldh,
+               float* __restrict__ save, int B, int T, int H, int nu, int BG, int HP) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int NC = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int b0 = (blockIdx.x / NC) * BG;
+    const int u0 = rank * nu;
+    const int nown = max(0, min(nu, H - u0));
+    extern __shared__ __align__(16) float smem[];
+    float* Ws = smem;                       // [3][nu][HP]
+    float* hs = smem + 3 * nu * HP;         // [2][BG][HP]
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < 3 * nu * HP; idx += blockDim.x) {
+        int k = idx % HP;
+        int gu = idx / HP;
+        int u = gu % nu, g = gu / nu;
+        Ws[idx] = (u < nown && k < H) ? w_hh[((long long)g * H + u0 + u) * H + k] : 0.f;
+    }
+    for (int idx = tid; idx < 2 * BG * HP; idx += blockDim.x) hs[idx] = 0.f;
+    __syncthreads();
+    cluster.sync();
+
+    const int u = tid / BG, b = tid - u * BG;
+    const bool active = u < nown && (b0 + b) < B && tid < nu * BG;
+    const int uu = u0 + u;
+    float bhr = 0.f, bhz = 0.f, bhn = 0.f;
+    if (active) {
+        bhr = b_hh[uu]; bhz = b_hh[H + uu]; bhn = b_hh[2 * H + uu];
+    }
+    const long long row0 = (long long)(b0 + b) * T;
+    float hprev = 0.f;
+    float gir = 0.f, giz = 0.f, gin = 0.f;
+    if (active) {
+        const float* g0 = gi + row0 * 3 * H;
+        gir = g0[uu]; giz = g0[H + uu]; gin = g0[2 * H + uu];
+    }
+    for (int t = 0; t < T; ++t) {
+        const int cur = t & 1;
+        if (active) {
+            float nr = 0.f, nz = 0.f, nn = 0.f;
+            if (t + 1 < T) {       // prefetch next step's input projection
+                const float* g1 = gi + (row0 + t + 1) * 3 * H;
+                nr = g1[uu]; nz = g1[H + uu]; nn = g1[2 * H + uu];
+            }
+            const float4* wr = reinterpret_cast<const float4*>(Ws + (0 * nu + u) * HP);
+            const float4* wz = reinterpret_cast<const float4*>(Ws + (1 * nu + u) * HP);
+            const float4* wn = reinterpret_cast<const float4*>(Ws + (2 * nu + u) * HP);
+            const float4* hv = reinterpret_cast<const float4*>(hs + (cur * BG + b) * HP);
+            float ar = 0.f, az = 0.f, an = 0.f;
+            const int n4 = (H + 3) / 4;
+#pragma unroll 4
+            for (int k = 0; k < n4; ++k) {
+                float4 h4 = hv[k];
+                float4 a4 = wr[k], b4 = wz[k], c4 = wn[k];
+                ar = fmaf(a4.x, h4.x, ar); ar = fmaf(a4.y, h4.y, ar); ar = fmaf(a4.z, h4.z, ar); ar = fmaf(a4.w, h4.w, ar);
+                az = fmaf(b4.x, h4.x, az); az = fmaf(b4.y, h4.y, az); az = fmaf(b4.z, h4.z, az); az = fmaf(b4.w, h4.w, az);
+                an = fmaf(c4.x, h4.x, an); an = fmaf(c4.y, h4.y, an); an = fmaf(c4.z, h4.z, an); an = fmaf(c4.w, h4.w, an);
+            }
+            float r = sigmoidf_(gir + (ar + bhr));
+            float z = sigmoidf_(giz + (az + bhz));
+            float ghn = an + bhn;
+            float n = tanhf(gin + r * ghn);
+            float h = (1.f - z) * n + z * hprev;
+            hprev = h;
+            const long long row = row0 + t;
+            h_out[row * ldh + uu] = h;
+            if (SAVE) {
+                float* sv = save + row * 4 * H;
+                sv[uu] = r; sv[H + uu] = z; sv[2 * H + uu] = n; sv[3 * H + uu] = ghn;
+            }
+            const int off = ((cur ^ 1) * BG + b) * HP + uu;
+            for (int rk = 0; rk < NC; ++rk) cluster.map_shared_rank(hs, rk)[off] = h;
+            gir = nr; giz = nz; gin = nn;
+        }
+        cluster.sync();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gru_bwd_kernel(const float* __restrict__ dh_out, int ldd, const float* __restrict__ h_out, int ldh,
+               const float* __restrict__ save, const float* __restrict__ w_hh,
+               float* __restrict__ dgi, float* __restrict__ dgh, int B, int T, int H, int nu, int BG,
+               int HP3) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int NC = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int b0 = (blockIdx.x / NC) * BG;
+    const int u0 = rank * nu;
+    const int nown = max(0, min(nu, H - u0));
+    extern __shared__ __align__(16) float smem[];
+    float* WT = smem;                    // [nu][HP3]: WT[u][j] = w_hh[j][u0+u]
+    float* ds = smem + nu * HP3;         // [2][BG][HP3]
+    const int tid = threadIdx.x;
+    const int H3 = 3 * H;
+    // coalesced read of w_hh rows, transposed store
+    for (int idx = tid; idx < nu * HP3; idx += blockDim.x) WT[idx] = 0.f;
+    for (int idx = tid; idx < 2 * BG * HP3; idx += blockDim.x) ds[idx] = 0.f;
+    __syncthreads();
+    for (int idx = tid; idx < H3 * nu; idx += blockDim.x) {
+        int u = idx % nu, j = idx / nu;
+        if (u < nown) WT[u * HP3 + j] = w_hh[(long long)j * H + u0 + u];
+    }
+    __syncthreads();
+    cluster.sync();
+
+    const int u = tid / BG, b = tid - u * BG;
+    const bool active = u < nown && (b0 + b) < B && tid < nu * BG;
+    const int uu = u0 + u;
+    const long long row0 = (long long)(b0 + b) * T;
+    float dh_rec = 0.f;
+    // prefetched operands of the current step
+    float p_dh = 0.f, p_r = 0.f, p_z = 0.f, p_n = 0.f, p_g = 0.f, p_hp = 0.f;
+    auto fetch = [&](int t) {
+        const long long row = row0 + t;
+        p_dh = dh_out[row * ldd + uu];
+        const float* sv = save + row * 4 * H;
+        p_r = sv[uu]; p_z = sv[H + uu]; p_n = sv[2 * H + uu]; p_g = sv[3 * H + uu];
+        p_hp = t > 0 ? h_out[(row - 1) * ldh + uu] : 0.f;
+    };
+    if (active) fetch(T - 1);
+    for (int t = T - 1; t >= 0; --t) {
+        const int cur = (T - 1 - t) & 1;
+        float dh_direct = 0.f;
+        if (active) {
+            const float dh = p_dh + dh_rec;
+            const float r = p_r, z = p_z, n = p_n, ghn = p_g, hp = p_hp;
+            if (t > 0) fetch(t - 1);
+            const float dn = dh * (1.f - z);
+            const float dz = dh * (hp - n);
+            const float dnp = dn * (1.f - n * n);
+            const float dzp = dz * z * (1.f - z);
+            const float drp = dnp * ghn * r * (1.f - r);
+            const float dghn = dnp * r;
+            const long long row = row0 + t;
+            float* gi_ = dgi + row * H3;
+            float* gh_ = dgh + row * H3;
+            gi_[uu] = drp; gi_[H + uu] = dzp; gi_[2 * H + uu] = dnp;
+            gh_[uu] = drp; gh_[H + uu] = dzp; gh_[2 * H + uu] = dghn;
+            const int off = (cur * BG + b) * HP3;
+            for (int rk = 0; rk < NC; ++rk) {
+                float* d = cluster.map_shared_rank(ds, rk) + off;
+                d[uu] = drp; d[H + uu] = dzp; d[2 * H + uu] = dghn;
+            }
+            dh_direct = dh * z;
+        }
+        cluster.sync();
+        if (active && t > 0) {
+            const float4* wv = reinterpret_cast<const float4*>(WT + u * HP3);
+            const float4* dv = reinterpret_cast<const float4*>(ds + (cur * BG + b) * HP3);
+            float a0 = 0.f, a1 = 0.f;
+            const int n4 = (H3 + 3) / 4;
+#pragma unroll 4
+            for (int k = 0; k < n4; ++k) {
+                float4 w4 = wv[k], d4 = dv[k];
+                a0 = fmaf(w4.x, d4.x, a0); a1 = fmaf(w4.y, d4.y, a1);
+                a0 = fmaf(w4.z, d4.z, a0); a1 = fmaf(w4.w, d4.w, a1);
+            }
+            dh_rec = dh_direct + (a0 + a1);
+        }
+    }
+}
+
+template <typename K, typename... Args>
+static int launch_cluster(K kernel, int nblocks, int NC, size_t smem, cudaStream_t st, Args... args) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("gru: smem attribute (%zu B): %s", smem, cudaGetErrorString(e));
+        return M2D_ERR_CUDA;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)nblocks);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)NC;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kernel, args...);
+    if (e != cudaSuccess) {
+        set_error("gru: launch: %s", cudaGetErrorString(e));
+        return M2D_ERR_CUDA;
+    }
+    return M2D_OK;
+}
+
+}  // namespace m2d
+
+using namespace m2d;
+
+extern "C" int m2d_gru_forward(const float* gi, const float* w_hh, const float* b_hh, float* h_out,
+                               int ldh, float* save, int B, int T, int H, void* stream) {
+    M2D_REQUIRE(gi && w_hh && b_hh && h_out && B > 0 && T > 0 && H > 0 && ldh >= H, "gru_forward: bad args");
+    GruPlan p = make_plan(H);
+    size_t smem = (size_t)(3 * p.nu * p.HP + 2 * p.BG * p.HP) * sizeof(float);
+    M2D_REQUIRE(smem <= 220 * 1024, "gru_forward: hidden size %d needs %zu B of shared memory", H, smem);
+    int groups = (B + p.BG - 1) / p.BG;
+    if (save)
+        return launch_cluster(gru_fwd_kernel<true>, groups * p.NC, p.NC, smem, (cudaStream_t)stream, gi,
+                              w_hh, b_hh, h_out, ldh, save, B, T, H, p.nu, p.BG, p.HP);
+    return launch_cluster(gru_fwd_kernel<false>, groups * p.NC, p.NC, smem, (cudaStream_t)stream, gi,
+                          w_hh, b_hh, h_out, ldh, save, B, T, H, p.nu, p.BG, p.HP);
+}
+
+extern "C" int m2d_gru_backward(const float* dh_out, int ldd, const float* h_out, int ldh,
+                                const float* save, const float* w_hh, float* dgi, float* dgh, int B,
+                                int T, int H, void* stream) {
+    M2D_REQUIRE(dh_out && h_out && save && w_hh && dgi && dgh && B > 0 && T > 0 && H > 0,
+                "gru_backward: bad args");
+    GruPlan p = make_plan(H);
+    size_t smem = (size_t)(p.nu * p.HP3 + 2 * p.BG * p.HP3) * sizeof(float);
+    M2D_REQUIRE(smem <= 220 * 1024, "gru_backward: hidden size %d needs %zu B of shared memory", H, smem);
+    int groups = (B + p.BG - 1) / p.BG;
+    return launch_cluster(gru_bwd_kernel, groups * p.NC, p.NC, smem, (cudaStream_t)stream, dh_out, ldd,
+                          h_out, ldh, save, w_hh, dgi, dgh, B, T, H, p.nu, p.BG, p.HP3);
+}

@@ -1,0 +1,783 @@
+"""Manual forward/backward executors for the phase3 generator and critic.
+
+These classes own no parameters: they are handed the parameter / gradient tensors
+of the drop-in modules (``archis/default.py``) and drive the C-ABI kernels on
+channels-last activations.  Reference: phase3/archis/default.py (every class),
+losses.py:5-60, phase3/train.py:186-237.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .ops import Mat
+
+ACT_ID, ACT_RELU, ACT_LEAKY, ACT_TANH = 0, 1, 2, 3
+ACT_CODE = {"id": ACT_ID, "relu": ACT_RELU, "tanh": ACT_TANH, "leaky": ACT_LEAKY}
+
+
+class Workspace:
+    """Named, shape-keyed activation buffers (stable addresses across steps, which
+    is what CUDA-graph capture needs) + a shared split-K scratch + fp64 accumulators."""
+
+    def __init__(self, device, scratch_floats=1 << 25, acc_doubles=1 << 16):
+        self.device = device
+        self.bufs = {}
+        self.scratch = torch.empty(scratch_floats, dtype=torch.float32, device=device)
+        self.acc = torch.zeros(acc_doubles, dtype=torch.float64, device=device)
+        self.acc_used = 0
+
+    def mat(self, name, nb, rows, cols, ld=None):
+        ld = cols if ld is None else ld
+        key = (name, nb, rows, cols, ld)
+        t = self.bufs.get(key)
+        if t is None:
+            t = torch.empty(nb * rows * ld, dtype=torch.float32, device=self.device)
+            self.bufs[key] = t
+        return Mat(t, nb, rows, cols, ld)
+
+    def vec(self, name, n, dtype=torch.float32):
+        key = (name, n, dtype)
+        t = self.bufs.get(key)
+        if t is None:
+            t = torch.zeros(n, dtype=dtype, device=self.device)
+            self.bufs[key] = t
+        return t
+
+    def acc_reset(self):
+        """Zero the fp64 accumulator arena and restart slot allocation."""
+        self.acc.zero_()
+        self.acc_used = 0
+
+    def acc_slot(self, n):
+        assert self.acc_used + n <= self.acc.numel(), "fp64 accumulator arena exhausted"
+        s = self.acc[self.acc_used:self.acc_used + n]
+        self.acc_used += n
+        return s
+
+    def bytes(self):
+        return sum(t.numel() * t.element_size() for t in self.bufs.values()) + self.scratch.numel() * 4
+
+
+def conv_out_len(L, k, s, p):
+    return (L + 2 * p - k) // s + 1
+
+
+class ConvLayer:
+    """Conv1d / Linear as row-convolution GEMMs.  `w` (Cout,Cin,k) or (Cout,Cin),
+    `b` (Cout,), `gw`/`gb` same-shaped gradient tensors (views of a flat buffer)."""
+
+    def __init__(self, name, w, b, gw, gb, Cin, Cout, k=1, stride=1, pad=0, Lin=1, need_dgrad=True):
+        self.name, self.w, self.b, self.gw, self.gb = name, w, b, gw, gb
+        self.Cin, self.Cout, self.k, self.s, self.p, self.Lin = Cin, Cout, k, stride, pad, Lin
+        self.Lout = conv_out_len(Lin, k, stride, pad)
+        self.full = (pad == 0 and self.Lout == 1)          # collapses the row axis: acts like Linear(k*Cin, Cout)
+        self.need_dgrad = need_dgrad
+        dev = w.device
+        n = Cout * Cin * k
+        self.wp = None if (Cin == 1 or k == 1) else torch.empty(n, dtype=torch.float32, device=dev)
+        self.wd = torch.empty(n, dtype=torch.float32, device=dev) if (need_dgrad and Cin > 1) else None
+        self.res = []                                       # (r0, rho, c0, Trho, offset) per stride residue
+        off = 0
+        for rho in range(stride):
+            Trho = max(0, -(-(k - rho) // stride))
+            self.res.append((rho, Trho, off))
+            off += Cin * Cout * Trho
+
+    def wf(self):
+        return self.w if self.wp is None else self.wp
+
+    def pack(self):
+        if self.wp is not None:
+            ops.pack_conv_fwd(self.w, self.wp, self.Cout, self.Cin, self.k)
+        if self.wd is not None:
+            if self.full or self.k == 1:
+                ops.pack_conv_bwd(self.wf(), self.wd, self.Cout, self.Cin * self.k, 1, 1)
+            else:
+                ops.pack_conv_bwd(self.w, self.wd, self.Cout, self.Cin, self.k, self.s)
+
+    # y[b,l,:] = act(conv(x)[b,l,:] + bias)
+    def fwd(self, x, y, act=0, bias=True, ws=None, win=None, **epi):
+        ops.rowconv(x, self.wf(), y, T=self.k, Cc=self.Cin, N=self.Cout, sr=self.s, roff0=-self.p,
+                    droff=1, bias=self.b if bias else None, act=act, ws=ws, win=win, **epi)
+
+    # dx = conv_transpose(dy) with fused epilogue (mask by act'(prev), residual add, ...)
+    def dgrad(self, dy, dx, ws=None, mask=None, mask_mode=0, add=None, add_before_mask=False, y2=None):
+        assert self.wd is not None
+        if self.full or self.k == 1:
+            K = self.k * self.Cin
+            xd = dy.flat_rows()
+            fl = self.k > 1          # full-length conv: (n, L, C) -> (n, L*C); Linear: rows as they are
+            f = (lambda m: None if m is None else (m.flatten_cols().flat_rows() if fl else m.flat_rows()))
+            yd = f(dx)
+            ops.rowconv(xd, self.wd, yd, T=1, Cc=self.Cout, N=K, ws=ws, mask=f(mask), mask_mode=mask_mode,
+                        add=f(add), add_before_mask=add_before_mask, y2=f(y2))
+            return
+        s = self.s
+        for r0 in range(s):
+            rho, c0 = (r0 + self.p) % s, (r0 + self.p) // s
+            _, Trho, off = self.res[rho]
+            nrows = -(-(dx.rows - r0) // s)
+            if nrows <= 0:
+                continue
+            assert Trho > 0
+
+            def sub(m):
+                if m is None:
+                    return None
+                v = Mat(m.t, m.nb, nrows, m.cols, m.ld * s, m.bs)
+                v.ptr = m.ptr + 4 * r0 * m.ld
+                return v
+            wd = self.wd[off:]
+            ops.rowconv(dy, wd, sub(dx), T=Trho, Cc=self.Cout, N=self.Cin, sr=1, roff0=c0, droff=-1,
+                        ws=ws, mask=sub(mask), mask_mode=mask_mode, add=sub(add),
+                        add_before_mask=add_before_mask, y2=sub(y2))
+
+    def wgrad(self, dy, x, ws, scale=1.0, beta=0.0, win=None, bias=True, acc=None, bbeta=None):
+        """gw = beta*gw + scale*dW;  gb = bbeta*gb + scale*db (bbeta defaults to beta)."""
+        ops.wgrad(dy, x, self.gw, Cout=self.Cout, T=self.k, Cc=self.Cin, sr=self.s, roff0=-self.p, droff=1,
+                  scale=scale, beta=beta, ws=ws, win=win)
+        if bias and self.gb is not None:
+            ops.colsum(dy.flat_rows(), self.gb, acc, scale=scale, beta=beta if bbeta is None else bbeta)
+
+
+class BNLayer:
+    def __init__(self, name, P, G):
+        self.name = name
+        self.gamma, self.beta = P[name + ".weight"], P[name + ".bias"]
+        self.rm, self.rv, self.nbt = P[name + ".running_mean"], P[name + ".running_var"], P[name + ".num_batches_tracked"]
+        self.ggamma, self.gbeta = G.get(name + ".weight"), G.get(name + ".bias")
+        self.C = self.gamma.numel()
+        self.mr = torch.empty(2 * self.C, dtype=torch.float32, device=self.gamma.device)
+
+    def fwd(self, c, a, act, train, wk):
+        """a = act(BN(c)).  `a` None: only update running statistics (dead branch)."""
+        cf = c.flat_rows()
+        if train:
+            acc = wk.acc_slot(2 * self.C)
+            ops.colstats(cf, acc)
+            ops.bn_apply(cf, None if a is None else a.flat_rows(), acc, self.gamma, self.beta, self.rm,
+                         self.rv, self.mr, act)
+        elif a is not None:
+            ops.bn_eval(cf, a.flat_rows(), self.gamma, self.beta, self.rm, self.rv, act)
+
+    def bwd(self, e_a, a, c, dc, act_mode, wk):
+        """dc = d(loss)/d(c) from e_a = d(loss)/d(a)."""
+        acc = wk.acc_slot(2 * self.C)
+        ops.bn_bwd_reduce(e_a.flat_rows(), a.flat_rows(), c.flat_rows(), self.mr, act_mode, acc)
+        ops.bn_bwd_apply(e_a.flat_rows(), a.flat_rows(), c.flat_rows(), dc.flat_rows(), self.mr, self.gamma,
+                         act_mode, acc, self.ggamma, self.gbeta)
+
+
+def _conv_from(P, G, name, Cin, Cout, k, s, p, Lin, need_dgrad=True):
+    return ConvLayer(name, P[name + ".weight"], P[name + ".bias"], G.get(name + ".weight"),
+                     G.get(name + ".bias"), Cin, Cout, k, s, p, Lin, need_dgrad)
+
+
+class ConvBNAct:
+    """conv -> BatchNorm(train/eval) -> activation, with its backward."""
+
+    def __init__(self, P, G, conv_name, bn_name, Cin, Cout, k, s, p, Lin, act, need_dgrad=True):
+        self.conv = _conv_from(P, G, conv_name, Cin, Cout, k, s, p, Lin, need_dgrad)
+        self.bn = BNLayer(bn_name, P, G)
+        self.act = act
+        self.tag = conv_name
+
+    def fwd(self, x, nb, wk, train, win=None, out=None):
+        cv = self.conv
+        c = wk.mat(self.tag + ":c", nb, cv.Lout, cv.Cout)
+        a = out if out is not None else wk.mat(self.tag + ":a", nb, cv.Lout, cv.Cout)
+        cv.fwd(x, c, ws=wk.scratch, win=win)
+        if out is not None and (a.ld != a.cols):
+            # BN kernels take a row stride, so writing into a concat buffer is direct
+            pass
+        self.bn.fwd(c, a, self.act, train, wk)
+        self.x, self.c, self.a = x, c, a
+        return a
+
+    def bwd(self, e_a, wk, win=None, e_x=None, **dg):
+        """e_a: gradient w.r.t. the post-activation output.  Writes parameter grads;
+        if e_x is given, the gradient w.r.t. the input (fused epilogue options in dg)."""
+        cv = self.conv
+        dc = wk.mat(self.tag + ":dc", self.c.nb, cv.Lout, cv.Cout)
+        self.bn.bwd(e_a, self.a, self.c, dc, self.act, wk)
+        cv.wgrad(dc, self.x, wk.scratch, win=win, acc=wk.acc_slot(cv.Cout))
+        if e_x is not None:
+            cv.dgrad(dc, e_x, ws=wk.scratch, **dg)
+
+
+# ===========================================================================
+# generator
+# ===========================================================================
+
+class _Encoder:
+    def layers(self):
+        raise NotImplementedError
+
+
+class DefaultEncoder(_Encoder):
+    """default.py:59-82: conv(1->32,k250,s50,p124)+BN+ReLU; 5x[conv(k4,s2,p1)+BN+ReLU];
+    conv(1024->out,k2)+activ.  The first conv reads raw audio with fused windowing."""
+
+    def __init__(self, P, G, cfg):
+        p = "audio_enc.model."
+        W = cfg["audio_feat_samples"]
+        self.blocks = [ConvBNAct(P, G, p + "conv_layers.0", p + "activations.0.0", 1, 32, 250, 50, 124, W,
+                                 ACT_RELU, need_dgrad=False)]
+        L, C = self.blocks[0].conv.Lout, 32
+        for i in range(1, 6):
+            self.blocks.append(ConvBNAct(P, G, p + f"conv_layers.{i}", p + f"activations.{i}.0", C, 2 * C, 4,
+                                         2, 1, L, ACT_RELU))
+            L, C = self.blocks[-1].conv.Lout, 2 * C
+        self.head = _conv_from(P, G, p + "conv_layers.6", C, cfg["input_vector_size"], 2, 1, 0, L)
+        assert self.head.Lout == 1, "window size incompatible with the default encoder (Q11)"
+        self.act = ACT_CODE[cfg["activ"]]
+
+    def convs(self):
+        return [b.conv for b in self.blocks] + [self.head]
+
+    def fwd(self, audio, nb, win, wk, train, out):
+        x = audio
+        for i, blk in enumerate(self.blocks):
+            x = blk.fwd(x, nb, wk, train, win=win if i == 0 else None)
+        self.head.fwd(x, out, act=self.act, ws=wk.scratch)
+        self.hx, self.out = x, out
+
+    def bwd(self, e_out, audio, nb, win, wk):
+        """e_out: gradient w.r.t. the encoder output [nb,1,out] (modified in place)."""
+        if self.act != ACT_ID:
+            ops.act_bwd(e_out, self.out, nb * self.head.Cout, self.act)
+        self.head.wgrad(e_out, self.hx, wk.scratch, acc=wk.acc_slot(self.head.Cout))
+        e = wk.mat("enc:e_head", nb, self.head.Lin, self.head.Cin)
+        self.head.dgrad(e_out, e, ws=wk.scratch)
+        for i in range(len(self.blocks) - 1, -1, -1):
+            blk = self.blocks[i]
+            if i > 0:
+                e_x = wk.mat(f"enc:e{i}", nb, blk.conv.Lin, blk.conv.Cin)
+                blk.bwd(e, wk, e_x=e_x)
+                e = e_x
+            else:
+                blk.bwd(e, wk, win=win)
+
+
+class WaveGANEncoder(_Encoder):
+    """default.py:114-143: 4x[conv(k25,s4,no pad)+BN+ReLU], conv(256->out,k5)+activ."""
+
+    def __init__(self, P, G, cfg):
+        p = "audio_enc.model."
+        L, C = cfg["audio_feat_samples"], 1
+        self.blocks = []
+        for i in range(1, 5):
+            Co = 32 * (2 ** (i - 1))
+            self.blocks.append(ConvBNAct(P, G, p + f"l{i}", p + f"bn{i}", C, Co, 25, 4, 0, L, ACT_RELU,
+                                         need_dgrad=(i > 1)))
+            L, C = self.blocks[-1].conv.Lout, Co
+        self.head = _conv_from(P, G, p + "l5", C, cfg["input_vector_size"], 5, 1, 0, L)
+        assert self.head.Lout == 1, "window size incompatible with the WaveGAN encoder"
+        self.act = ACT_CODE[cfg["activ"]]
+
+    convs = DefaultEncoder.convs
+    fwd = DefaultEncoder.fwd
+    bwd = DefaultEncoder.bwd
+
+
+class UNetEncoder(_Encoder):
+    """default.py:85-111,213-246."""
+
+    def __init__(self, P, G, cfg):
+        p = "audio_enc.model."
+        W = cfg["audio_feat_samples"]
+        self.stem = [ConvBNAct(P, G, p + "conv_layers.0", p + "activations.0.0", 1, 32, 160, 4, 79, W,
+                               ACT_LEAKY, need_dgrad=False)]
+        L = self.stem[0].conv.Lout
+        self.stem.append(ConvBNAct(P, G, p + "conv_layers.1", p + "activations.1.0", 32, 64, 4, 2, 1, L, ACT_LEAKY))
+        L = self.stem[1].conv.Lout
+        self.stem.append(ConvBNAct(P, G, p + "conv_layers.2", p + "activations.2.0", 64, 128, 4, 2, 1, L, ACT_LEAKY))
+        L = self.stem[2].conv.Lout
+        self.L0 = L
+        C = 128
+        q = p + "ublock.convblock"
+        Ls = [L, L // 2, L // 4, L // 8]
+        self.Ls = Ls
+        mk = lambda i, cin, Li: ConvBNAct(P, G, q + f"{i}.conv", q + f"{i}.bn", cin, C, 3, 1, 1, Li, ACT_LEAKY)
+        self.cb = [None, mk(1, C, Ls[0]), mk(2, C, Ls[1]), mk(3, C, Ls[2]), mk(4, C, Ls[3]),
+                   mk(5, 2 * C, Ls[2]), mk(6, 2 * C, Ls[1]), mk(7, 2 * C, Ls[0])]
+        assert 2 * Ls[3] == Ls[2] and 2 * Ls[2] == Ls[1] and 2 * Ls[1] == Ls[0], "U-block needs L divisible by 8"
+        self.head = _conv_from(P, G, p + "fc", C, cfg["input_vector_size"], L, 1, 0, L)
+        assert self.head.Lout == 1
+        self.act = ACT_CODE[cfg["activ"]]
+        self.C = C
+
+    def convs(self):
+        return [b.conv for b in self.stem] + [b.conv for b in self.cb[1:]] + [self.head]
+
+    def fwd(self, audio, nb, win, wk, train, out):
+        C, Ls, cb = self.C, self.Ls, self.cb
+        x = audio
+        for i, blk in enumerate(self.stem):
+            x = blk.fwd(x, nb, wk, train, win=win if i == 0 else None)
+        # concat buffers: [upsampled | skip], skip written directly by the producing block
+        cat5 = wk.mat("unet:cat5", nb, Ls[2], 2 * C)
+        cat6 = wk.mat("unet:cat6", nb, Ls[1], 2 * C)
+        cat7 = wk.mat("unet:cat7", nb, Ls[0], 2 * C)
+        x1 = cb[1].fwd(x, nb, wk, train, out=cat7.cols_slice(C, 2 * C))
+        d1 = wk.mat("unet:d1", nb, Ls[1], C)
+        ops.maxpool2(x1, d1, nb, Ls[0], C)
+        x2 = cb[2].fwd(d1, nb, wk, train, out=cat6.cols_slice(C, 2 * C))
+        d2 = wk.mat("unet:d2", nb, Ls[2], C)
+        ops.maxpool2(x2, d2, nb, Ls[1], C)
+        x3 = cb[3].fwd(d2, nb, wk, train, out=cat5.cols_slice(C, 2 * C))
+        d3 = wk.mat("unet:d3", nb, Ls[3], C)
+        ops.maxpool2(x3, d3, nb, Ls[2], C)
+        x4 = cb[4].fwd(d3, nb, wk, train)
+        ops.upsample2(x4, cat5.cols_slice(0, C), nb, Ls[3], C)
+        y3 = cb[5].fwd(cat5, nb, wk, train)
+        ops.upsample2(y3, cat6.cols_slice(0, C), nb, Ls[2], C)
+        y2 = cb[6].fwd(cat6, nb, wk, train)
+        ops.upsample2(y2, cat7.cols_slice(0, C), nb, Ls[1], C)
+        y1 = cb[7].fwd(cat7, nb, wk, train)
+        self.head.fwd(y1, out, act=self.act, ws=wk.scratch)
+        self.sv = (x, x1, x2, x3, x4, y3, y2, y1, d1, d2, d3)
+        self.out = out
+
+    def bwd(self, e_out, audio, nb, win, wk):
+        C, Ls, cb = self.C, self.Ls, self.cb
+        x, x1, x2, x3, x4, y3, y2, y1, d1, d2, d3 = self.sv
+        if self.act != ACT_ID:
+            ops.act_bwd(e_out, self.out, nb * self.head.Cout, self.act)
+        self.head.wgrad(e_out, y1, wk.scratch, acc=wk.acc_slot(self.head.Cout))
+        e_y1 = wk.mat("unet:e_y1", nb, Ls[0], C)
+        self.head.dgrad(e_out, e_y1, ws=wk.scratch)
+        e_cat7 = wk.mat("unet:e_cat7", nb, Ls[0], 2 * C)
+        cb[7].bwd(e_y1, wk, e_x=e_cat7)
+        e_y2 = wk.mat("unet:e_y2", nb, Ls[1], C)
+        ops.upsample2_bwd(e_cat7.cols_slice(0, C), e_y2, nb, Ls[1], C, False)
+        e_cat6 = wk.mat("unet:e_cat6", nb, Ls[1], 2 * C)
+        cb[6].bwd(e_y2, wk, e_x=e_cat6)
+        e_y3 = wk.mat("unet:e_y3", nb, Ls[2], C)
+        ops.upsample2_bwd(e_cat6.cols_slice(0, C), e_y3, nb, Ls[2], C, False)
+        e_cat5 = wk.mat("unet:e_cat5", nb, Ls[2], 2 * C)
+        cb[5].bwd(e_y3, wk, e_x=e_cat5)
+        e_x4 = wk.mat("unet:e_x4", nb, Ls[3], C)
+        ops.upsample2_bwd(e_cat5.cols_slice(0, C), e_x4, nb, Ls[3], C, False)
+        e_d3 = wk.mat("unet:e_d3", nb, Ls[3], C)
+        cb[4].bwd(e_x4, wk, e_x=e_d3)
+        # x3 receives: skip part of cat5 + maxpool backward
+        e_x3 = e_cat5.cols_slice(C, 2 * C)
+        ops.maxpool2_bwd(x3, e_d3, e_x3, nb, Ls[2], C, True)
+        e_d2 = wk.mat("unet:e_d2", nb, Ls[2], C)
+        cb[3].bwd(e_x3, wk, e_x=e_d2)
+        e_x2 = e_cat6.cols_slice(C, 2 * C)
+        ops.maxpool2_bwd(x2, e_d2, e_x2, nb, Ls[1], C, True)
+        e_d1 = wk.mat("unet:e_d1", nb, Ls[1], C)
+        cb[2].bwd(e_x2, wk, e_x=e_d1)
+        e_x1 = e_cat7.cols_slice(C, 2 * C)
+        ops.maxpool2_bwd(x1, e_d1, e_x1, nb, Ls[0], C, True)
+        e_x = wk.mat("unet:e_x", nb, Ls[0], C)
+        cb[1].bwd(e_x1, wk, e_x=e_x)
+        e = e_x
+        for i in (2, 1):
+            blk = self.stem[i]
+            e_in = wk.mat(f"unet:e_s{i}", nb, blk.conv.Lin, blk.conv.Cin)
+            blk.bwd(e, wk, e_x=e_in)
+            e = e_in
+        self.stem[0].bwd(e, wk, win=win)
+
+
+ENCODERS = {"default": DefaultEncoder, "wavegan": WaveGANEncoder, "unet": UNetEncoder}
+
+
+class GRUStack:
+    """torch.nn.GRU(I, H, n_layers, batch_first) — default.py:349-355."""
+
+    def __init__(self, P, G, name, I, H, n_layers):
+        self.name, self.I, self.H, self.n = name, I, H, n_layers
+        self.ih, self.hh = [], []
+        for l in range(n_layers):
+            Il = I if l == 0 else H
+            self.ih.append(ConvLayer(f"{name}.ih{l}", P[f"{name}.weight_ih_l{l}"], P[f"{name}.bias_ih_l{l}"],
+                                     G.get(f"{name}.weight_ih_l{l}"), G.get(f"{name}.bias_ih_l{l}"),
+                                     Il, 3 * H, need_dgrad=True))
+            self.hh.append((P[f"{name}.weight_hh_l{l}"], P[f"{name}.bias_hh_l{l}"],
+                            G.get(f"{name}.weight_hh_l{l}"), G.get(f"{name}.bias_hh_l{l}")))
+
+    def convs(self):
+        return list(self.ih)
+
+    def fwd(self, x, out, B, T, wk, save):
+        """x [1, B*T, I] rows (b,t); out: Mat [1, B*T, H] possibly a column slice."""
+        H = self.H
+        self.xs, self.hs, self.saves = [], [], []
+        for l in range(self.n):
+            gi = wk.mat(f"{self.name}:gi{l}", 1, B * T, 3 * H)
+            self.ih[l].fwd(x, gi, ws=wk.scratch)
+            h = out if l == self.n - 1 else wk.mat(f"{self.name}:h{l}", 1, B * T, H)
+            sv = wk.mat(f"{self.name}:sv{l}", 1, B * T, 4 * H) if save else None
+            w_hh, b_hh, _, _ = self.hh[l]
+            ops.gru_forward(gi, w_hh, b_hh, h, h.ld, sv, B, T, H)
+            self.xs.append(x)
+            self.hs.append(h)
+            self.saves.append(sv)
+            x = h
+
+    def bwd(self, e_out, B, T, wk, e_x=None):
+        """e_out: Mat gradient w.r.t. the top layer output; e_x: Mat for d/d(input) or None."""
+        H = self.H
+        e = e_out
+        for l in range(self.n - 1, -1, -1):
+            dgi = wk.mat(f"{self.name}:dgi{l}", 1, B * T, 3 * H)
+            dgh = wk.mat(f"{self.name}:dgh{l}", 1, B * T, 3 * H)
+            w_hh, _, gw_hh, gb_hh = self.hh[l]
+            h = self.hs[l]
+            ops.gru_backward(e, e.ld, h, h.ld, self.saves[l], w_hh, dgi, dgh, B, T, H)
+            # dW_hh = sum dgh (x) h_{t-1}: rows shifted by one step inside each sequence
+            hB = Mat(h.t, B, T, H, h.ld, T * h.ld)
+            hB.ptr = h.ptr
+            ops.wgrad(dgh.as_rows(B, T), hB, gw_hh, Cout=3 * H, T=1, Cc=H, sr=1, roff0=-1, droff=1,
+                      ws=wk.scratch)
+            ops.colsum(dgh, gb_hh, wk.acc_slot(3 * H))
+            self.ih[l].wgrad(dgi, self.xs[l], wk.scratch, acc=wk.acc_slot(3 * H))
+            if l > 0:
+                e = wk.mat(f"{self.name}:e{l}", 1, B * T, H)
+                self.ih[l].dgrad(dgi, e, ws=wk.scratch)
+            elif e_x is not None:
+                self.ih[l].dgrad(dgi, e_x, ws=wk.scratch)
+
+
+class GeneratorNet:
+    """SequenceGenerator.forward (default.py:25-42) and its backward."""
+
+    def __init__(self, P, G, cfg):
+        self.cfg = cfg
+        self.dev = next(iter(P.values())).device
+        self.enc = ENCODERS[cfg["enc_type"]](P, G, cfg)
+        self.I, self.Lat, self.Nz = cfg["input_vector_size"], cfg["latent_vector_size"], cfg["noise_size"]
+        self.H = self.Lat - self.Nz
+        self.rnn = GRUStack(P, G, "audio_rnn.rnn", self.I, self.H, cfg["n_cells"])
+        self.nrnn = GRUStack(P, G, "noise_gen.rnn", self.Nz, self.Nz, 1)
+        S, O = cfg["size"], cfg["output_size"]
+        self.S, self.O = S, O
+        self.fc1 = _conv_from(P, G, "decoder.fc1", self.Lat, S, need_dgrad=True, k=1, s=1, p=0, Lin=1)
+        self.bn1 = BNLayer("decoder.bn1", P, G)
+        self.blocks = []
+        for b in range(cfg["nblocks_gen"]):
+            q = f"decoder.blocks.{b}."
+            dead = ConvLayer(q + "fc1", P[q + "fc1.weight"], P[q + "fc1.bias"], None, None, S, S, need_dgrad=False)
+            live = _conv_from(P, G, q + "fc2", S, S, 1, 1, 0, 1)
+            self.blocks.append((dead, BNLayer(q + "bn1", P, G), live, BNLayer(q + "bn2", P, G)))
+        self.last = _conv_from(P, G, "decoder.lastfc", S, O, 1, 1, 0, 1)
+        self.wk = Workspace(self.dev)
+        self.nbt = [v for k, v in P.items() if k.endswith("num_batches_tracked")]
+
+    def convs(self):
+        c = self.enc.convs() + self.rnn.convs() + self.nrnn.convs() + [self.fc1, self.last]
+        for dead, _, live, _ in self.blocks:
+            c += [dead, live]
+        return c
+
+    def pack(self):
+        for c in self.convs():
+            c.pack()
+
+    def window(self, T):
+        cfg = self.cfg
+        pad = cfg["pad_samples"]
+        return (T, cfg["cutting_stride"], pad // 2, None, cfg["audio_feat_samples"])
+
+    def forward(self, audio, noise, B, T, train=True, out=None, slices=None):
+        """audio [B, A] raw (fused windowing) or, if `slices` [B,T,W] is given, explicit
+        windows (the drop-in module path).  noise [B,T,Nz].  Returns Mat [1,B*T,O]."""
+        wk, cfg = self.wk, self.cfg
+        wk.acc_reset()
+        nb = B * T
+        if slices is not None:
+            src, win = slices, (1, 0, 0, cfg["audio_feat_samples"], cfg["audio_feat_samples"])
+        else:
+            w = self.window(T)
+            src, win = audio, (T, w[1], w[2], audio.shape[-1], w[4])
+        self.src, self.win, self.B, self.T = src, win, B, T
+        enc_out = wk.mat("g:enc", nb, 1, self.I)
+        self.enc.fwd(src, nb, win, wk, train, enc_out)
+        z = wk.mat("g:z", 1, nb, self.Lat)
+        self.rnn.fwd(enc_out.as_rows(1, nb), z.cols_slice(0, self.H), B, T, wk, save=True)
+        nz = Mat.of(noise, 1, nb, self.Nz)
+        self.nrnn.fwd(nz, z.cols_slice(self.H, self.Lat), B, T, wk, save=True)
+        c = wk.mat("g:dec_c0", 1, nb, self.S)
+        self.fc1.fwd(z, c, ws=wk.scratch)
+        d = wk.mat("g:dec_d0", 1, nb, self.S)
+        self.bn1.fwd(c, d, ACT_RELU, train, wk)
+        self.dec = [(z, c, d)]
+        for i, (dead, bnd, live, bnl) in enumerate(self.blocks):
+            cd = wk.mat(f"g:dec_dead{i}", 1, nb, self.S)
+            dead.fwd(d, cd, ws=wk.scratch)
+            bnd.fwd(cd, None, ACT_RELU, train, wk)           # Q1: statistics only
+            cl = wk.mat(f"g:dec_c{i + 1}", 1, nb, self.S)
+            live.fwd(d, cl, ws=wk.scratch)
+            r = wk.mat(f"g:dec_r{i + 1}", 1, nb, self.S)
+            bnl.fwd(cl, r, ACT_RELU, train, wk)
+            dn = wk.mat(f"g:dec_d{i + 1}", 1, nb, self.S)
+            ops.axpby(d, r, dn, nb * self.S, 1.0, 1.0)
+            self.dec.append((d, cl, r))
+            d = dn
+        fake = out if out is not None else wk.mat("g:fake", 1, nb, self.O)
+        self.last.fwd(d, fake, ws=wk.scratch)
+        self.d_last = d
+        if train:
+            for t in self.nbt:
+                t.add_(1)
+        return fake
+
+    def backward(self, dfake):
+        """dfake: Mat [1,B*T,O].  Fills every live parameter gradient (overwrite)."""
+        wk, B, T = self.wk, self.B, self.T
+        nb = B * T
+        wk.acc_reset()
+        self.last.wgrad(dfake, self.d_last, wk.scratch, acc=wk.acc_slot(self.O))
+        e = wk.mat("g:e_d", 1, nb, self.S)
+        self.last.dgrad(dfake, e, ws=wk.scratch)
+        for i in range(len(self.blocks) - 1, -1, -1):
+            dead, bnd, live, bnl = self.blocks[i]
+            d, cl, r = self.dec[i + 1]
+            dc = wk.mat(f"g:dc{i + 1}", 1, nb, self.S)
+            bnl.bwd(e, r, cl, dc, ACT_RELU, wk)
+            live.wgrad(dc, d, wk.scratch, acc=wk.acc_slot(self.S))
+            e2 = wk.mat(f"g:e_d{i}", 1, nb, self.S)
+            live.dgrad(dc, e2, ws=wk.scratch, add=e)
+            e = e2
+        z, c, d0 = self.dec[0]
+        dc = wk.mat("g:dc0", 1, nb, self.S)
+        self.bn1.bwd(e, d0, c, dc, ACT_RELU, wk)
+        self.fc1.wgrad(dc, z, wk.scratch, acc=wk.acc_slot(self.S))
+        e_z = wk.mat("g:e_z", 1, nb, self.Lat)
+        self.fc1.dgrad(dc, e_z, ws=wk.scratch)
+        self.nrnn.bwd(e_z.cols_slice(self.H, self.Lat), B, T, wk)
+        e_enc = wk.mat("g:e_enc", 1, nb, self.I)
+        self.rnn.bwd(e_z.cols_slice(0, self.H), B, T, wk, e_x=e_enc)
+        self.enc.bwd(e_enc.as_rows(nb, 1), self.src, nb, self.win, wk)
+
+
+# ===========================================================================
+# critic
+# ===========================================================================
+
+class CriticNet:
+    """SequenceDiscriminator / AblatedSequenceDiscriminator (default.py:249-346) with the
+    passes the WGAN-GP step needs: forward, backward-data, tangent (JVP) and weight grads."""
+
+    def __init__(self, P, G, cfg):
+        self.cfg = cfg
+        self.dev = next(iter(P.values())).device
+        self.ablated = bool(cfg["ablated"])
+        O, Ch, code, T = cfg["output_size"], cfg["channels"], cfg["code_size"], cfg["stick_length"]
+        self.O, self.Ch, self.code, self.T = O, Ch, code, T
+        k0 = P["stick_d.conv1.weight"].shape[-1]
+        self.s_conv1 = _conv_from(P, G, "stick_d.conv1", O, Ch, k0, 1, (k0 - 1) // 2, T)
+        self.s_blocks = []
+        for b in range(2):
+            self.s_blocks.append((_conv_from(P, G, f"stick_d.blocks.{b}.conv1", Ch, Ch, 7, 1, 3, T),
+                                  _conv_from(P, G, f"stick_d.blocks.{b}.conv2", Ch, Ch, 7, 1, 3, T)))
+        self.s_fconv = _conv_from(P, G, "stick_d.fconv", Ch, code, P["stick_d.fconv.weight"].shape[-1], 1, 0, T)
+        assert self.s_fconv.Lout == 1, "critic sequence length is fixed by fconv (Q12)"
+        self.act = ACT_CODE[cfg["activ"]]
+        self.a_layers = []
+        if not self.ablated:
+            A = cfg["audio_length"]
+            chans = [1, 32, 64, 128, 256, 512]
+            L = A
+            for i in range(1, 6):
+                self.a_layers.append(_conv_from(P, G, f"audio_d.l{i}", chans[i - 1], chans[i], 25, 4, 11, L,
+                                                need_dgrad=True))
+                L = self.a_layers[-1].Lout
+            self.a_l6 = _conv_from(P, G, "audio_d.l6", 512, code, P["audio_d.l6.weight"].shape[-1], 1, 0, L)
+            assert self.a_l6.Lout == 1, "critic audio length is fixed by l6 (Q12)"
+        self.F = code if self.ablated else 2 * code
+        self.fc1 = _conv_from(P, G, "fc1", self.F, 128, 1, 1, 0, 1)
+        self.fc2 = _conv_from(P, G, "fc2", 128, 1, 1, 1, 0, 1)
+        self.wk = Workspace(self.dev)
+
+    def convs(self):
+        c = [self.s_conv1] + [x for blk in self.s_blocks for x in blk] + [self.s_fconv]
+        if not self.ablated:
+            c += self.a_layers + [self.a_l6]
+        return c + [self.fc1, self.fc2]
+
+    def pack(self):
+        for c in self.convs():
+            c.pack()
+
+    # ---------------------------------------------------------------- pose branch
+    def pose_fwd(self, X, n, tag):
+        """X Mat [n,T,O] channels-last; sv["code"] = activ(fconv(...)) as a dense [1,n,code]."""
+        wk, T, Ch = self.wk, self.T, self.Ch
+        code_out = wk.mat(f"{tag}:code_s", 1, n, self.code)
+        r0 = wk.mat(f"{tag}:r0", n, T, Ch)
+        self.s_conv1.fwd(X, r0, act=ACT_RELU, ws=wk.scratch)
+        sv = {"X": X, "r0": r0, "blk": []}
+        x = r0
+        for b, (c1, c2) in enumerate(self.s_blocks):
+            r1 = wk.mat(f"{tag}:b{b}r1", n, T, Ch)
+            c1.fwd(x, r1, act=ACT_RELU, ws=wk.scratch)
+            r2 = wk.mat(f"{tag}:b{b}r2", n, T, Ch)
+            y = wk.mat(f"{tag}:b{b}y", n, T, Ch)
+            c2.fwd(r1, y, act=ACT_RELU, ws=wk.scratch, add=x, y2=r2)
+            sv["blk"].append((x, r1, r2, y))
+            x = y
+        self.s_fconv.fwd(x, code_out.as_rows(n, 1), act=self.act, ws=wk.scratch)
+        sv["y"], sv["code"] = x, code_out
+        return sv
+
+    def pose_bwd(self, sv, d_code, n, tag, scale=1.0, beta=0.0, wgrads=True, dX=None, bbeta=None):
+        """d_code Mat [1,n,code] = gradient w.r.t. the pose code (post-activ; modified in
+        place when activ != id).  Produces pre-activation deltas (kept in `sv` for the GP
+        weight gradients), optional weight grads (scale/beta) and optional dX."""
+        wk, T, Ch = self.wk, self.T, self.Ch
+        if self.act != ACT_ID:
+            ops.act_bwd(d_code, sv["code"], n * self.code, self.act)
+        dl = {"fconv": d_code}
+        e = wk.mat(f"{tag}:e_top", n, T, Ch)
+        nb = len(self.s_blocks)
+        # gradient w.r.t. last block output y; masked copy = delta of its conv2
+        x_last, r1_last, r2_last, _ = sv["blk"][-1]
+        dc2 = wk.mat(f"{tag}:b{nb - 1}dc2", n, T, Ch)
+        self.s_fconv.dgrad(d_code.as_rows(n, 1), dc2, ws=wk.scratch, y2=e, mask=r2_last, mask_mode=ACT_RELU)
+        for b in range(nb - 1, -1, -1):
+            x, r1, r2, y = sv["blk"][b]
+            c1, c2 = self.s_blocks[b]
+            dc1 = wk.mat(f"{tag}:b{b}dc1", n, T, Ch)
+            c2.dgrad(dc2, dc1, ws=wk.scratch, mask=r1, mask_mode=ACT_RELU)
+            dl[f"b{b}c2"], dl[f"b{b}c1"] = dc2, dc1
+            # e_x = e + dgrad_conv1(dc1); masked by the producer of x
+            e_x = wk.mat(f"{tag}:e_b{b}", n, T, Ch)
+            if b > 0:
+                prev_r2 = sv["blk"][b - 1][2]
+                dnext = wk.mat(f"{tag}:b{b - 1}dc2", n, T, Ch)
+                c1.dgrad(dc1, dnext, ws=wk.scratch, add=e, add_before_mask=True, y2=e_x, mask=prev_r2,
+                         mask_mode=ACT_RELU)
+                dc2, e = dnext, e_x
+            else:
+                dc0 = wk.mat(f"{tag}:dc0", n, T, Ch)
+                c1.dgrad(dc1, dc0, ws=wk.scratch, add=e, add_before_mask=True, mask=sv["r0"], mask_mode=ACT_RELU)
+                dl["conv1"] = dc0
+        sv["delta"] = dl
+        if dX is not None:
+            self.s_conv1.dgrad(dl["conv1"], dX, ws=wk.scratch)
+        if wgrads:
+            self.pose_wgrads(dl, sv["X"], sv, scale, beta, bias=True, bbeta=bbeta)
+        return dl
+
+    def pose_wgrads(self, dl, X, acts, scale, beta, bias, bbeta=None):
+        """weight grads from deltas `dl` and layer inputs (X, acts['r0'], blocks, y)."""
+        wk = self.wk
+        A = lambda c: wk.acc_slot(c.Cout)
+        kw = dict(scale=scale, beta=beta, bias=bias, bbeta=bbeta)
+        self.s_conv1.wgrad(dl["conv1"], X, wk.scratch, acc=A(self.s_conv1), **kw)
+        for b, (c1, c2) in enumerate(self.s_blocks):
+            x, r1 = acts["blk"][b][0], acts["blk"][b][1]
+            c1.wgrad(dl[f"b{b}c1"], x, wk.scratch, acc=A(c1), **kw)
+            c2.wgrad(dl[f"b{b}c2"], r1, wk.scratch, acc=A(c2), **kw)
+        n = acts["y"].nb
+        self.s_fconv.wgrad(dl["fconv"].as_rows(n, 1), acts["y"], wk.scratch, acc=A(self.s_fconv), **kw)
+
+    def pose_tangent(self, sv, V, n, tag, t_code):
+        """JVP of the pose branch along V [n,T,O] with the ReLU masks of `sv` (no biases)."""
+        wk, T, Ch = self.wk, self.T, self.Ch
+        t0 = wk.mat(f"{tag}:t0", n, T, Ch)
+        self.s_conv1.fwd(V, t0, bias=False, ws=wk.scratch, mask=sv["r0"], mask_mode=ACT_RELU)
+        tv = {"X": V, "r0": t0, "blk": []}
+        x = t0
+        for b, (c1, c2) in enumerate(self.s_blocks):
+            _, r1, r2, _ = sv["blk"][b]
+            t1 = wk.mat(f"{tag}:tb{b}1", n, T, Ch)
+            c1.fwd(x, t1, bias=False, ws=wk.scratch, mask=r1, mask_mode=ACT_RELU)
+            ty = wk.mat(f"{tag}:tb{b}y", n, T, Ch)
+            c2.fwd(t1, ty, bias=False, ws=wk.scratch, mask=r2, mask_mode=ACT_RELU, add=x)
+            tv["blk"].append((x, t1, None, ty))
+            x = ty
+        m = dict(mask=sv["code"].as_rows(n, 1), mask_mode=self.act) if self.act != ACT_ID else {}
+        self.s_fconv.fwd(x, t_code.as_rows(n, 1), bias=False, ws=wk.scratch, **m)
+        tv["y"] = x
+        return tv
+
+    # ---------------------------------------------------------------- audio branch
+    def audio_fwd(self, audio, n, tag):
+        """audio: tensor [n, A] (C=1 channels-last == raw); sv["code"] dense [1,n,code]."""
+        wk = self.wk
+        code_out = wk.mat(f"{tag}:code_a", 1, n, self.code)
+        A = self.cfg["audio_length"]
+        x = audio if isinstance(audio, Mat) else Mat.of(audio, n, A, 1)
+        sv = {"X": x, "q": []}
+        for l in self.a_layers:
+            q = wk.mat(f"{tag}:q{l.name}", n, l.Lout, l.Cout)
+            l.fwd(x, q, act=ACT_RELU, ws=wk.scratch)
+            sv["q"].append(q)
+            x = q
+        self.a_l6.fwd(x, code_out.as_rows(n, 1), act=self.act, ws=wk.scratch)
+        sv["code"] = code_out
+        return sv
+
+    def audio_bwd(self, sv, d_code, n, tag, scale=1.0, beta=0.0, wgrads=True, dX=None, bbeta=None):
+        """Backward through the audio branch from d_code [1,n,code].  dX: tensor [n,A] or None."""
+        wk = self.wk
+        if self.act != ACT_ID:
+            ops.act_bwd(d_code, sv["code"], n * self.code, self.act)
+        dl = {"l6": d_code}
+        q = sv["q"]
+        d = wk.mat(f"{tag}:dq5", n, q[4].rows, q[4].cols)
+        self.a_l6.dgrad(d_code.as_rows(n, 1), d, ws=wk.scratch, mask=q[4], mask_mode=ACT_RELU)
+        dl[4] = d
+        for i in range(4, 0, -1):
+            dn = wk.mat(f"{tag}:dq{i}", n, q[i - 1].rows, q[i - 1].cols)
+            self.a_layers[i].dgrad(dl[i], dn, ws=wk.scratch, mask=q[i - 1], mask_mode=ACT_RELU)
+            dl[i - 1] = dn
+        sv["delta"] = dl
+        if dX is not None:
+            l1 = self.a_layers[0]
+            ops.conv_dgrad_c1(dl[0], l1.w, dX, nb=n, Lout=l1.Lout, Cout=l1.Cout, k=l1.k, stride=l1.s,
+                              pad=l1.p, Lin=l1.Lin)
+        if wgrads:
+            self.audio_wgrads(dl, sv["X"], sv["q"], scale, beta, bias=True, bbeta=bbeta)
+        return dl
+
+    def audio_wgrads(self, dl, X, q, scale, beta, bias, bbeta=None):
+        wk = self.wk
+        kw = dict(scale=scale, beta=beta, bias=bias, bbeta=bbeta)
+        x = X
+        for i, l in enumerate(self.a_layers):
+            l.wgrad(dl[i], x, wk.scratch, acc=wk.acc_slot(l.Cout), **kw)
+            x = q[i]
+        n = x.nb
+        self.a_l6.wgrad(dl["l6"].as_rows(n, 1), x, wk.scratch, acc=wk.acc_slot(self.a_l6.Cout), **kw)
+
+    def audio_tangent(self, sv, V, n, tag, t_code):
+        wk = self.wk
+        A = self.cfg["audio_length"]
+        x = V if isinstance(V, Mat) else Mat.of(V, n, A, 1)
+        x0 = x
+        tq = []
+        for i, l in enumerate(self.a_layers):
+            t = wk.mat(f"{tag}:t{l.name}", n, l.Lout, l.Cout)
+            l.fwd(x, t, bias=False, ws=wk.scratch, mask=sv["q"][i], mask_mode=ACT_RELU)
+            tq.append(t)
+            x = t
+        m = dict(mask=sv["code"].as_rows(n, 1), mask_mode=self.act) if self.act != ACT_ID else {}
+        self.a_l6.fwd(x, t_code.as_rows(n, 1), bias=False, ws=wk.scratch, **m)
+        return {"X": x0, "q": tq}
+
+    # ---------------------------------------------------------------- fusion MLP
+    def fusion_fwd(self, sa, n, tag):
+        """sa Mat [1,n,F] -> scores Mat [1,n,1]; keeps u = relu(fc1(sa))."""
+        wk = self.wk
+        u = wk.mat(f"{tag}:u", 1, n, 128)
+        self.fc1.fwd(sa, u, act=ACT_RELU, ws=wk.scratch)
+        d = wk.mat(f"{tag}:d", 1, n, 1)
+        self.fc2.fwd(u, d, ws=wk.scratch)
+        return u, d
+
+    def fusion_bwd(self, dd, u, n, tag):
+        """dd Mat [1,n,1] -> (dh [1,n,128] masked, dsa [1,n,F])."""
+        wk = self.wk
+        dh = wk.mat(f"{tag}:dh", 1, n, 128)
+        self.fc2.dgrad(dd, dh, ws=wk.scratch, mask=u, mask_mode=ACT_RELU)
+        dsa = wk.mat(f"{tag}:dsa", 1, n, self.F)
+        self.fc1.dgrad(dh, dsa, ws=wk.scratch)
+        return dh, dsa

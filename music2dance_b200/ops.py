@@ -1,0 +1,297 @@
+"""Thin tensor-level wrappers over the C ABI (include/m2d.h).
+
+PyTorch is plumbing here: it owns device memory and the current CUDA stream.
+Every function enqueues hand-written kernels from libm2d_b200.so on
+``torch.cuda.current_stream()``; none of them falls back to a torch op.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT, RowConvArgs, WgradArgs, call
+
+LAUNCHES = [0]          # number of C-ABI calls issued (bench.py reports it)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    if t is None:
+        return None
+    if isinstance(t, Mat):
+        return t.ptr
+    assert t.is_cuda, "music2dance_b200 kernels need CUDA tensors (no CPU fallback)"
+    return t.data_ptr()
+
+
+class Mat:
+    """Channels-last activation view: element (b, l, c) at ptr + 4*(b*bs + l*ld + c)."""
+    __slots__ = ("t", "ptr", "nb", "rows", "cols", "ld", "bs")
+
+    def __init__(self, t, nb, rows, cols, ld=None, bs=None, offset=0):
+        self.t = t
+        self.ptr = t.data_ptr() + 4 * offset
+        self.nb, self.rows, self.cols = nb, rows, cols
+        self.ld = cols if ld is None else ld
+        self.bs = rows * self.ld if bs is None else bs
+
+    @staticmethod
+    def of(t, nb, rows, cols):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        assert t.numel() == nb * rows * cols, (tuple(t.shape), nb, rows, cols)
+        return Mat(t, nb, rows, cols)
+
+    def cols_slice(self, c0, c1):
+        m = Mat(self.t, self.nb, self.rows, c1 - c0, self.ld, self.bs)
+        m.ptr = self.ptr + 4 * c0
+        return m
+
+    def batch_slice(self, b0, b1):
+        m = Mat(self.t, b1 - b0, self.rows, self.cols, self.ld, self.bs)
+        m.ptr = self.ptr + 4 * b0 * self.bs
+        return m
+
+    def flat_rows(self):
+        """(nb, rows, C) viewed as (1, nb*rows, C); needs bs == rows*ld."""
+        assert self.bs == self.rows * self.ld
+        m = Mat(self.t, 1, self.nb * self.rows, self.cols, self.ld, self.nb * self.rows * self.ld)
+        m.ptr = self.ptr
+        return m
+
+    def as_rows(self, nb, rows):
+        """Re-interpret the batch/row split of a dense matrix (bs == rows*ld)."""
+        assert self.bs == self.rows * self.ld and nb * rows == self.nb * self.rows
+        m = Mat(self.t, nb, rows, self.cols, self.ld, rows * self.ld)
+        m.ptr = self.ptr
+        return m
+
+    def flatten_cols(self):
+        """(nb, rows, C) dense -> (nb, 1, rows*C) for full-length convolutions."""
+        assert self.ld == self.cols and self.bs == self.rows * self.cols
+        m = Mat(self.t, self.nb, 1, self.rows * self.cols)
+        m.ptr = self.ptr
+        return m
+
+    @property
+    def M(self):
+        return self.nb * self.rows
+
+
+def new_mat(nb, rows, cols, device, ld=None):
+    ld = cols if ld is None else ld
+    t = torch.empty(nb * rows * ld, dtype=torch.float32, device=device)
+    return Mat(t, nb, rows, cols, ld)
+
+
+# ---------------------------------------------------------------------------
+
+def rowconv(x, w, y, *, T, Cc, N, sr=1, roff0=0, droff=1, w_ld=None, bias=None, act=0,
+            mask=None, mask_mode=0, add=None, add_before_mask=False, y2=None, ws=None, win=None):
+    """y = epi(rowconv(x, w)); see m2d_rowconv in include/m2d.h.  `win` = (T_frames,
+    stride, pad, seq_len) switches on fused audio windowing (x = raw audio)."""
+    a = RowConvArgs()
+    if win is None:
+        a.x, a.x_bs, a.x_ld, a.x_rows = x.ptr, x.bs, x.ld, x.rows
+        a.win_T = 0
+    else:
+        a.x, a.x_bs, a.x_ld, a.x_rows = _p(x), 0, 1, win[4]
+        a.win_T, a.win_stride, a.win_pad, a.win_seq_len = win[0], win[1], win[2], win[3]
+    a.nb = y.nb
+    a.w, a.w_ld = _p(w), (T * Cc if w_ld is None else w_ld)
+    a.N, a.T, a.Cc = N, T, Cc
+    a.sr, a.roff0, a.droff = sr, roff0, droff
+    a.y, a.y_bs, a.y_ld, a.y_rows = y.ptr, y.bs, y.ld, y.rows
+    a.y2 = None if y2 is None else y2.ptr
+    if y2 is not None:
+        assert (y2.bs, y2.ld) == (y.bs, y.ld)
+    a.bias = _p(bias)
+    a.act = act
+    if mask is not None:
+        a.mask, a.m_bs, a.m_ld, a.mask_mode = mask.ptr, mask.bs, mask.ld, mask_mode
+    if add is not None:
+        a.add, a.a_bs, a.a_ld, a.add_before_mask = add.ptr, add.bs, add.ld, int(add_before_mask)
+    if ws is not None:
+        a.ws, a.ws_floats = ws.data_ptr(), ws.numel()
+    LAUNCHES[0] += 1
+    call("m2d_rowconv", C.byref(a), _stream())
+
+
+def wgrad(dy, x, dw, *, Cout, T, Cc, sr=1, roff0=0, droff=1, scale=1.0, beta=0.0, ws=None, win=None):
+    a = WgradArgs()
+    a.dy, a.dy_bs, a.dy_ld, a.dy_rows = dy.ptr, dy.bs, dy.ld, dy.rows
+    a.nb = dy.nb
+    if win is None:
+        a.x, a.x_bs, a.x_ld, a.x_rows = x.ptr, x.bs, x.ld, x.rows
+        a.win_T = 0
+    else:
+        a.x, a.x_bs, a.x_ld, a.x_rows = _p(x), 0, 1, win[4]
+        a.win_T, a.win_stride, a.win_pad, a.win_seq_len = win[0], win[1], win[2], win[3]
+    a.Cout, a.T, a.Cc = Cout, T, Cc
+    a.sr, a.roff0, a.droff = sr, roff0, droff
+    a.dw = _p(dw)
+    a.scale, a.beta = scale, beta
+    a.ws, a.ws_floats = ws.data_ptr(), ws.numel()
+    LAUNCHES[0] += 2
+    call("m2d_wgrad", C.byref(a), _stream())
+
+
+def pack_conv_fwd(w, wp, Cout, Cin, k):
+    LAUNCHES[0] += 1
+    call("m2d_pack_conv_fwd", _p(w), _p(wp), Cout, Cin, k, _stream())
+
+
+def pack_conv_bwd(w, wd, Cout, Cin, k, stride):
+    LAUNCHES[0] += 1
+    call("m2d_pack_conv_bwd", _p(w), _p(wd), Cout, Cin, k, stride, _stream())
+
+
+def conv_dgrad_c1(dy, w, dx, *, nb, Lout, Cout, k, stride, pad, Lin):
+    LAUNCHES[0] += 1
+    call("m2d_conv_dgrad_c1", _p(dy), nb, Lout, Cout, _p(w), k, stride, pad, _p(dx), Lin, _stream())
+
+
+def gru_forward(gi, w_hh, b_hh, h_out, ldh, save, B, T, H):
+    LAUNCHES[0] += 1
+    call("m2d_gru_forward", _p(gi), _p(w_hh), _p(b_hh), _p(h_out), ldh, _p(save), B, T, H, _stream())
+
+
+def gru_backward(dh_out, ldd, h_out, ldh, save, w_hh, dgi, dgh, B, T, H):
+    LAUNCHES[0] += 1
+    call("m2d_gru_backward", _p(dh_out), ldd, _p(h_out), ldh, _p(save), _p(w_hh), _p(dgi), _p(dgh),
+         B, T, H, _stream())
+
+
+def colstats(x, acc):
+    LAUNCHES[0] += 1
+    call("m2d_colstats", x.ptr, x.ld, x.M, x.cols, _p(acc), _stream())
+
+
+def bn_apply(x, y, acc, gamma, beta, rm, rv, mr, act, momentum=0.1, eps=1e-5):
+    LAUNCHES[0] += 1
+    call("m2d_bn_apply", x.ptr, x.ld, None if y is None else y.ptr, 0 if y is None else y.ld, x.M, x.cols,
+         _p(acc), _p(gamma), _p(beta), _p(rm), _p(rv), momentum, eps, _p(mr), act, _stream())
+
+
+def bn_eval(x, y, gamma, beta, rm, rv, act, eps=1e-5):
+    LAUNCHES[0] += 1
+    call("m2d_bn_eval", x.ptr, x.ld, y.ptr, y.ld, x.M, x.cols, _p(gamma), _p(beta), _p(rm), _p(rv),
+         eps, act, _stream())
+
+
+def bn_bwd_reduce(dy, y, x, mr, act, acc):
+    LAUNCHES[0] += 1
+    call("m2d_bn_bwd_reduce", dy.ptr, dy.ld, y.ptr, y.ld, x.ptr, x.ld, x.M, x.cols, _p(mr), act,
+         _p(acc), _stream())
+
+
+def bn_bwd_apply(dy, y, x, dx, mr, gamma, act, acc, dgamma, dbeta):
+    LAUNCHES[0] += 1
+    call("m2d_bn_bwd_apply", dy.ptr, dy.ld, y.ptr, y.ld, x.ptr, x.ld, dx.ptr, dx.ld, x.M, x.cols,
+         _p(mr), _p(gamma), act, _p(acc), _p(dgamma), _p(dbeta), _stream())
+
+
+def colsum(x, out, acc, scale=1.0, beta=0.0):
+    LAUNCHES[0] += 2
+    call("m2d_colsum", x.ptr, x.ld, x.M, x.cols, _p(out), scale, beta, _p(acc), _stream())
+
+
+def axpby(x, z, y, n, a=1.0, b=1.0):
+    LAUNCHES[0] += 1
+    call("m2d_axpby", _p(x), _p(z), _p(y), n, a, b, _stream())
+
+
+def fill(y, n, v):
+    LAUNCHES[0] += 1
+    call("m2d_fill", _p(y), n, v, _stream())
+
+
+def scale_rows(x, s, y, nb, per):
+    LAUNCHES[0] += 1
+    call("m2d_scale_rows", _p(x), _p(s), _p(y), nb, per, _stream())
+
+
+def interp(real, fake, alpha, xi, nb, per):
+    LAUNCHES[0] += 1
+    call("m2d_interp", _p(real), _p(fake), _p(alpha), _p(xi), nb, per, _stream())
+
+
+def rows_sumsq(x, nb, per, out):
+    LAUNCHES[0] += 1
+    call("m2d_rows_sumsq", _p(x), nb, per, _p(out), _stream())
+
+
+def sum_(x, n, out):
+    LAUNCHES[0] += 1
+    call("m2d_sum", _p(x), n, _p(out), _stream())
+
+
+def gp_finalize(ss0, ss1, B, gp, k0, k1):
+    LAUNCHES[0] += 1
+    call("m2d_gp_finalize", _p(ss0), _p(ss1), B, _p(gp), _p(k0), _p(k1), _stream())
+
+
+def pose_losses(real, fake, dfake, B, T, Cn, beta, eta, accumulate, acc):
+    LAUNCHES[0] += 1
+    call("m2d_pose_losses", _p(real), _p(fake), _p(dfake), B, T, Cn, beta, eta, int(accumulate), _p(acc),
+         _stream())
+
+
+def act_bwd(d, y, n, mode):
+    LAUNCHES[0] += 1
+    call("m2d_act_bwd", _p(d), _p(y), n, mode, _stream())
+
+
+def maxpool2(x, y, nb, Lin, Cn):
+    LAUNCHES[0] += 1
+    call("m2d_maxpool2", x.ptr, x.ld, y.ptr, y.ld, nb, Lin, Cn, _stream())
+
+
+def maxpool2_bwd(x, dy, dx, nb, Lin, Cn, accumulate):
+    LAUNCHES[0] += 1
+    call("m2d_maxpool2_bwd", x.ptr, x.ld, dy.ptr, dy.ld, dx.ptr, dx.ld, nb, Lin, Cn, int(accumulate), _stream())
+
+
+def upsample2(x, y, nb, Lin, Cn):
+    LAUNCHES[0] += 1
+    call("m2d_upsample2", x.ptr, x.ld, y.ptr, y.ld, nb, Lin, Cn, _stream())
+
+
+def upsample2_bwd(dy, dx, nb, Lin, Cn, accumulate):
+    LAUNCHES[0] += 1
+    call("m2d_upsample2_bwd", dy.ptr, dy.ld, dx.ptr, dx.ld, nb, Lin, Cn, int(accumulate), _stream())
+
+
+def copy2d(x, y, accumulate=False):
+    LAUNCHES[0] += 1
+    call("m2d_copy2d", x.ptr, x.ld, y.ptr, y.ld, x.M, x.cols, int(accumulate), _stream())
+
+
+def transpose_bcl(x, y, nb, R, Cn):
+    """[b, R, C] -> [b, C, R] (dense)."""
+    LAUNCHES[0] += 1
+    call("m2d_transpose_bcl", _p(x), _p(y), nb, R, Cn, _stream())
+
+
+def wgan_scalars(sums, gp, B, n_l1, n_tv, c0, c1, mode, out):
+    LAUNCHES[0] += 1
+    call("m2d_wgan_scalars", _p(sums), _p(gp), B, n_l1, n_tv, c0, c1, mode, _p(out), _stream())
+
+
+def slice_audio(audio, out, nseq, A, nwin, W, stride, pad_left):
+    LAUNCHES[0] += 1
+    call("m2d_slice_audio", _p(audio), _p(out), nseq, A, nwin, W, stride, pad_left, _stream())
+
+
+def adam(p, g, m, v, n, step, lr, b1=0.9, b2=0.999, eps=1e-8, gscale=1.0):
+    LAUNCHES[0] += 2
+    call("m2d_adam", _p(p), _p(g), _p(m), _p(v), n, _p(step), lr, b1, b2, eps, gscale, _stream())
+
+
+def check_device(dev=0):
+    call("m2d_check_device", dev)
+    return _lib.load().m2d_version()

@@ -1,0 +1,239 @@
+"""Fused phase3 WGAN-GP train step (reference: phase3/train.py:184-243).
+
+One train step = `n_critic_steps` critic iterations (each on its own batch: generator
+forward with train-mode BatchNorm, gradient penalty, Wasserstein terms, Adam) followed by
+one generator update on the last batch (Q7).  Everything between the host->device copy of
+a batch and the scalar log runs in libm2d_b200 kernels on channels-last activations:
+
+  * audio windowing is fused into the first encoder convolution (never materialised),
+  * the critic's audio branch is evaluated once per iteration and shared by the
+    interpolated / real / fake evaluations (Q13),
+  * the gradient penalty's weight gradients come from one tangent pass + weight-gradient
+    GEMMs (wgan.py) instead of autograd's double backward,
+  * Adam is one flat kernel per network, followed by the weight re-layouts,
+  * with world_size > 1 the flat gradient buffer is all-reduced over NCCL before Adam
+    (batch data parallelism; per-replica generator BatchNorm statistics),
+  * the whole step is captured in CUDA graphs (one launch per iteration).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .ops import Mat
+from .wgan import critic_forward, gradient_penalty_pass, rows, wasserstein_backward
+
+LOG_CRITIC = ("loss_critic", "gp", "w_dist", "err_real", "err_fake")
+LOG_GEN = ("loss_gen", "l1", "tv", "err_real", "err_fake")
+
+
+class Phase3Trainer:
+    def __init__(self, gen, critic, cfg, batch_size, use_graphs=True, process_group=None):
+        dev = next(gen.parameters()).device
+        assert dev.type == "cuda", "Phase3Trainer needs the modules on a CUDA device"
+        self.dev, self.cfg, self.B = dev, cfg, batch_size
+        self.T, self.O, self.A = cfg["stick_length"], cfg["output_size"], cfg["audio_length"]
+        self.Nz, self.nc = cfg["noise_size"], int(cfg["n_critic_steps"])
+        gen.cutting_stride, gen.pad_samples = cfg["cutting_stride"], cfg["pad_samples"]
+        gen.__dict__.pop("_m2d_engine", None)
+        self.gen, self.critic = gen, critic
+        with torch.cuda.device(dev):
+            self.ge, self.de = gen._engine(), critic._engine()
+            self.G, self.D = self.ge.net, self.de.net
+            self.ge.net.pack()
+            self.de.net.pack()
+        self.ge.packed_version, self.de.packed_version = self.ge.fp.version(), self.de.fp.version()
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        B, T, O, A, Nz, nc = self.B, self.T, self.O, self.A, self.Nz, self.nc
+        f = dict(dtype=torch.float32, device=dev)
+        # staged inputs of one train step (device resident)
+        self.in_real = torch.zeros(nc, B, T, O, **f)
+        self.in_audio = torch.zeros(nc, B, A, **f)
+        self.in_noise = torch.zeros(nc, B, T, Nz, **f)
+        self.in_alpha = torch.zeros(nc, B, **f)
+        self.in_noise_g = torch.zeros(B, T, Nz, **f)
+        self.log_c = torch.zeros(nc, 8, **f)
+        self.log_g = torch.zeros(8, **f)
+        self.fake_c = torch.zeros(B * T, O, **f)       # generated poses of the last critic iteration
+        self.fake_g = torch.zeros(B * T, O, **f)       # ... of the generator update
+        nD, nG = self.de.fp.n_live_padded, self.ge.fp.n_live_padded
+        self.mD, self.vD = torch.zeros(nD, **f), torch.zeros(nD, **f)
+        self.mG, self.vG = torch.zeros(nG, **f), torch.zeros(nG, **f)
+        self.stepD = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.stepG = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.gp_buf = torch.zeros(1, **f)
+        self.k0, self.k1 = torch.zeros(B, **f), torch.zeros(B, **f)
+        self.use_graphs = use_graphs
+        self.graphs = None
+
+    # ------------------------------------------------------------------ pieces
+    def _all_reduce(self, flat):
+        if self.world > 1:
+            torch.distributed.all_reduce(flat, group=self.pg)
+
+    def _adam(self, eng, m, v, step, lr):
+        n = eng.fp.n_live_padded
+        self._all_reduce(eng.fp.grad[:n])
+        ops.adam(eng.fp.flat, eng.fp.grad, m, v, n, step, float(lr), gscale=1.0 / self.world)
+        eng.net.pack()
+
+    def critic_iteration(self, i, update=True):
+        """train.py:187-216 on staged batch i."""
+        B, T, O, D, G = self.B, self.T, self.O, self.D, self.G
+        real, audio = self.in_real[i], self.in_audio[i]
+        fake = Mat.of(self.fake_c, 1, B * T, O)
+        G.forward(audio, self.in_noise[i], B, T, train=True, out=fake)
+        wk = D.wk
+        wk.acc_reset()
+        n3 = 3 * B
+        X3 = wk.mat("c:X3", n3, T, O)
+        per = T * O
+        ops.interp(real, self.fake_c, self.in_alpha[i], X3, B, per)
+        ops.axpby(real, None, rows(X3, B, 2 * B), B * per, 1.0, 0.0)
+        ops.axpby(self.fake_c, None, rows(X3, 2 * B, n3), B * per, 1.0, 0.0)
+        fw = critic_forward(D, X3, None if D.ablated else audio, n3, B, "c", groups=3)
+        sums = wk.acc_slot(4)
+        d = fw["d"]
+        ops.sum_(rows(d, B, 2 * B), B, sums[0:1])
+        ops.sum_(rows(d, 2 * B, n3), B, sums[1:2])
+        gamma = float(self.cfg["gamma"])
+        gradient_penalty_pass(D, fw, B, "c:gp", gamma, 0.0, self.gp_buf, self.k0, self.k1)
+        wasserstein_backward(D, fw, B, 2 * B, (-1.0, 1.0), B, "c:w", beta=1.0)
+        ops.wgan_scalars(sums, self.gp_buf, B, 1, 1, gamma, 0.0, 0, self.log_c[i])
+        if update:
+            self._adam(self.de, self.mD, self.vD, self.stepD, self.cfg["lr_critic"])
+
+    def generator_update(self, update=True):
+        """train.py:222-237 on the last staged batch."""
+        B, T, O, D, G = self.B, self.T, self.O, self.D, self.G
+        i = self.nc - 1
+        real, audio = self.in_real[i], self.in_audio[i]
+        fake = Mat.of(self.fake_g, 1, B * T, O)
+        G.forward(audio, self.in_noise_g, B, T, train=True, out=fake)
+        wk = D.wk
+        wk.acc_reset()
+        n2 = 2 * B
+        X2 = wk.mat("g:X2", n2, T, O)
+        per = T * O
+        ops.axpby(real, None, rows(X2, 0, B), B * per, 1.0, 0.0)
+        ops.axpby(self.fake_g, None, rows(X2, B, n2), B * per, 1.0, 0.0)
+        fw = critic_forward(D, X2, None if D.ablated else audio, n2, B, "g", groups=2)
+        sums = wk.acc_slot(4)
+        d = fw["d"]
+        ops.sum_(rows(d, 0, B), B, sums[0:1])
+        ops.sum_(rows(d, B, n2), B, sums[1:2])
+        dfake = wk.mat("g:dfake", B, T, O)
+        wasserstein_backward(D, fw, B, B, (-1.0,), B, "g:w", beta=0.0, dX_rows=0, dX=dfake, param_grads=False)
+        beta, eta = float(self.cfg["beta"]), float(self.cfg["eta"])
+        ops.pose_losses(real, self.fake_g, dfake, B, T, O, beta, eta, True, sums[2:4])
+        ops.wgan_scalars(sums, None, B, B * T * O, B * (T - 1) * O, beta, eta, 1, self.log_g)
+        G.backward(dfake.flat_rows())
+        if update:
+            self._adam(self.ge, self.mG, self.vG, self.stepG, self.cfg["lr_gen"])
+
+    # ------------------------------------------------------------------ step
+    def _state(self):
+        ts = [self.ge.fp.flat, self.de.fp.flat, self.mD, self.vD, self.mG, self.vG, self.stepD, self.stepG]
+        ts += [b for _, b in self.gen.named_buffers()]
+        return ts
+
+    def _capture(self):
+        """Warm up once eagerly (allocates every workspace buffer), then capture the step
+        in CUDA graphs; model / optimiser state is restored afterwards."""
+        saved = [t.clone() for t in self._state()]
+        torch.cuda.synchronize(self.dev)
+        self._run_eager()
+        torch.cuda.synchronize(self.dev)
+        graphs = []
+        if self.world == 1:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._run_eager()
+            graphs.append(("all", g))
+        else:
+            # NCCL all-reduce stays outside the graphs: [grads] -> all-reduce -> [adam + repack]
+            for i in range(self.nc):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.critic_iteration(i, update=False)
+                graphs.append(("c", g))
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    ops.adam(self.de.fp.flat, self.de.fp.grad, self.mD, self.vD, self.de.fp.n_live_padded,
+                             self.stepD, float(self.cfg["lr_critic"]), gscale=1.0 / self.world)
+                    self.de.net.pack()
+                graphs.append(("cu", g))
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.generator_update(update=False)
+            graphs.append(("g", g))
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                ops.adam(self.ge.fp.flat, self.ge.fp.grad, self.mG, self.vG, self.ge.fp.n_live_padded,
+                         self.stepG, float(self.cfg["lr_gen"]), gscale=1.0 / self.world)
+                self.ge.net.pack()
+            graphs.append(("gu", g))
+        torch.cuda.synchronize(self.dev)
+        with torch.no_grad():
+            for t, s in zip(self._state(), saved):
+                t.copy_(s)
+        self.ge.net.pack()
+        self.de.net.pack()
+        torch.cuda.synchronize(self.dev)
+        self.graphs = graphs
+
+    def _run_eager(self):
+        for i in range(self.nc):
+            self.critic_iteration(i)
+        self.generator_update()
+
+    def load_batches(self, real, audio, noise, alpha, noise_g, non_blocking=True):
+        """Stage one train step's inputs (host or device tensors):
+        real (nc,B,T,23,3)|(nc,B,T,69), audio (nc,B,A), noise (nc,B,T,Nz), alpha (nc,B[,1]),
+        noise_g (B,T,Nz)."""
+        self.in_real.copy_(real.reshape(self.in_real.shape), non_blocking=non_blocking)
+        self.in_audio.copy_(audio.reshape(self.in_audio.shape), non_blocking=non_blocking)
+        self.in_noise.copy_(noise.reshape(self.in_noise.shape), non_blocking=non_blocking)
+        self.in_alpha.copy_(alpha.reshape(self.in_alpha.shape), non_blocking=non_blocking)
+        self.in_noise_g.copy_(noise_g.reshape(self.in_noise_g.shape), non_blocking=non_blocking)
+
+    def train_step(self):
+        """Run one train step on the staged inputs (asynchronous; read `logs()` to sync)."""
+        with torch.cuda.device(self.dev):
+            if not self.use_graphs:
+                self._run_eager()
+                return
+            if self.graphs is None:
+                self._capture()
+            for kind, g in self.graphs:
+                g.replay()
+                if kind == "c":
+                    self._all_reduce(self.de.fp.grad[:self.de.fp.n_live_padded])
+                elif kind == "g":
+                    self._all_reduce(self.ge.fp.grad[:self.ge.fp.n_live_padded])
+
+    def logs(self):
+        """Scalars of the last train step (device->host read; synchronises)."""
+        c = self.log_c.cpu()
+        g = self.log_g.cpu()
+        out = {"critic": [dict(zip(LOG_CRITIC, c[i, :5].tolist())) for i in range(self.nc)],
+               "gen": dict(zip(LOG_GEN, g[:5].tolist()))}
+        return out
+
+    def launches_per_step(self):
+        """Number of libm2d kernel launches one train step issues (counted, not estimated)."""
+        before = ops.LAUNCHES[0]
+        saved = [t.clone() for t in self._state()]
+        with torch.cuda.device(self.dev):
+            self._run_eager()
+            n = ops.LAUNCHES[0] - before
+            torch.cuda.synchronize(self.dev)
+            with torch.no_grad():
+                for t, s in zip(self._state(), saved):
+                    t.copy_(s)
+            self.ge.net.pack()
+            self.de.net.pack()
+        return n

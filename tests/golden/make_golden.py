@@ -36,7 +36,11 @@ def put(out, prefix, d):
     out[f"{prefix}/samples"] = d["samples"].numpy()
 
 
-def one_state(cfg, state, out):
+MARGIN = 1e-6
+N_SEEDS = 16
+
+
+def build_state(cfg, state):
     gen, critic = R.build_models(cfg, seed=0)
     if state == "perturbed":
         sg, sd = gen.state_dict(), critic.state_dict()
@@ -44,9 +48,55 @@ def one_state(cfg, state, out):
         O.perturb_params(sd)
         gen.load_state_dict(sg)
         critic.load_state_dict(sd)
+    return gen, critic
+
+
+def kink_margin(cfg, gen, critic, seed):
+    """Smallest |pre-activation| seen by the ReLUs of the critic's pose branch over the
+    four pose inputs of one critic iteration + generator update (interpolate, real, fake,
+    generator-step fake).  ReLU makes the gradients DISCONTINUOUS in the inputs: a
+    pre-activation within fp32 noise (~1e-7) of zero flips its mask between two summation
+    orders and moves every generator gradient by percents (observed: one unit at -3.4e-7
+    -> 2.7 % on decoder.lastfc.weight).  These layers have only B*128*120 units, so the
+    fixture seed is the best of N_SEEDS candidates and must keep a >= 1e-6 margin; the audio
+    branch and the generator have ~1e6 units per layer, where a flip is both unavoidable
+    and negligible."""
+    _, _, utils = R.import_reference()
+    lo = [float("inf")]
+    hooks = []
+    for name, m in critic.stick_d.named_modules():
+        if isinstance(m, torch.nn.Conv1d) and "fconv" not in name:
+            hooks.append(m.register_forward_hook(
+                lambda mod, i, o: lo.__setitem__(0, min(lo[0], float(o.detach().abs().min())))))
+    real, audio, noise, _, noise_g = O.synthetic_batch(cfg, B, seed)
+    T, Oo = cfg["stick_length"], cfg["output_size"]
+    sd = {k: v.clone() for k, v in gen.state_dict().items()}
+    with torch.no_grad():
+        sl = utils.slice_audio_batch(audio, cfg["audio_feat_samples"], cfg["cutting_stride"], cfg["pad_samples"])
+        gen.train()
+        fake = gen(sl, [T] * B, noise=noise).view(B, T, Oo).permute(0, 2, 1)
+        fake_g = gen(sl, [T] * B, noise=noise_g).view(B, T, Oo).permute(0, 2, 1)
+        rl = real.view(B, T, Oo).permute(0, 2, 1)
+        torch.manual_seed(ALPHA_SEED)
+        a = torch.rand(B, 1).view(B, 1, 1)
+        for x in (rl, fake, fake_g, a * rl + (1 - a) * fake):
+            critic.stick_d(x.contiguous())
+    gen.load_state_dict(sd)          # undo the BatchNorm running-stat updates
+    for h in hooks:
+        h.remove()
+    return lo[0]
+
+
+def one_state(cfg, state, out):
+    gen, critic = build_state(cfg, state)
+    cands = [(kink_margin(cfg, gen, critic, DATA_SEED + i), DATA_SEED + i) for i in range(N_SEEDS)]
+    m, seed = max(cands)
+    assert m > MARGIN, f"no seed with a ReLU margin above {MARGIN}: best {m:.2e}"
+    out[f"{state}/data_seed"] = np.int64(seed)
+    out[f"{state}/relu_margin"] = np.float64(m)
     for k, v in list(gen.state_dict().items()) + list(critic.state_dict().items()):
         put(out, f"{state}/init/{k}", O.tensor_digest(v))
-    real, audio, noise, _, noise_g = O.synthetic_batch(cfg, B, DATA_SEED)
+    real, audio, noise, _, noise_g = O.synthetic_batch(cfg, B, seed)
     r = R.critic_iteration(gen, critic, cfg, real, audio, noise, ALPHA_SEED, None)
     for k in ("loss_critic", "gp", "w_dist", "err_real", "err_fake"):
         out[f"{state}/critic/{k}"] = np.float64(r[k])

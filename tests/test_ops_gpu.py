@@ -1,0 +1,391 @@
+"""Kernel-level parity: every C-ABI entry point against the same operation written
+with torch fp32 on the CPU (the arithmetic the reference delegates to PyTorch).
+Tolerances: fp32 accumulation-order differences only (rtol 2e-5 of the tensor scale)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def close(a, b, tol=3e-5, what=""):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    scale = max(float(b.abs().max()), 1e-6)
+    err = float((a - b).abs().max()) / scale
+    assert err < tol, f"{what}: rel-to-max err {err:.3e}"
+
+
+def cl(x):      # (B,C,L) -> channels-last (B,L,C) contiguous on device
+    return x.permute(0, 2, 1).contiguous().to(DEV)
+
+
+def ncl(m, B, L, C):
+    return m.t.view(B, L, C).permute(0, 2, 1).cpu()
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from music2dance_b200 import ops
+    ops.check_device(0)
+    return ops
+
+
+CONV_CASES = [
+    # Cin, Cout, k, s, p, L, B
+    (32, 64, 4, 2, 1, 64, 3),
+    (32, 64, 25, 4, 11, 4800, 2),
+    (64, 128, 25, 4, 0, 193, 2),      # ragged: floor((193-25)/4)+1 = 43
+    (69, 128, 25, 1, 12, 120, 3),
+    (128, 128, 7, 1, 3, 120, 2),
+    (128, 128, 3, 1, 1, 50, 2),
+    (256, 96, 3, 1, 1, 25, 2),
+    (12, 20, 5, 3, 2, 37, 2),         # nothing aligned
+    (1, 32, 25, 4, 11, 7680, 2),
+    (1, 32, 250, 50, 124, 3200, 3),
+    (1, 32, 160, 4, 79, 3200, 2),
+    (1, 32, 25, 4, 0, 3200, 2),
+]
+
+
+def make_layer(Cin, Cout, k, s, p, L, need_dgrad=True, seed=0):
+    from music2dance_b200.nets import ConvLayer
+    g = torch.Generator().manual_seed(seed)
+    w = (torch.randn(Cout, Cin, k, generator=g) / (Cin * k) ** 0.5)
+    b = torch.randn(Cout, generator=g) * 0.1
+    wd, bd = w.to(DEV), b.to(DEV)
+    gw, gb = torch.zeros_like(wd), torch.zeros_like(bd)
+    lay = ConvLayer("t", wd, bd, gw, gb, Cin, Cout, k, s, p, L, need_dgrad=need_dgrad and Cin > 1)
+    lay.pack()
+    return lay, w, b
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd_dgrad_wgrad(lib, case):
+    from music2dance_b200.ops import Mat
+    Cin, Cout, k, s, p, L, B = case
+    lay, w, b = make_layer(*case[:6])
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, Cin, L, generator=g)
+    xr = x.clone().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y_ref = F.relu(F.conv1d(xr, wr, br, stride=s, padding=p))
+    Lout = y_ref.shape[-1]
+    assert Lout == lay.Lout
+    dy = torch.randn(B, Cout, Lout, generator=g)
+    y_ref.backward(dy)
+    scratch = torch.empty(1 << 22, device=DEV)
+    acc = torch.zeros(4096, dtype=torch.float64, device=DEV)
+    X = Mat.of(cl(x), B, L, Cin)
+    Y = Mat.of(torch.empty(B, Lout, Cout, device=DEV), B, Lout, Cout)
+    lay.fwd(X, Y, act=1, ws=scratch)
+    close(ncl(Y, B, Lout, Cout), y_ref, what="fwd")
+    # delta w.r.t. the pre-activation = dy * relu'(y)
+    d = cl(dy * (y_ref > 0).float())
+    D = Mat.of(d, B, Lout, Cout)
+    lay.wgrad(D, X, scratch, acc=acc[:Cout])
+    close(lay.gw, wr.grad, what="wgrad")
+    close(lay.gb, br.grad, what="bgrad")
+    # accumulate form: beta=1, scale=0.5
+    lay.wgrad(D, X, scratch, scale=0.5, beta=1.0, acc=acc[:Cout])
+    close(lay.gw, 1.5 * wr.grad, what="wgrad-acc")
+    if Cin > 1:
+        DX = Mat.of(torch.empty(B, L, Cin, device=DEV), B, L, Cin)
+        lay.dgrad(D, DX, ws=scratch)
+        close(ncl(DX, B, L, Cin), xr.grad, what="dgrad")
+    else:
+        dx = torch.empty(B, L, device=DEV)
+        lib.conv_dgrad_c1(d, lay.w, dx, nb=B, Lout=Lout, Cout=Cout, k=k, stride=s, pad=p, Lin=L)
+        close(dx.cpu(), xr.grad[:, 0], what="dgrad_c1")
+
+
+def test_conv_epilogue_mask_add_y2(lib):
+    from music2dance_b200.ops import Mat
+    Cin, Cout, k, s, p, L, B = 128, 128, 7, 1, 3, 120, 2
+    lay, w, b = make_layer(Cin, Cout, k, s, p, L)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(B, Cin, L, generator=g)
+    res = torch.randn(B, Cout, L, generator=g)
+    msk = torch.randn(B, Cout, L, generator=g)
+    X = Mat.of(cl(x), B, L, Cin)
+    R = Mat.of(cl(res), B, L, Cout)
+    Mk = Mat.of(cl(msk), B, L, Cout)
+    Y = Mat.of(torch.empty(B, L, Cout, device=DEV), B, L, Cout)
+    Y2 = Mat.of(torch.empty(B, L, Cout, device=DEV), B, L, Cout)
+    conv = F.conv1d(x, w, b, padding=p)
+    # forward residual form: y2 = relu(conv), y = res + relu(conv)
+    lay.fwd(X, Y, act=1, add=R, y2=Y2)
+    close(ncl(Y2, B, L, Cout), F.relu(conv), what="y2")
+    close(ncl(Y, B, L, Cout), res + F.relu(conv), what="residual")
+    # tangent form: no bias, mask by relu'(msk), then add
+    lay.fwd(X, Y, bias=False, mask=Mk, mask_mode=1, add=R)
+    close(ncl(Y, B, L, Cout), F.conv1d(x, w, None, padding=p) * (msk > 0) + res, what="tangent")
+    # backward form: add before mask, y2 = unmasked sum
+    lay.fwd(X, Y, bias=False, mask=Mk, mask_mode=1, add=R, add_before_mask=True, y2=Y2)
+    full = F.conv1d(x, w, None, padding=p) + res
+    close(ncl(Y2, B, L, Cout), full, what="y2-before-mask")
+    close(ncl(Y, B, L, Cout), full * (msk > 0), what="masked")
+    # tanh derivative mask
+    th = torch.tanh(msk)
+    lay.fwd(X, Y, bias=False, mask=Mat.of(cl(th), B, L, Cout), mask_mode=3)
+    close(ncl(Y, B, L, Cout), F.conv1d(x, w, None, padding=p) * (1 - th * th), what="tanh-mask")
+
+
+@pytest.mark.parametrize("case", [(128, 100, 120, 3), (512, 100, 75, 2), (1024, 250, 2, 5), (256, 250, 5, 4)])
+def test_full_length_conv(lib, case):
+    """Conv1d whose kernel spans the whole input (fconv, l6, encoder heads): forward in
+    conv form with split-K, backward-data in linear form."""
+    from music2dance_b200.ops import Mat
+    Cin, Cout, L, B = case
+    lay, w, b = make_layer(Cin, Cout, L, 1, 0, L)
+    assert lay.full
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, Cin, L, generator=g)
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    y_ref = F.conv1d(xr, wr, b)
+    dy = torch.randn(B, Cout, 1, generator=g)
+    y_ref.backward(dy)
+    scratch = torch.empty(1 << 23, device=DEV)
+    acc = torch.zeros(4096, dtype=torch.float64, device=DEV)
+    X = Mat.of(cl(x), B, L, Cin)
+    Y = Mat.of(torch.empty(B, Cout, device=DEV), B, 1, Cout)
+    lay.fwd(X, Y, ws=scratch)
+    close(Y.t.view(B, Cout).cpu(), y_ref[:, :, 0], what="fwd")
+    D = Mat.of(dy[:, :, 0].contiguous().to(DEV), B, 1, Cout)
+    DX = Mat.of(torch.empty(B, L, Cin, device=DEV), B, L, Cin)
+    msk = torch.randn(B, Cin, L, generator=g)
+    lay.dgrad(D, DX, ws=scratch, mask=Mat.of(cl(msk), B, L, Cin), mask_mode=1)
+    close(ncl(DX, B, L, Cin), xr.grad * (msk > 0), what="dgrad")
+    lay.wgrad(D, X, scratch, acc=acc[:Cout])
+    close(lay.gw, wr.grad, what="wgrad")
+
+
+def test_linear_unaligned(lib):
+    from music2dance_b200.ops import Mat
+    from music2dance_b200.nets import ConvLayer
+    g = torch.Generator().manual_seed(4)
+    M, I, O = 240, 250, 720
+    w, b = torch.randn(O, I, generator=g) / I ** 0.5, torch.randn(O, generator=g)
+    x = torch.randn(M, I, generator=g)
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    y = F.linear(xr, wr, b)
+    dy = torch.randn(M, O, generator=g)
+    y.backward(dy)
+    wd, bd = w.to(DEV), b.to(DEV)
+    lay = ConvLayer("l", wd, bd, torch.zeros_like(wd), torch.zeros_like(bd), I, O)
+    lay.pack()
+    scratch = torch.empty(1 << 22, device=DEV)
+    acc = torch.zeros(4096, dtype=torch.float64, device=DEV)
+    # input lives in a wider buffer (row stride 256) to exercise ld != cols
+    buf = torch.zeros(M, 256, device=DEV)
+    buf[:, :I] = x.to(DEV)
+    X = Mat(buf, 1, M, I, 256)
+    Y = Mat.of(torch.empty(M, O, device=DEV), 1, M, O)
+    lay.fwd(X, Y, ws=scratch)
+    close(Y.t.view(M, O), y, what="linear fwd")
+    D = Mat.of(dy.to(DEV), 1, M, O)
+    DX = Mat.of(torch.empty(M, I, device=DEV), 1, M, I)
+    lay.dgrad(D, DX, ws=scratch)
+    close(DX.t.view(M, I), xr.grad, what="linear dgrad")
+    lay.wgrad(D, X, scratch, acc=acc[:O])
+    close(lay.gw, wr.grad, what="linear wgrad")
+    close(lay.gb, dy.sum(0), what="linear bgrad")
+
+
+def test_windowed_first_conv(lib):
+    """slice_audio_batch fused into the first encoder conv == conv over explicit windows."""
+    from music2dance_b200.ops import Mat
+    import sys, os
+    from oracle import phase3_oracle as O
+    B, A, W, stride = 2, 76800, 3200, 640
+    g = torch.Generator().manual_seed(5)
+    audio = torch.rand(B, A, generator=g) - 0.5
+    sl = O.slice_audio_batch(audio, W, stride, W - stride)
+    T = sl.shape[1]
+    lay, w, b = make_layer(1, 32, 250, 50, 124, W, need_dgrad=False)
+    wr = w.clone().requires_grad_(True)
+    y_ref = F.conv1d(sl.reshape(B * T, 1, W), wr, b, stride=50, padding=124)
+    Lout = y_ref.shape[-1]
+    Y = Mat.of(torch.empty(B * T, Lout, 32, device=DEV), B * T, Lout, 32)
+    win = (T, stride, (W - stride) // 2, A, W)
+    lay.fwd(audio.to(DEV), Y, win=win)
+    close(ncl(Y, B * T, Lout, 32), y_ref, what="windowed fwd")
+    dy = torch.randn(B * T, 32, Lout, generator=g)
+    y_ref.backward(dy)
+    scratch = torch.empty(1 << 22, device=DEV)
+    acc = torch.zeros(64, dtype=torch.float64, device=DEV)
+    lay.wgrad(Mat.of(cl(dy), B * T, Lout, 32), audio.to(DEV), scratch, win=win, acc=acc[:32])
+    close(lay.gw, wr.grad, what="windowed wgrad")
+
+
+def test_slice_audio_bit_exact(lib):
+    from oracle import phase3_oracle as O
+    g = torch.Generator().manual_seed(6)
+    for (n, W, stride) in [(76800, 3200, 640), (6400, 3200, 640), (5000, 700, 160), (3200, 3200, 640)]:
+        a = torch.rand(3, n, generator=g)
+        ref = O.slice_audio_batch(a, W, stride, W - stride)
+        out = torch.empty(ref.shape, device=DEV)
+        lib.slice_audio(a.to(DEV), out, 3, n, ref.shape[1], W, stride, (W - stride) // 2)
+        assert torch.equal(out.cpu(), ref)
+
+
+@pytest.mark.parametrize("case", [(7, 120, 250, 240, 3), (3, 17, 10, 10, 1), (9, 30, 100, 150, 2), (2, 5, 50, 50, 1)])
+def test_gru(lib, case):
+    from music2dance_b200.nets import GRUStack, Workspace
+    from music2dance_b200.ops import Mat
+    B, T, I, H, nl = case
+    torch.manual_seed(7)
+    ref = torch.nn.GRU(I, H, nl, batch_first=True)
+    for p in ref.parameters():
+        torch.nn.init.normal_(p, 0, 0.15)
+    x = torch.randn(B, T, I)
+    xr = x.clone().requires_grad_(True)
+    y = ref(xr)[0]
+    dy = torch.randn(B, T, H)
+    y.backward(dy)
+    P = {"g." + k: v.detach().to(DEV).contiguous() for k, v in ref.named_parameters()}
+    G = {k: torch.zeros_like(v) for k, v in P.items()}
+    st = GRUStack(P, G, "g", I, H, nl)
+    for c in st.convs():
+        c.pack()
+    wk = Workspace(DEV, 1 << 22)
+    out = wk.mat("out", 1, B * T, H + 6, None).cols_slice(3, 3 + H)     # strided output slice
+    st.fwd(Mat.of(x.to(DEV).view(B * T, I), 1, B * T, I), out, B, T, wk, save=True)
+    got = out.t.view(B * T, H + 6)[:, 3:3 + H].view(B, T, H)
+    close(got, y, tol=2e-5, what="gru fwd")
+    e = wk.mat("e", 1, B * T, H + 6).cols_slice(3, 3 + H)
+    e.t.view(B * T, H + 6)[:, 3:3 + H] = dy.view(B * T, H).to(DEV)
+    ex = wk.mat("ex", 1, B * T, I)
+    wk.acc_reset()
+    st.bwd(e, B, T, wk, e_x=ex)
+    close(ex.t.view(B, T, I), xr.grad, tol=5e-5, what="gru dx")
+    for k, v in ref.named_parameters():
+        close(G["g." + k], v.grad, tol=5e-5, what="gru " + k)
+
+
+@pytest.mark.parametrize("act", [1, 2])
+@pytest.mark.parametrize("case", [(53760, 32), (1680, 1024), (840, 256), (77, 250)])
+def test_batchnorm(lib, case, act):
+    from music2dance_b200.nets import BNLayer, Workspace
+    from music2dance_b200.ops import Mat
+    M, C = case
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(M, C, generator=g) * 2 + 3          # mean >> 0: exercises the variance path
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    rm, rv = torch.randn(C, generator=g), torch.rand(C, generator=g) + 0.5
+    xr, gr, br = x.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm2, rv2 = rm.clone(), rv.clone()
+    f = F.relu if act == 1 else (lambda t: F.leaky_relu(t, 0.2))
+    y = f(F.batch_norm(xr, rm2, rv2, gr, br, True, 0.1, 1e-5))
+    dy = torch.randn(M, C, generator=g)
+    y.backward(dy)
+    P = {"bn.weight": gamma.to(DEV), "bn.bias": beta.to(DEV), "bn.running_mean": rm.to(DEV),
+         "bn.running_var": rv.to(DEV), "bn.num_batches_tracked": torch.zeros((), dtype=torch.long, device=DEV)}
+    G = {"bn.weight": torch.zeros(C, device=DEV), "bn.bias": torch.zeros(C, device=DEV)}
+    bn = BNLayer("bn", P, G)
+    wk = Workspace(DEV, 1 << 10)
+    wk.acc_reset()
+    X = Mat.of(x.to(DEV), 1, M, C)
+    Y = wk.mat("y", 1, M, C)
+    bn.fwd(X, Y, act, True, wk)
+    close(Y.t.view(M, C), y, what="bn fwd")
+    close(P["bn.running_mean"], rm2, what="running_mean")
+    close(P["bn.running_var"], rv2, what="running_var")
+    DX = wk.mat("dx", 1, M, C)
+    bn.bwd(Mat.of(dy.to(DEV), 1, M, C), Y, X, DX, act, wk)
+    close(DX.t.view(M, C), xr.grad, tol=1e-4, what="bn dx")
+    close(G["bn.weight"], gr.grad, tol=1e-4, what="bn dgamma")
+    close(G["bn.bias"], br.grad, tol=1e-4, what="bn dbeta")
+    # eval mode
+    bn.fwd(X, Y, act, False, wk)
+    close(Y.t.view(M, C), f(F.batch_norm(x, rm2, rv2, gamma, beta, False, 0.1, 1e-5)), what="bn eval")
+
+
+def test_pool_upsample(lib):
+    from music2dance_b200.ops import Mat
+    g = torch.Generator().manual_seed(9)
+    B, L, C = 3, 50, 128
+    x = torch.randn(B, C, L, generator=g)
+    x[:, :, 4] = x[:, :, 5]                         # ties
+    xr = x.clone().requires_grad_(True)
+    y = F.max_pool1d(xr, 2, 2)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    X = Mat.of(cl(x), B, L, C)
+    Y = Mat.of(torch.empty(B, L // 2, C, device=DEV), B, L // 2, C)
+    lib.maxpool2(X, Y, B, L, C)
+    close(ncl(Y, B, L // 2, C), y, what="maxpool")
+    DX = Mat.of(torch.ones(B, L, C, device=DEV), B, L, C)
+    lib.maxpool2_bwd(X, Mat.of(cl(dy), B, L // 2, C), DX, B, L, C, True)
+    close(ncl(DX, B, L, C), xr.grad + 1, what="maxpool bwd (accumulate)")
+    xr.grad = None
+    u = F.interpolate(xr, scale_factor=2, mode="linear", align_corners=False)
+    du = torch.randn(u.shape, generator=g)
+    u.backward(du)
+    # write into the left half of a concat buffer
+    cat = torch.zeros(B, 2 * L, 2 * C, device=DEV)
+    U = Mat(cat, B, 2 * L, C, 2 * C)
+    lib.upsample2(X, U, B, L, C)
+    close(cat[:, :, :C].permute(0, 2, 1), u, what="upsample")
+    DU = Mat.of(cl(du), B, 2 * L, C)
+    lib.upsample2_bwd(DU, DX, B, L, C, False)
+    close(ncl(DX, B, L, C), xr.grad, what="upsample bwd")
+
+
+def test_elementwise_and_losses(lib):
+    g = torch.Generator().manual_seed(10)
+    B, T, C = 5, 120, 69
+    real, fake = torch.rand(B, T, C, generator=g), torch.randn(B, T, C, generator=g)
+    alpha = torch.rand(B, generator=g)
+    xi = torch.empty(B, T, C, device=DEV)
+    lib.interp(real.to(DEV), fake.to(DEV), alpha.to(DEV), xi, B, T * C)
+    a = alpha.view(B, 1, 1)
+    close(xi, a * real + (1 - a) * fake, tol=1e-6, what="interp")
+    ss = torch.zeros(B, dtype=torch.float64, device=DEV)
+    lib.rows_sumsq(fake.to(DEV), B, T * C, ss)
+    close(ss, (fake.double() ** 2).sum((1, 2)), tol=1e-6, what="sumsq")
+    ss1 = (torch.rand(B, generator=g).double() * 1e-3).to(DEV)
+    gp, k0, k1 = torch.zeros(1, device=DEV), torch.zeros(B, device=DEV), torch.zeros(B, device=DEV)
+    lib.gp_finalize(ss, ss1, B, gp, k0, k1)
+    n0, n1 = torch.sqrt(ss.cpu().float() + 1e-12), torch.sqrt(ss1.cpu().float() + 1e-12)
+    close(gp, (((n0 - 1) ** 2).mean() + ((n1 - 1) ** 2).mean()).view(1), tol=1e-6, what="gp")
+    close(k0, 2 / B * (n0 - 1) / n0, tol=1e-6, what="kappa0")
+    close(k1, 2 / B * (n1 - 1) / n1, tol=1e-5, what="kappa1")
+    # pose losses and their gradient
+    fr = fake.clone().requires_grad_(True)
+    fb = fr.permute(0, 2, 1)
+    l1 = (real.permute(0, 2, 1) - fb).abs().mean()
+    tv = (fb[:, :, 1:] - fb[:, :, :-1]).abs().mean()
+    (1.5 * l1 + 0.7 * tv).backward()
+    acc = torch.zeros(2, dtype=torch.float64, device=DEV)
+    df = torch.ones(B, T, C, device=DEV)
+    lib.pose_losses(real.to(DEV), fake.to(DEV), df, B, T, C, 1.5, 0.7, True, acc)
+    close(acc[0:1] / (B * T * C), l1.view(1), tol=1e-6, what="l1")
+    close(acc[1:2] / (B * (T - 1) * C), tv.view(1), tol=1e-6, what="tv")
+    close(df, fr.grad + 1, tol=1e-6, what="dfake")
+    # transpose
+    x = torch.randn(B, C, T, generator=g)
+    y = torch.empty(B, T, C, device=DEV)
+    lib.transpose_bcl(x.to(DEV), y, B, C, T)
+    assert torch.equal(y.cpu(), x.permute(0, 2, 1).contiguous())
+
+
+def test_adam_matches_torch(lib):
+    g = torch.Generator().manual_seed(11)
+    n = 100003
+    p0 = torch.randn(n, generator=g)
+    pt = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pt], lr=2e-4)
+    p = p0.to(DEV)
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    step = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for it in range(5):
+        gr = torch.randn(n, generator=g) * (10.0 ** (it - 2))
+        pt.grad = gr.clone()
+        opt.step()
+        lib.adam(p, (gr * 4).to(DEV), m, v, n, step, 2e-4, gscale=0.25)
+        close(p, pt, tol=1e-6, what=f"adam step {it}")
+    assert int(step.item()) == 5

@@ -1,0 +1,242 @@
+"""GPU parity proper: the CUDA path, called through the drop-in API (archis.default /
+losses / utils — the reference-facing boundary over the C ABI), against
+  (1) golden fixtures produced by the UNMODIFIED reference modules, and
+  (2) the CPU oracle evaluated in-test on the same seeded inputs.
+Tolerances are written next to each check (tests/parity.py)."""
+import copy
+
+import pytest
+import torch
+
+from oracle import phase3_oracle as O
+from tests.parity import (ALPHA_SEED, B_GOLD, TOL_FP32, TOL_GEN_GRAD_E2E, TOL_GRAD, TOL_NORTH_STAR, VARIANTS,
+                          digest_check, load_golden, scalar_check)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def build(cfg, state="init"):
+    from music2dance_b200.archis.default import (AblatedSequenceDiscriminator, SequenceDiscriminator,
+                                                 SequenceGenerator)
+    torch.manual_seed(0)                                         # phase3/train.py:35
+    gen = SequenceGenerator(cfg["audio_feat_samples"], cfg["input_vector_size"], cfg["latent_vector_size"],
+                            cfg["size"], cfg["output_size"], cfg["noise_size"], cfg["nblocks_gen"],
+                            cfg["n_cells"], cfg["enc_type"], cfg["activ"], DEV)
+    cls = AblatedSequenceDiscriminator if cfg["ablated"] else SequenceDiscriminator
+    critic = cls(cfg["output_size"], cfg["channels"], cfg["code_size"], cfg["stick_length"],
+                 init_ker=cfg["init_kernel"], activ=cfg["activ"], device=DEV)
+    if state == "perturbed":
+        for m in (gen, critic):
+            sd = {k: v.cpu() for k, v in m.state_dict().items()}
+            O.perturb_params(sd)
+            m.load_state_dict(sd, strict=True)
+    return gen, critic
+
+
+def oracle_params(module):
+    return {k: v.detach().cpu().clone() for k, v in module.state_dict().items()}
+
+
+@pytest.mark.parametrize("state", ["init", "perturbed"])
+@pytest.mark.parametrize("variant", ["default", "wavegan", "unet", "ablated"])
+def test_dropin_step_vs_reference_fixtures(variant, state):
+    """phase3/train.py:187-237 written with the drop-in API, compared with what the
+    reference modules produced for the same seeds (fixtures)."""
+    from music2dance_b200.losses import gradient_penalty, tv_loss
+    from music2dance_b200.utils import slice_audio_batch
+    cfg = O.make_cfg(**VARIANTS[variant])
+    gold = load_golden(variant)
+    gen, critic = build(cfg, state)
+    for m in (gen, critic):                                      # a15 + Appendix A: same keys, same init
+        for k, v in m.state_dict().items():
+            digest_check(v, gold, f"{state}/init/{k}", 1e-7, f"init {k}")
+    B, T, Oo = B_GOLD, cfg["stick_length"], cfg["output_size"]
+    real_bt, audio, noise, _, noise_g = O.synthetic_batch(cfg, B, int(gold[f"{state}/data_seed"]))
+    gen.train()
+    critic.zero_grad()
+    slices = slice_audio_batch(audio, cfg["audio_feat_samples"], cfg["cutting_stride"], cfg["pad_samples"])
+    assert torch.equal(slices.cpu(), O.slice_audio_batch(audio, cfg["audio_feat_samples"],
+                                                         cfg["cutting_stride"], cfg["pad_samples"]))
+    real = real_bt.to(DEV).view(B, T, Oo).permute(0, 2, 1).contiguous()
+    aud = audio.to(DEV).unsqueeze(1)
+    fake = gen(slices, [T] * B, noise=noise.to(DEV)).view(B, T, Oo).permute(0, 2, 1).contiguous()
+    ref_fake = torch.from_numpy(gold[f"{state}/critic/fake"])
+    assert float((fake.detach().cpu() - ref_fake).abs().max()) < TOL_FP32 * float(ref_fake.abs().max())
+    torch.manual_seed(ALPHA_SEED)
+    if cfg["ablated"]:
+        gp = gradient_penalty(critic, B, real, fake, is_seq=True, lp=False, device=DEV)
+        err_real, err_fake = critic(real).mean(), critic(fake.detach()).mean()
+    else:
+        gp = gradient_penalty(critic, B, real, fake, aud, is_seq=True, lp=False, device=DEV)
+        err_real, err_fake = critic(real, aud).mean(), critic(fake.detach(), aud).mean()
+    err = err_fake - err_real + cfg["gamma"] * gp
+    err.backward()
+    # north-star tolerance: 1e-3 relative on losses and gradient-penalty terms; fp32 path held tighter
+    scalar_check(gp, gold[f"{state}/critic/gp"], TOL_FP32, "gp")
+    scalar_check(err, gold[f"{state}/critic/loss_critic"], TOL_FP32, "loss_critic")
+    scalar_check(err_fake - err_real, gold[f"{state}/critic/w_dist"], TOL_FP32, "w_dist")
+    for k, p in critic.named_parameters():
+        assert p.grad is not None or k == "fc2.bias", k
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        digest_check(g, gold, f"{state}/critic/grad/{k}", TOL_GRAD, f"critic grad {k}", abs_floor=1e-4)
+    for k, v in gen.state_dict().items():                       # Q2: running stats advanced by the forward
+        if "running" in k or "num_batches" in k:
+            digest_check(v, gold, f"{state}/critic/genbuf/{k}", TOL_FP32, f"bn buffer {k}")
+    # generator update (train.py:222-237); `fake` stays a permuted view (Q8)
+    gen.zero_grad()
+    fake = gen(slices, [T] * B, noise=noise_g.to(DEV)).view(B, T, Oo).permute(0, 2, 1)
+    l1 = torch.nn.L1Loss(reduction="mean")(real, fake)
+    if cfg["ablated"]:
+        err_real, err_fake = critic(real).mean(), critic(fake).mean()
+    else:
+        err_real, err_fake = critic(real, aud).mean(), critic(fake, aud).mean()
+    tv = tv_loss(fake)
+    err_g = err_real - err_fake + cfg["beta"] * l1 + cfg["eta"] * tv
+    err_g.backward()
+    scalar_check(err_g, gold[f"{state}/gen/loss_gen"], TOL_FP32, "loss_gen")
+    scalar_check(l1, gold[f"{state}/gen/l1"], TOL_FP32, "l1")
+    scalar_check(tv, gold[f"{state}/gen/tv"], TOL_FP32, "tv")
+    skip = set(O.pre_bn_bias_names(dict(gen.state_dict())))
+    for k, p in gen.named_parameters():
+        if f"{state}/gen/nograd/{k}" in gold.files:              # Q1: dead branch never gets a gradient
+            assert p.grad is None, k
+        elif k not in skip:
+            digest_check(p.grad, gold, f"{state}/gen/grad/{k}", TOL_GEN_GRAD_E2E, f"gen grad {k}", abs_floor=1e-4)
+
+
+@pytest.mark.parametrize("variant", ["default", "wavegan", "unet"])
+def test_generator_backward_smooth(variant):
+    """Generator forward/backward against oracle autograd with a SMOOTH upstream gradient
+    (no L1 sign, no critic ReLU kinks): every parameter gradient within TOL_GRAD."""
+    cfg = O.make_cfg(**VARIANTS[variant])
+    gen, _ = build(cfg, "perturbed")
+    B, T = 3, 120
+    g = torch.Generator().manual_seed(21)
+    audio = (torch.rand(B, cfg["audio_length"], generator=g) - 0.5) * 0.6
+    noise = torch.randn(B, T, cfg["noise_size"], generator=g)
+    up = torch.randn(B * T, cfg["output_size"], generator=g)
+    P = O._leaf(oracle_params(gen))
+    sl = O.slice_audio_batch(audio, cfg["audio_feat_samples"], cfg["cutting_stride"], cfg["pad_samples"])
+    out_ref = O.generator_forward(P, cfg, sl, noise, train=True)
+    names = O.trainable_names(P)
+    gl = torch.autograd.grad((out_ref * up).sum(), [P[k] for k in names], allow_unused=True)
+    from music2dance_b200.utils import slice_audio_batch
+    gen.train()
+    out = gen(slice_audio_batch(audio.to(DEV), cfg["audio_feat_samples"], cfg["cutting_stride"],
+                                cfg["pad_samples"]), [T] * B, noise=noise.to(DEV))
+    err = float((out.detach().cpu() - out_ref.detach()).abs().max() / out_ref.abs().max())
+    assert err < TOL_FP32, f"generator output rel err {err:.3e}"
+    (out * up.to(DEV)).sum().backward()
+    skip = set(O.pre_bn_bias_names(P))
+    got = dict(gen.named_parameters())
+    for k, gr in zip(names, gl):
+        if gr is None:
+            assert got[k].grad is None, k
+            continue
+        if k in skip:
+            continue
+        e = float((got[k].grad.cpu() - gr).abs().max() / max(float(gr.abs().max()), 1e-4))
+        assert e < TOL_GRAD, f"{variant} {k}: {e:.3e}"
+    # eval mode (running statistics) — train.py:245-261
+    gen.eval()
+    with torch.no_grad():
+        out_e = gen(slice_audio_batch(audio.to(DEV), cfg["audio_feat_samples"], cfg["cutting_stride"],
+                                      cfg["pad_samples"]), [T] * B, noise=noise.to(DEV))
+    Pe = oracle_params(gen)
+    ref_e = O.generator_forward(Pe, cfg, sl, noise, train=False)
+    err = float((out_e.cpu() - ref_e).abs().max() / ref_e.abs().max())
+    assert err < TOL_FP32, f"eval-mode generator output rel err {err:.3e}"
+
+
+def test_generator_long_sequence():
+    """Generator is length-agnostic (phase3/test.py:49: 30 s = 750 frames)."""
+    cfg = O.make_cfg()
+    gen, _ = build(cfg)
+    T = 750
+    g = torch.Generator().manual_seed(22)
+    audio = (torch.rand(1, T * 640, generator=g) - 0.5) * 0.6
+    noise = torch.randn(1, T, cfg["noise_size"], generator=g)
+    from music2dance_b200.utils import slice_audio_batch
+    sl = O.slice_audio_batch(audio, 3200, 640, 2560)
+    assert sl.shape[1] == T
+    gen.eval()
+    with torch.no_grad():
+        out = gen(slice_audio_batch(audio.to(DEV), 3200, 640, 2560), [T], noise=noise.to(DEV))
+    ref = O.generator_forward(oracle_params(gen), cfg, sl, noise, train=False)
+    assert float((out.cpu() - ref).abs().max() / ref.abs().max()) < TOL_FP32
+
+
+@pytest.mark.parametrize("variant,B,nc", [("default", 2, 2), ("default", 7, 3), ("wavegan", 3, 2), ("ablated", 4, 2)])
+@pytest.mark.parametrize("graphs", [False, True])
+def test_fused_trainer_vs_oracle(variant, B, nc, graphs):
+    """Phase3Trainer (fused step, Adam included, optionally CUDA-graph replayed) against the
+    oracle's train_step on the same staged batches.  Losses are continuous in the weights, so
+    they are held to the north-star 1e-3 through `nc` chained Adam updates."""
+    from music2dance_b200.trainer import Phase3Trainer
+    cfg = O.make_cfg(n_critic_steps=nc, **VARIANTS[variant])
+    gen, critic = build(cfg)
+    G, D = oracle_params(gen), oracle_params(critic)
+    tr = Phase3Trainer(gen, critic, cfg, B, use_graphs=graphs)
+    ad, ag = O.AdamState(D, cfg["lr_critic"]), O.AdamState(G, cfg["lr_gen"])
+    for step in range(2):
+        batches = [O.synthetic_batch(cfg, B, 4000 + step * nc + i) for i in range(nc)]
+        tr.load_batches(torch.stack([b[0] for b in batches]), torch.stack([b[1] for b in batches]),
+                        torch.stack([b[2] for b in batches]), torch.stack([b[3] for b in batches]),
+                        batches[-1][4])
+        tr.train_step()
+        logs = tr.logs()
+        for i, b in enumerate(batches):
+            o = O.critic_iteration(G, D, cfg, b[0], b[1], b[2], b[3], ad)
+            for k in ("loss_critic", "gp", "w_dist"):
+                scalar_check(logs["critic"][i][k], o[k], TOL_NORTH_STAR, f"step{step} it{i} {k}")
+        b = batches[-1]
+        o = O.generator_update(G, D, cfg, b[0], b[1], b[4], ag)
+        for k in ("loss_gen", "l1", "tv"):
+            scalar_check(logs["gen"][k], o[k], TOL_NORTH_STAR, f"step{step} gen {k}")
+        f = tr.fake_g.view(B, cfg["stick_length"], cfg["output_size"]).permute(0, 2, 1).cpu()
+        assert float((f - o["fake"]).abs().max() / o["fake"].abs().max()) < TOL_NORTH_STAR
+    # parameters after 2*nc critic and 2 generator Adam steps: mean deviation in units of lr
+    skip = set(O.pre_bn_bias_names(G))
+    for mod, P, lr, steps in ((critic, D, cfg["lr_critic"], 2 * nc), (gen, G, cfg["lr_gen"], 2)):
+        for k, v in mod.state_dict().items():
+            if k in skip:
+                continue
+            if not v.is_floating_point():
+                assert int(v) == int(P[k]), k
+                continue
+            d = (v.cpu() - P[k]).abs()
+            assert float(d.mean()) < 0.05 * lr * steps + 1e-6 * float(P[k].abs().max()), (k, float(d.mean()))
+
+
+def test_critic_batch_additivity():
+    """Data-parallel property (no BatchNorm in the critic): the critic gradients of a batch
+    equal the mean of the gradients of its two halves — what the all-reduce relies on."""
+    from music2dance_b200.trainer import Phase3Trainer
+    cfg = O.make_cfg(n_critic_steps=1)
+    B = 4
+    batch = O.synthetic_batch(cfg, B, 4100)
+    grads = []
+    for sl in (slice(0, 4), slice(0, 2), slice(2, 4)):
+        gen, critic = build(cfg)
+        n = sl.stop - sl.start
+        tr = Phase3Trainer(gen, critic, cfg, n, use_graphs=False)
+        # the generator's BatchNorm couples the batch, so feed every run the SAME fake poses
+        tr.load_batches(batch[0][sl][None], batch[1][sl][None], batch[2][sl][None], batch[3][sl][None], batch[4][sl])
+        if n == B:
+            full = tr
+            tr.critic_iteration(0, update=False)
+            fake_full = tr.fake_c.clone().view(B, -1)
+        else:
+            orig = tr.G.forward
+
+            def fwd(audio, noise, Bn, T, train=True, out=None, _sl=sl, _o=orig):
+                r = _o(audio, noise, Bn, T, train=train, out=out)
+                out.t.view(Bn, -1).copy_(fake_full[_sl])
+                return r
+            tr.G.forward = fwd
+            tr.critic_iteration(0, update=False)
+        grads.append(tr.de.fp.grad[:tr.de.fp.n_live_padded].clone())
+    mean = 0.5 * (grads[1] + grads[2])
+    e = float((grads[0] - mean).abs().max() / grads[0].abs().max())
+    assert e < TOL_GRAD, f"batch additivity violated: {e:.3e}"
