@@ -1,0 +1,457 @@
+#!/usr/bin/env python
+"""bench.py — phase3 WGAN-GP train steps/sec (seq = 120) on N B200s, with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B] [--enc default]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path (reference phase3/train.py:186-237 until the `continue`
+at :219 falls through): n_critic = 8 critic iterations, each on its own fresh batch (generator
+forward with train-mode BatchNorm, gradient penalty, Wasserstein terms, backward, Adam), then
+one generator update (forward, L1 + critic terms + TV, backward, Adam).  Workload =
+BASELINE.json configs[3] (default.yaml: default audio encoder, 4.8 s audio / 120 frames,
+batch 7 per GPU).  Data: synthetic tensors of the reference shape; random-init weights.
+
+Printed (rank 0, ONE JSON line):
+  value   train steps/s summed over ranks (weak scaling: every rank runs batch-B steps on its own
+          shard; gradients are all-reduced over NCCL), inputs already resident in HBM
+  e2e     the same through the public API with HOST (pinned) input buffers: per step one
+          host->device copy of the step's inputs and one device->host read of its scalars
+  roofline   dominant kernel family, algorithmic FLOPs / CUDA-event time, vs MEASURED_PEAKS.json
+  cpu_baseline   the oracle port of the reference path timed on this box's host cores (N = 1)
+
+`--impl reference` times the CPU implementation of the same path (the oracle port: the
+reference is Python/PyTorch and /root/reference does not exist on the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "phase3 WGAN-GP train steps/sec (seq=120)"
+UNIT = "train steps/s"
+L2_BYTES = 126 << 20
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=7, help="sequences per GPU per iteration (default.yaml: 7)")
+    ap.add_argument("--enc", default="default", choices=["default", "wavegan", "unet"])
+    ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        d["source"] = "measured (MEASURED_PEAKS.json)"
+        return d
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+def workload_name(args, cfg):
+    return (f"phase3 audio-conditioned WGAN-GP, {args.enc} audio encoder, 4.8 s synthetic audio/120 frames, "
+            f"batch {args.batch}/GPU, n_critic {cfg['n_critic_steps']}")
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of phase3/train.py:186-237 (reference = PyTorch CPU eager)
+# ----------------------------------------------------------------------------------------------
+
+def cpu_step_time(cfg, B, budget_s, full_steps=0):
+    """Time the CPU path.  Returns (seconds per train step, description of the sample)."""
+    import torch
+    from oracle import phase3_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    G, D = O.init_generator_params(cfg), O.init_critic_params(cfg)
+    ad, ag = O.AdamState(D, cfg["lr_critic"]), O.AdamState(G, cfg["lr_gen"])
+    nc = cfg["n_critic_steps"]
+    b = O.synthetic_batch(cfg, B, 1234)
+    O.critic_iteration(G, D, cfg, b[0], b[1], b[2], b[3], ad)           # warm-up (thread pools, allocator)
+    t0 = time.perf_counter()
+    O.critic_iteration(G, D, cfg, b[0], b[1], b[2], b[3], ad)
+    t_c1 = time.perf_counter() - t0
+    est = nc * t_c1 * 1.15
+    if full_steps and full_steps * est <= budget_s:
+        ts = []
+        for s in range(full_steps):
+            t0 = time.perf_counter()
+            O.train_step(G, D, cfg, B, s, ag, ad)
+            ts.append(time.perf_counter() - t0)
+        ts.sort()
+        return ts[len(ts) // 2], f"{full_steps} full train steps ({nc} critic iterations + 1 generator update each), median", cores
+    n_c = max(1, min(nc, int(budget_s * 0.6 / max(t_c1, 1e-3))))
+    t0 = time.perf_counter()
+    for i in range(n_c):
+        bb = O.synthetic_batch(cfg, B, 2000 + i)
+        O.critic_iteration(G, D, cfg, bb[0], bb[1], bb[2], bb[3], ad)
+    t_c = (time.perf_counter() - t0) / n_c
+    t0 = time.perf_counter()
+    O.generator_update(G, D, cfg, b[0], b[1], b[4], ag)
+    t_g = time.perf_counter() - t0
+    return nc * t_c + t_g, (f"{n_c} critic iteration(s) + 1 generator update at batch {B} (data generation included), "
+                            f"extrapolated to {nc} + 1"), cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import phase3_oracle as O
+    cfg = O.make_cfg(enc_type=args.enc)
+    total = args.steps + args.warmup
+    t_step, sample, cores = cpu_step_time(cfg, args.batch, args.cpu_budget_s,
+                                          full_steps=total if total <= 6 else 0)
+    v = 1.0 / t_step
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args, cfg), "device": "host CPU (PyTorch eager fp32)"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.sm.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        s = sorted(self.sm)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------------------------
+# per-kernel-family instrumentation (roofline)
+# ----------------------------------------------------------------------------------------------
+
+class KernelTimer:
+    """Wraps the C-ABI wrappers in music2dance_b200.ops with CUDA events recorded on the launching
+    stream (torch's current stream == the stream handed to the C ABI) and the algorithmic
+    FLOPs / bytes of each launch."""
+
+    def __init__(self, ops, torch):
+        self.ops, self.torch = ops, torch
+        self.rec = []            # (family, flops, bytes, ev0, ev1)
+        self.saved = {}
+
+    def _wrap(self, name, fam_fn):
+        orig = getattr(self.ops, name)
+        self.saved[name] = orig
+        torch = self.torch
+
+        def wrapped(*a, **k):
+            fam, flops, nbytes = fam_fn(*a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = orig(*a, **k)
+            e1.record()
+            self.rec.append((fam, flops, nbytes, e0, e1))
+            return r
+        setattr(self.ops, name, wrapped)
+
+    def install(self):
+        def f_rowconv(x, w, y, *, T, Cc, N, **k):
+            M = y.nb * y.rows
+            fam = "rowconv_c1" if Cc == 1 else "rowconv"
+            return fam, 2.0 * M * N * T * Cc, 4.0 * (M * N + N * T * Cc + M * Cc)
+
+        def f_wgrad(dy, x, dw, *, Cout, T, Cc, **k):
+            Kt = dy.nb * dy.rows
+            fam = "wgrad_c1" if Cc == 1 else "wgrad"
+            return fam, 2.0 * Kt * Cout * T * Cc, 4.0 * (Kt * Cout + Kt * Cc + Cout * T * Cc)
+
+        def f_gru_f(gi, w_hh, b_hh, h_out, ldh, save, B, T, H):
+            return "gru_forward", 2.0 * B * T * 3 * H * H, 4.0 * B * T * (3 * H + H + (4 * H if save is not None else 0))
+
+        def f_gru_b(dh_out, ldd, h_out, ldh, save, w_hh, dgi, dgh, B, T, H):
+            return "gru_backward", 2.0 * B * T * 3 * H * H, 4.0 * B * T * (H + H + 4 * H + 6 * H)
+
+        def f_adam(p, g, m, v, n, *a, **k):
+            return "adam", 0.0, 28.0 * n
+
+        def f_dg1(dy, w, dx, *, nb, Lout, Cout, k, stride, pad, Lin):
+            return "conv_dgrad_c1", 2.0 * nb * Lout * Cout * k, 4.0 * nb * (Lout * Cout + Lin)
+        self._wrap("rowconv", f_rowconv)
+        self._wrap("wgrad", f_wgrad)
+        self._wrap("gru_forward", f_gru_f)
+        self._wrap("gru_backward", f_gru_b)
+        self._wrap("adam", f_adam)
+        self._wrap("conv_dgrad_c1", f_dg1)
+
+    def remove(self):
+        for n, f in self.saved.items():
+            setattr(self.ops, n, f)
+
+    def summary(self):
+        fam = {}
+        for f, fl, nb, e0, e1 in self.rec:
+            d = fam.setdefault(f, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += fl
+            d["bytes"] += nb
+        return fam
+
+
+# ----------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from oracle import phase3_oracle as O          # configuration + synthetic-data generator only
+    from music2dance_b200 import ops
+    from music2dance_b200.archis.default import SequenceDiscriminator, SequenceGenerator
+    from music2dance_b200.trainer import Phase3Trainer
+
+    cfg = O.make_cfg(enc_type=args.enc)
+    B, nc = args.batch, cfg["n_critic_steps"]
+    torch.manual_seed(0)
+    gen = SequenceGenerator(cfg["audio_feat_samples"], cfg["input_vector_size"], cfg["latent_vector_size"],
+                            cfg["size"], cfg["output_size"], cfg["noise_size"], cfg["nblocks_gen"],
+                            cfg["n_cells"], cfg["enc_type"], cfg["activ"], dev)
+    critic = SequenceDiscriminator(cfg["output_size"], cfg["channels"], cfg["code_size"], cfg["stick_length"],
+                                   init_ker=cfg["init_kernel"], activ=cfg["activ"], device=dev)
+    tr = Phase3Trainer(gen, critic, cfg, B, use_graphs=not args.no_graphs)
+
+    # synthetic inputs of the reference shape: NSETS distinct step-input sets, pinned on the host and
+    # mirrored in HBM; every rank draws its own shard (weak scaling)
+    NSETS = 4
+    host, devs = [], []
+    for s in range(NSETS):
+        bs = [O.synthetic_batch(cfg, B, 1234 + 7919 * rank + s * nc + i) for i in range(nc)]
+        hs = [torch.stack([b[j] for b in bs]).pin_memory() for j in range(4)] + [bs[-1][4].pin_memory()]
+        host.append(hs)
+        devs.append([t.to(dev) for t in hs])
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    d2h = tr.log_c.numel() * 4 + tr.log_g.numel() * 4
+    flush = torch.empty(2 * L2_BYTES // 4, dtype=torch.float32, device=dev)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def step_resident(i):
+        tr.load_batches(*devs[i % NSETS])
+        flush.zero_()                                   # L2 flush between steps (252 MiB write)
+        tr.train_step()
+
+    def step_e2e(i):
+        tr.load_batches(*host[i % NSETS])               # H2D of this step's inputs (pinned)
+        flush.zero_()
+        tr.train_step()
+        return tr.logs()                                # D2H read of the step's scalars (synchronises)
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    sync_all()
+    launches = tr.launches_per_step()                   # counted C-ABI kernel launches of one step
+    sync_all()
+
+    def timed(fn):
+        sampler = ClockSampler(local)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record()
+        for i in range(args.steps):
+            fn(i)
+        e1.record()
+        sync_all()
+        clocks = sampler.stop()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), clocks
+
+    ms_res, clocks = timed(step_resident)
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e, clocks_e2e = timed(step_e2e)
+    logs = tr.logs()
+
+    # flush cost (excluded from nothing: it is inside both timed regions; reported for transparency)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(10):
+        flush.zero_()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    flush_ms = e0.elapsed_time(e1) / 10
+
+    roof = None
+    fams = None
+    pk = peaks()
+    if rank == 0 and not args.no_roofline:
+        # one more train step, eager, with CUDA events around every GEMM-family launch
+        kt = KernelTimer(ops, torch)
+        kt.install()
+        saved_flag = tr.use_graphs
+        tr.use_graphs = False
+        tr.load_batches(*devs[0])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        if world == 1:
+            tr.train_step()
+        else:                                            # no collectives on a single rank: kernels only
+            for i in range(nc):
+                tr.critic_iteration(i, update=False)
+            tr.generator_update(update=False)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        eager_ms = e0.elapsed_time(e1)
+        tr.use_graphs = saved_flag
+        kt.remove()
+        fams = kt.summary()
+        top = max(fams, key=lambda f: fams[f]["ms"])
+        d = fams[top]
+        tensor_bound = d["flops"] / max(d["bytes"], 1.0) > 100.0
+        if tensor_bound:
+            ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
+            peak = pk["bf16_tflops_sustained"]
+            roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "traffic": None}
+        else:
+            ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+            peak = pk["hbm_gbs"]
+            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None}
+        roof.update({"kernel": top, "launches_per_step": d["launches"],
+                     "avg_launch_us": 1e3 * d["ms"] / d["launches"],
+                     "share_of_eager_step": d["ms"] / eager_ms,
+                     "peak_source": pk["source"] + ("; dense bf16 sustained — the kernel computes in fp32/tf32 whose "
+                                                    "tensor peak is half of it" if tensor_bound else ""),
+                     "algorithmic_gflop_per_launch": d["flops"] / d["launches"] / 1e9})
+        for f in fams.values():
+            f["tflops"] = f["flops"] / max(f["ms"], 1e-9) / 1e9
+            f["gbs"] = f["bytes"] / max(f["ms"], 1e-9) / 1e6
+            f["share_of_eager_step"] = f["ms"] / eager_ms
+            for k in ("flops", "bytes"):
+                f[k] = float(f[k])
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        t_step, sample, cores = cpu_step_time(cfg, B, 25.0)
+        cpu = {"value": 1.0 / t_step, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        v = world * args.steps / (ms_res * 1e-3)
+        e = world * args.steps / (ms_e2e * 1e-3)
+        wk_bytes = tr.G.wk.bytes() + tr.D.wk.bytes()
+        line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_res / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name(args, cfg), "global_batch": B * world,
+                           "sequences_per_step": (nc) * B * world, "parallelism": f"dp{world}",
+                           "cuda_graphs": not args.no_graphs,
+                           "l2": (f"L2 flushed between steps by a {2 * L2_BYTES >> 20} MiB write ({flush_ms:.3f} ms, inside the "
+                                  f"timed region); inputs rotate over {NSETS} staged sets; per-iteration working set "
+                                  f"(weights + Adam moments {(tr.de.fp.n_live_padded * 16) >> 20} MiB + activations "
+                                  f"{wk_bytes >> 20} MiB) exceeds the 126 MiB L2")},
+                "e2e": {"value": e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
+                "clocks": clocks, "clocks_e2e": clocks_e2e,
+                "sequences_per_s": v * nc * B,
+                "last_step_logs": {"loss_critic": logs["critic"][-1]["loss_critic"], "gp": logs["critic"][-1]["gp"],
+                                   "loss_gen": logs["gen"]["loss_gen"]}}
+        if roof is not None:
+            line["roofline"] = roof
+            line["kernel_families"] = fams
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

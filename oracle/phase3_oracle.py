@@ -243,9 +243,50 @@ def _bn(P, name, x, train):
                         momentum=0.1, eps=1e-5)
 
 
+_TAPS = None        # set by activation_margins(): list of (rows per channel, min|x| / rms(x))
+
+
+def _tap(x):
+    if _TAPS is not None:
+        with torch.no_grad():
+            rms = float(x.pow(2).mean().sqrt())
+            _TAPS.append((x.numel() // x.shape[1], float(x.abs().min()) / max(rms, 1e-30)))
+
+
+def _relu(x):
+    _tap(x)
+    return F.relu(x)
+
+
+def _lrelu(x):
+    _tap(x)
+    return F.leaky_relu(x, 0.2)
+
+
+class activation_margins:
+    """Context manager for the parity tests: records, for every ReLU / LeakyReLU input
+    evaluated inside it, (rows per channel, smallest |pre-activation| relative to the layer's
+    rms).  Gradients are discontinuous at the kink, so test points are chosen where no SMALL
+    layer (few rows per channel: one flipped unit moves a gradient by ~1/rows) has a unit
+    within rounding noise of zero."""
+
+    def __enter__(self):
+        global _TAPS
+        _TAPS = []
+        return self
+
+    def __exit__(self, *a):
+        global _TAPS
+        self.taps, _TAPS = _TAPS, None
+
+    def margin(self, max_rows):
+        m = [r for n, r in self.taps if n <= max_rows]
+        return min(m) if m else float("inf")
+
+
 def _final_activ(x, activ):
     if activ == "relu":
-        return F.relu(x)
+        return _relu(x)
     if activ == "tanh":
         return torch.tanh(x)
     return x
@@ -254,9 +295,9 @@ def _final_activ(x, activ):
 def encoder_default(P, x, activ, train):
     """default.py:59-82.  x (N,1,3200) -> (N,250)."""
     p = "audio_enc.model."
-    x = F.relu(_bn(P, p + "activations.0.0", _conv(P, p + "conv_layers.0", x, 50, 124), train))
+    x = _relu(_bn(P, p + "activations.0.0", _conv(P, p + "conv_layers.0", x, 50, 124), train))
     for i in range(1, 6):
-        x = F.relu(_bn(P, p + f"activations.{i}.0", _conv(P, p + f"conv_layers.{i}", x, 2, 1), train))
+        x = _relu(_bn(P, p + f"activations.{i}.0", _conv(P, p + f"conv_layers.{i}", x, 2, 1), train))
     x = _final_activ(_conv(P, p + "conv_layers.6", x), activ)
     return x.squeeze()                                      # Q10
 
@@ -265,14 +306,14 @@ def encoder_wavegan(P, x, activ, train):
     """default.py:114-143.  lengths 3200->794->193->43->5->1."""
     p = "audio_enc.model."
     for i in range(1, 5):
-        x = F.relu(_bn(P, p + f"bn{i}", _conv(P, p + f"l{i}", x, 4, 0), train))
+        x = _relu(_bn(P, p + f"bn{i}", _conv(P, p + f"l{i}", x, 4, 0), train))
     return _final_activ(_conv(P, p + "l5", x), activ).squeeze(-1)
 
 
 def encoder_unet(P, x, activ, train):
     """default.py:85-111,213-246."""
     p = "audio_enc.model."
-    lr = lambda t: F.leaky_relu(t, 0.2)
+    lr = lambda t: _lrelu(t)
     x = lr(_bn(P, p + "activations.0.0", _conv(P, p + "conv_layers.0", x, 4, 79), train))
     x = lr(_bn(P, p + "activations.1.0", _conv(P, p + "conv_layers.1", x, 2, 1), train))
     x = lr(_bn(P, p + "activations.2.0", _conv(P, p + "conv_layers.2", x, 2, 1), train))
@@ -325,11 +366,11 @@ def gru_forward(P, name, x, n_layers):
 def decoder_forward(P, x, nblocks, train):
     """default.py:146-192.  Q1: LinearBlock computes x + relu(bn2(fc2(x))); the
     fc1->bn1 branch is dead but bn1 still updates its running statistics."""
-    x = F.relu(_bn(P, "decoder.bn1", F.linear(x, P["decoder.fc1.weight"], P["decoder.fc1.bias"]), train))
+    x = _relu(_bn(P, "decoder.bn1", F.linear(x, P["decoder.fc1.weight"], P["decoder.fc1.bias"]), train))
     for b in range(nblocks):
         q = f"decoder.blocks.{b}."
         _bn(P, q + "bn1", F.linear(x, P[q + "fc1.weight"], P[q + "fc1.bias"]), train)   # dead branch
-        x = x + F.relu(_bn(P, q + "bn2", F.linear(x, P[q + "fc2.weight"], P[q + "fc2.bias"]), train))
+        x = x + _relu(_bn(P, q + "bn2", F.linear(x, P[q + "fc2.weight"], P[q + "fc2.bias"]), train))
     return F.linear(x, P["decoder.lastfc.weight"], P["decoder.lastfc.bias"])
 
 
@@ -347,10 +388,10 @@ def generator_forward(P, cfg, slices, noise, train=True):
 def stick_d_forward(P, x, cfg):
     """default.py:322-346,195-210.  x (B,69,T) -> (B,code)."""
     k0 = P["stick_d.conv1.weight"].shape[-1]
-    x = F.relu(_conv(P, "stick_d.conv1", x, 1, (k0 - 1) // 2))
+    x = _relu(_conv(P, "stick_d.conv1", x, 1, (k0 - 1) // 2))
     for b in range(2):
-        y = F.relu(_conv(P, f"stick_d.blocks.{b}.conv1", x, 1, 3))
-        y = F.relu(_conv(P, f"stick_d.blocks.{b}.conv2", y, 1, 3))
+        y = _relu(_conv(P, f"stick_d.blocks.{b}.conv1", x, 1, 3))
+        y = _relu(_conv(P, f"stick_d.blocks.{b}.conv2", y, 1, 3))
         x = x + y
     return _final_activ(_conv(P, "stick_d.fconv", x), cfg["activ"]).squeeze(-1)
 
@@ -358,7 +399,7 @@ def stick_d_forward(P, x, cfg):
 def audio_d_forward(P, c, cfg):
     """default.py:294-319.  c (B,1,A) -> (B,code)."""
     for i in range(1, 6):
-        c = F.relu(_conv(P, f"audio_d.l{i}", c, 4, 11))
+        c = _relu(_conv(P, f"audio_d.l{i}", c, 4, 11))
     return _final_activ(_conv(P, "audio_d.l6", c), cfg["activ"]).squeeze(-1)
 
 
@@ -367,7 +408,7 @@ def critic_forward(P, cfg, x, c=None):
     s = stick_d_forward(P, x, cfg)
     if not cfg["ablated"]:
         s = torch.cat((s, audio_d_forward(P, c, cfg)), -1)
-    h = F.relu(F.linear(s, P["fc1.weight"], P["fc1.bias"]))
+    h = _relu(F.linear(s, P["fc1.weight"], P["fc1.bias"]))
     return F.linear(h, P["fc2.weight"], P["fc2.bias"])
 
 

@@ -24,14 +24,35 @@ TOL_GRAD = 1e-3
 # digests therefore allow a handful of flips; the smooth-upstream component tests
 # (test_generator_backward_smooth) hold the same kernels to TOL_GRAD.
 TOL_GEN_GRAD_E2E = 5e-3
+# Measured on B200 (tools/diag_gen.py, fp64 oracle as ground truth): without a kink flip every
+# generator gradient of the CUDA path is within 1-2e-6 of fp64 — the same as the fp32 reference.
+# One flipped ReLU unit in a layer of U units moves ALL upstream gradients by ~1/sqrt(U) in l2
+# (observed: one unit of decoder.blocks.1, U = 360*256 -> 4e-3 everywhere upstream, 5e-2 on the
+# flipped channel's own entries), and with ~4e6 ReLU units per generator pass about one unit per
+# test point lies inside fp32 rounding noise of zero.  In-test comparisons against the oracle
+# therefore bound the l2 error by TOL_KINK_L2 and single entries by TOL_KINK_MAX.
+TOL_KINK_L2 = 1e-2
+TOL_KINK_MAX = 6e-2
+# Chained iterations: Adam's first steps move every weight by ~lr*sign(g), so a flip (or the sign
+# of a noise-level gradient) changes the state the next iteration starts from; scalars after the
+# first optimiser step are compared at TOL_CHAINED instead of the single-iteration 1e-3.
+TOL_CHAINED = 1e-2
 
 
 def load_golden(name):
     return np.load(os.path.join(GOLD, f"phase3_{name}.npz"))
 
 
-def digest_check(t, gold, prefix, tol, what, abs_floor=0.0):
-    """Compare a tensor against a stored (sum, l2, maxabs, strided samples) digest."""
+def digest_check(t, gold, prefix, tol, what, abs_floor=0.0, kinks=False):
+    """Compare a tensor against a stored (sum, l2, maxabs, strided samples) digest.
+
+    kinks=False: every sample, the l2 norm and the sum within `tol` (relative to max|x|).
+    kinks=True (gradients that pass through ReLU / LeakyReLU / MaxPool / L1-sign kinks): the
+    gradient is a DISCONTINUOUS function of the inputs, so two fp32 evaluations of the same
+    network (the reference on 8 vs 16 threads, the oracle vs the reference, CUDA vs CPU) differ
+    by whole units whose pre-activation lies within rounding noise of zero: isolated entries
+    move by percents while everything else agrees to ~1e-4.  The check is therefore statistical:
+    90 % of the samples within `tol`, every sample within 10*tol, l2 and sum within 4*tol."""
     f = t.detach().double().cpu().reshape(-1)
     n = f.numel()
     step = max(1, n // 64)
@@ -41,8 +62,15 @@ def digest_check(t, gold, prefix, tol, what, abs_floor=0.0):
         step = max(1, n // gs.numel())
         samp = f[::step][:gs.numel()]
     scale = max(float(gold[prefix + "/maxabs"]), abs_floor, 1e-30)
-    e_s = float((samp - gs).abs().max()) / scale
-    assert e_s < tol, f"{what}: samples deviate {e_s:.3e} (rel. to max |x| = {scale:.3e})"
+    dev = (samp - gs).abs() / scale
+    if kinks:
+        q90 = float(dev.sort().values[max(0, int(0.9 * dev.numel()) - 1)])
+        assert q90 < tol, f"{what}: 90 % quantile of sample deviations {q90:.3e} (rel. to max |x| = {scale:.3e})"
+        assert float(dev.max()) < 10 * tol, f"{what}: worst sample deviates {float(dev.max()):.3e}"
+        tol = 4 * tol
+    else:
+        e_s = float(dev.max())
+        assert e_s < tol, f"{what}: samples deviate {e_s:.3e} (rel. to max |x| = {scale:.3e})"
     l2 = float(gold[prefix + "/l2"])
     e_l2 = abs(float(f.norm()) - l2) / max(l2, abs_floor * n ** 0.5, 1e-30)
     assert e_l2 < tol, f"{what}: l2 deviates {e_l2:.3e}"

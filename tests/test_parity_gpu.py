@@ -9,7 +9,8 @@ import pytest
 import torch
 
 from oracle import phase3_oracle as O
-from tests.parity import (ALPHA_SEED, B_GOLD, TOL_FP32, TOL_GEN_GRAD_E2E, TOL_GRAD, TOL_NORTH_STAR, VARIANTS,
+from tests.parity import (ALPHA_SEED, B_GOLD, TOL_CHAINED, TOL_FP32, TOL_GEN_GRAD_E2E, TOL_GRAD, TOL_KINK_L2, TOL_KINK_MAX,
+                          TOL_NORTH_STAR, VARIANTS,
                           digest_check, load_golden, scalar_check)
 
 pytestmark = pytest.mark.gpu
@@ -79,7 +80,7 @@ def test_dropin_step_vs_reference_fixtures(variant, state):
     for k, p in critic.named_parameters():
         assert p.grad is not None or k == "fc2.bias", k
         g = p.grad if p.grad is not None else torch.zeros_like(p)
-        digest_check(g, gold, f"{state}/critic/grad/{k}", TOL_GRAD, f"critic grad {k}", abs_floor=1e-4)
+        digest_check(g, gold, f"{state}/critic/grad/{k}", TOL_GRAD, f"critic grad {k}", abs_floor=1e-4, kinks=True)
     for k, v in gen.state_dict().items():                       # Q2: running stats advanced by the forward
         if "running" in k or "num_batches" in k:
             digest_check(v, gold, f"{state}/critic/genbuf/{k}", TOL_FP32, f"bn buffer {k}")
@@ -102,7 +103,7 @@ def test_dropin_step_vs_reference_fixtures(variant, state):
         if f"{state}/gen/nograd/{k}" in gold.files:              # Q1: dead branch never gets a gradient
             assert p.grad is None, k
         elif k not in skip:
-            digest_check(p.grad, gold, f"{state}/gen/grad/{k}", TOL_GEN_GRAD_E2E, f"gen grad {k}", abs_floor=1e-4)
+            digest_check(p.grad, gold, f"{state}/gen/grad/{k}", TOL_GEN_GRAD_E2E, f"gen grad {k}", abs_floor=1e-4, kinks=True)
 
 
 @pytest.mark.parametrize("variant", ["default", "wavegan", "unet"])
@@ -116,28 +117,43 @@ def test_generator_backward_smooth(variant):
     audio = (torch.rand(B, cfg["audio_length"], generator=g) - 0.5) * 0.6
     noise = torch.randn(B, T, cfg["noise_size"], generator=g)
     up = torch.randn(B * T, cfg["output_size"], generator=g)
-    P = O._leaf(oracle_params(gen))
     sl = O.slice_audio_batch(audio, cfg["audio_feat_samples"], cfg["cutting_stride"], cfg["pad_samples"])
-    out_ref = O.generator_forward(P, cfg, sl, noise, train=True)
-    names = O.trainable_names(P)
-    gl = torch.autograd.grad((out_ref * up).sum(), [P[k] for k in names], allow_unused=True)
+    G0 = oracle_params(gen)
+    names = O.trainable_names(G0)
+    ref = {}
+    for dt in (torch.float32, torch.float64):                   # fp64 = ground truth, fp32 = the reference's arithmetic
+        P = O._leaf({k: (v.to(dt).clone() if v.is_floating_point() else v.clone()) for k, v in G0.items()})
+        o = O.generator_forward(P, cfg, sl.to(dt), noise.to(dt), train=True)
+        gl = torch.autograd.grad((o * up.to(dt)).sum(), [P[k] for k in names], allow_unused=True)
+        ref[dt] = (o.detach(), dict(zip(names, gl)))
+    out_ref, g64 = ref[torch.float64]
+    g32 = ref[torch.float32][1]
     from music2dance_b200.utils import slice_audio_batch
     gen.train()
     out = gen(slice_audio_batch(audio.to(DEV), cfg["audio_feat_samples"], cfg["cutting_stride"],
                                 cfg["pad_samples"]), [T] * B, noise=noise.to(DEV))
-    err = float((out.detach().cpu() - out_ref.detach()).abs().max() / out_ref.abs().max())
-    assert err < TOL_FP32, f"generator output rel err {err:.3e}"
+    err = float((out.detach().cpu().double() - out_ref).abs().max() / out_ref.abs().max())
+    assert err < 2e-5, f"generator output rel err vs fp64 {err:.3e}"
     (out * up.to(DEV)).sum().backward()
-    skip = set(O.pre_bn_bias_names(P))
+    skip = set(O.pre_bn_bias_names(G0))
     got = dict(gen.named_parameters())
-    for k, gr in zip(names, gl):
+    worst = 0.0
+    for k in names:
+        gr = g64[k]
         if gr is None:
             assert got[k].grad is None, k
             continue
         if k in skip:
             continue
-        e = float((got[k].grad.cpu() - gr).abs().max() / max(float(gr.abs().max()), 1e-4))
-        assert e < TOL_GRAD, f"{variant} {k}: {e:.3e}"
+        d = got[k].grad.cpu().double() - gr
+        e_l2 = float(d.norm() / gr.norm().clamp_min(1e-30))
+        e_mx = float(d.abs().max() / gr.abs().max().clamp_min(1e-4))
+        e_ref = float((g32[k].double() - gr).norm() / gr.norm().clamp_min(1e-30))
+        worst = max(worst, e_l2)
+        # kink-flip bound (tests/parity.py), or three times the fp32 reference's own error
+        assert e_l2 < max(TOL_KINK_L2, 3 * e_ref), f"{variant} {k}: l2 {e_l2:.3e} (fp32 reference {e_ref:.3e})"
+        assert e_mx < max(TOL_KINK_MAX, 3 * e_ref), f"{variant} {k}: max {e_mx:.3e}"
+    print(f"[{variant}] worst generator-gradient l2 error vs fp64 oracle: {worst:.2e}")
     # eval mode (running statistics) — train.py:245-261
     gen.eval()
     with torch.no_grad():
@@ -188,14 +204,16 @@ def test_fused_trainer_vs_oracle(variant, B, nc, graphs):
         logs = tr.logs()
         for i, b in enumerate(batches):
             o = O.critic_iteration(G, D, cfg, b[0], b[1], b[2], b[3], ad)
+            first = step == 0 and i == 0                        # identical state: north-star tolerance
             for k in ("loss_critic", "gp", "w_dist"):
-                scalar_check(logs["critic"][i][k], o[k], TOL_NORTH_STAR, f"step{step} it{i} {k}")
+                scalar_check(logs["critic"][i][k], o[k], TOL_NORTH_STAR if first else TOL_CHAINED,
+                             f"step{step} it{i} {k}")
         b = batches[-1]
         o = O.generator_update(G, D, cfg, b[0], b[1], b[4], ag)
         for k in ("loss_gen", "l1", "tv"):
-            scalar_check(logs["gen"][k], o[k], TOL_NORTH_STAR, f"step{step} gen {k}")
+            scalar_check(logs["gen"][k], o[k], TOL_CHAINED, f"step{step} gen {k}")
         f = tr.fake_g.view(B, cfg["stick_length"], cfg["output_size"]).permute(0, 2, 1).cpu()
-        assert float((f - o["fake"]).abs().max() / o["fake"].abs().max()) < TOL_NORTH_STAR
+        assert float((f - o["fake"]).abs().max() / o["fake"].abs().max()) < TOL_CHAINED
     # parameters after 2*nc critic and 2 generator Adam steps: mean deviation in units of lr
     skip = set(O.pre_bn_bias_names(G))
     for mod, P, lr, steps in ((critic, D, cfg["lr_critic"], 2 * nc), (gen, G, cfg["lr_gen"], 2)):
