@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=7, help="sequences per GPU per iteration (default.yaml: 7)")
     ap.add_argument("--enc", default="default", choices=["default", "wavegan", "unet"])
+    ap.add_argument("--gemm", default="tf32x3", choices=["fp32", "tf32", "tf32x3"],
+                    help="arithmetic of the GEMM family (include/m2d.h): tcgen05 3xTF32 split (default, fp32-grade), "
+                         "tcgen05 single-pass TF32, or CUDA-core fp32")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
@@ -282,6 +285,7 @@ def run_b200(args):
 
     cfg = O.make_cfg(enc_type=args.enc)
     B, nc = args.batch, cfg["n_critic_steps"]
+    ops.set_gemm_mode(args.gemm)
     torch.manual_seed(0)
     gen = SequenceGenerator(cfg["audio_feat_samples"], cfg["input_vector_size"], cfg["latent_vector_size"],
                             cfg["size"], cfg["output_size"], cfg["noise_size"], cfg["nblocks_gen"],
@@ -388,7 +392,8 @@ def run_b200(args):
         tensor_bound = d["flops"] / max(d["bytes"], 1.0) > 100.0
         if tensor_bound:
             ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
-            peak = pk["bf16_tflops_sustained"]
+            # TF32 dense peak = half the bf16 rate (same tensor pipe, K = 8 instead of 16 per instruction)
+            peak = pk["bf16_tflops_sustained"] / 2.0
             roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "traffic": None}
         else:
@@ -398,8 +403,10 @@ def run_b200(args):
         roof.update({"kernel": top, "launches_per_step": d["launches"],
                      "avg_launch_us": 1e3 * d["ms"] / d["launches"],
                      "share_of_eager_step": d["ms"] / eager_ms,
-                     "peak_source": pk["source"] + ("; dense bf16 sustained — the kernel computes in fp32/tf32 whose "
-                                                    "tensor peak is half of it" if tensor_bound else ""),
+                     "peak_source": pk["source"] + ("; TF32 dense peak taken as half the measured sustained bf16 rate "
+                                                    "(no TF32 figure in the file); gemm mode " + args.gemm +
+                                                    (" issues 3 tensor-core products per algorithmic product"
+                                                     if args.gemm == "tf32x3" else "") if tensor_bound else ""),
                      "algorithmic_gflop_per_launch": d["flops"] / d["launches"] / 1e9})
         for f in fams.values():
             f["tflops"] = f["flops"] / max(f["ms"], 1e-9) / 1e9
@@ -419,8 +426,11 @@ def run_b200(args):
         wk_bytes = tr.G.wk.bytes() + tr.D.wk.bytes()
         line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_res / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_name(args, cfg), "global_batch": B * world,
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": {"fp32": "f32", "tf32": "tf32 (fp32 accumulate)",
+                          "tf32x3": "tf32x3 (3xTF32 operand split on tcgen05, fp32 accumulate; fp32-grade)"}[args.gemm],
+                "data": "synthetic",
+                "config": {"workload": workload_name(args, cfg), "global_batch": B * world, "gemm": args.gemm,
                            "sequences_per_step": (nc) * B * world, "parallelism": f"dp{world}",
                            "cuda_graphs": not args.no_graphs,
                            "l2": (f"L2 flushed between steps by a {2 * L2_BYTES >> 20} MiB write ({flush_ms:.3f} ms, inside the "

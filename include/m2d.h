@@ -43,6 +43,19 @@ int m2d_version(void);
 /* 0 if device `dev` is sm_100-class, M2D_ERR_ARCH otherwise. */
 int m2d_check_device(int dev);
 
+/* Arithmetic of the GEMM family (m2d_rowconv, m2d_wgrad).  The reference runs these
+ * contractions as fp32 cuDNN/cuBLAS calls (phase3/train.py:33-34 leaves TF32 at the
+ * PyTorch default).  Process-wide setting, not thread-safe against in-flight calls.
+ *   FP32   : CUDA-core FFMA kernels (fp32 products, fp32 accumulate)
+ *   TF32   : tcgen05 tensor cores, operands rounded to TF32 (round-to-nearest), fp32 accumulate
+ *   TF32X3 : tcgen05 tensor cores, 3xTF32 operand split (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo):
+ *            fp32-grade results on the tensor pipe — the default
+ * Shapes the tensor-core kernels do not cover (N < 8, tiny problems, weight gradients with
+ * Cout or Cc not a multiple of 4) run on the FP32 kernels in every mode. */
+enum { M2D_GEMM_FP32 = 0, M2D_GEMM_TF32 = 1, M2D_GEMM_TF32X3 = 3 };
+int m2d_set_gemm_mode(int mode);
+int m2d_get_gemm_mode(void);
+
 /* ------------------------------------------------------------------------
  * Row-convolution GEMM: the one contraction that serves Conv1d forward,
  * Conv1d backward-data (per stride residue), the WGAN-GP tangent pass and

@@ -55,6 +55,8 @@ _I, _F, _P, _L = C.c_int, C.c_float, C.c_void_p, i64
 SIGNATURES = {
     "m2d_version": [],
     "m2d_check_device": [_I],
+    "m2d_set_gemm_mode": [_I],
+    "m2d_get_gemm_mode": [],
     "m2d_rowconv": [C.POINTER(RowConvArgs), _P],
     "m2d_wgrad": [C.POINTER(WgradArgs), _P],
     "m2d_wgrad_min_ws": [_I, _I, _I],
@@ -89,6 +91,7 @@ SIGNATURES = {
     "m2d_adam": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _P],
 }
 _RESTYPE = {"m2d_wgrad_min_ws": i64}
+_NOCHECK = {"m2d_wgrad_min_ws", "m2d_version", "m2d_get_gemm_mode"}     # return a value, not a status
 
 _lib = None
 
@@ -122,6 +125,6 @@ def check(rc, what=""):
 def call(name, *args):
     lib = load()
     rc = getattr(lib, name)(*args)
-    if name not in _RESTYPE and rc != 0:
+    if name not in _NOCHECK and rc != 0:
         check(rc, name)
     return rc

@@ -10,7 +10,19 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+static int g_gemm_mode = M2D_GEMM_TF32X3;
+int gemm_mode() { return g_gemm_mode; }
 }  // namespace m2d
+
+extern "C" int m2d_set_gemm_mode(int mode) {
+    if (mode != M2D_GEMM_FP32 && mode != M2D_GEMM_TF32 && mode != M2D_GEMM_TF32X3) {
+        m2d::set_error("set_gemm_mode: unknown mode %d", mode);
+        return M2D_ERR_BAD_ARG;
+    }
+    m2d::g_gemm_mode = mode;
+    return M2D_OK;
+}
+extern "C" int m2d_get_gemm_mode(void) { return m2d::g_gemm_mode; }
 
 extern "C" const char* m2d_last_error(void) { return m2d::g_err; }
 extern "C" int m2d_version(void) { return 100; }

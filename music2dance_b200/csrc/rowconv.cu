@@ -439,7 +439,20 @@ conv_dgrad_c1_kernel(const float* __restrict__ dy, int Lout, int Cout, const flo
 
 }  // namespace m2d
 
+namespace m2d {
+int rowconv_tc_dispatch(const m2d_rowconv_args& a, int M, int mode, cudaStream_t st, int* splits_out);
+int wgrad_tc_dispatch(const m2d_wgrad_args& a, int Ktot, int Ncols, int mode, cudaStream_t st, int* splits_out);
+int gemm_mode();
+}  // namespace m2d
+
 using namespace m2d;
+
+static int run_splitk_epilogue(const m2d_rowconv_args& a, int M, int splits, cudaStream_t st) {
+    long long total = (long long)M * a.N;
+    int blocks = (int)(cdiv(total, 256) < 4 * kNumSMs ? cdiv(total, 256) : 4 * kNumSMs);
+    rowconv_splitk_epilogue<<<blocks, 256, 0, st>>>(a, M, splits);
+    return check_launch("rowconv_splitk_epilogue");
+}
 
 extern "C" int m2d_rowconv(const m2d_rowconv_args* ap, void* stream) {
     const m2d_rowconv_args& a = *ap;
@@ -451,6 +464,15 @@ extern "C" int m2d_rowconv(const m2d_rowconv_args* ap, void* stream) {
     long long Mll = (long long)a.nb * a.y_rows;
     M2D_REQUIRE(Mll < (1ll << 31), "rowconv: M too large");
     const int M = (int)Mll;
+    const int mode = gemm_mode();
+    if (mode != M2D_GEMM_FP32) {
+        int tc_splits = 1;
+        int rc = rowconv_tc_dispatch(a, M, mode, st, &tc_splits);
+        if (rc <= 0) {
+            if (rc == 0 && tc_splits > 1) rc = run_splitk_epilogue(a, M, tc_splits, st);
+            return rc;
+        }
+    }
     const bool c1 = a.Cc == 1;
     const bool vec = !c1 && a.Cc % 4 == 0 && a.x_ld % 4 == 0 && a.x_bs % 4 == 0 && a.w_ld % 4 == 0 &&
                      aligned16(a.x) && aligned16(a.w);
@@ -478,12 +500,7 @@ extern "C" int m2d_rowconv(const m2d_rowconv_args* ap, void* stream) {
     }
     int rc = check_launch("rowconv");
     if (rc) return rc;
-    if (splits > 1) {
-        long long total = (long long)M * a.N;
-        int blocks = (int)(cdiv(total, 256) < 4 * kNumSMs ? cdiv(total, 256) : 4 * kNumSMs);
-        rowconv_splitk_epilogue<<<blocks, 256, 0, st>>>(a, M, splits);
-        rc = check_launch("rowconv_splitk_epilogue");
-    }
+    if (splits > 1) rc = run_splitk_epilogue(a, M, splits, st);
     return rc;
 }
 
@@ -506,6 +523,17 @@ extern "C" int m2d_wgrad(const m2d_wgrad_args* ap, void* stream) {
     long long Kll = (long long)a.nb * a.dy_rows;
     M2D_REQUIRE(Kll < (1ll << 31), "wgrad: K too large");
     const int Ktot = (int)Kll;
+    const int mode = gemm_mode();
+    if (mode != M2D_GEMM_FP32) {
+        int tc_splits = 1;
+        int rc = wgrad_tc_dispatch(a, Ktot, Ncols, mode, st, &tc_splits);
+        if (rc < 0) return rc;
+        if (rc == 0) {
+            int blocks = (int)(cdiv(per, 256) < 8 * kNumSMs ? cdiv(per, 256) : 8 * kNumSMs);
+            wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(a, Ncols, tc_splits);
+            return check_launch("wgrad_reduce");
+        }
+    }
     const int nsteps = (int)cdiv(Ktot, BK);
     long long tiles = cdiv(a.Cout, 64) * cdiv(Ncols, BN);
     long long want = cdiv(3 * kNumSMs, tiles);

@@ -1,0 +1,694 @@
+// Row-convolution GEMM on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+//   y[m, n] = epi( sum_k A[m, k] * W[n, k] ),   m = (batch, row), k = (tap, channel)
+//
+// CTA tile 128 x BN (BN <= 128, multiple of 16), K consumed in blocks of 32 floats
+// (= one 128-byte swizzle row).  Roles (288 threads):
+//   warps 0-7  gather the A rows (strided / windowed / zero padded, exactly the
+//              index arithmetic of the fp32 SIMT kernel) and the weight rows from
+//              global memory, round them to TF32 with round-to-nearest
+//              (cvt.rna.tf32.f32) and store them into shared memory in the
+//              canonical K-major SWIZZLE_128B layout; afterwards they run the epilogue
+//   warp  8    allocates TMEM and issues tcgen05.mma (kind::tf32, M = 128, N = BN,
+//              K = 8 per instruction) from shared-memory descriptors; accumulators
+//              live in TMEM (128 lanes x BN fp32 columns)
+// Stages are handed over with mbarriers: full[s] (256 producer arrivals after
+// fence.proxy.async) and empty[s] (tcgen05.commit).  Precision modes:
+//   NS = 1 : one TF32 product per term (10-bit mantissas, fp32 accumulate)
+//   NS = 3 : 3xTF32 split  a = a_hi + a_lo :  a_hi*b_hi + a_lo*b_hi + a_hi*b_lo
+//            (error ~2^-21 per product: fp32-grade results on the tensor pipe)
+// Epilogue: tcgen05.ld (32x32b.x16) -> shared memory -> coalesced global stores with
+// the fused bias / activation / mask / residual epilogue of m2d_rowconv, or split-K
+// partials into the workspace.
+#include "common.cuh"
+
+namespace m2d {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;
+constexpr int TC_BNMAX = 128;
+constexpr int TC_PRODUCERS = 256;
+constexpr int TC_THREADS = TC_PRODUCERS + 32;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;        // 16 KiB
+constexpr int TC_B_BYTES = TC_BNMAX * TC_BK * 4;     // 16 KiB
+
+__host__ __device__ constexpr int tc_stage_bytes(int ns) { return (ns == 3 ? 2 : 1) * (TC_A_BYTES + TC_B_BYTES); }
+__host__ __device__ constexpr int tc_stages(int ns) { return ns == 3 ? 3 : 4; }
+// stages + epilogue staging tile never coexist: the C tile (128 x 129 floats) reuses the stages
+__host__ __device__ constexpr int tc_smem_bytes(int ns) { return tc_stages(ns) * tc_stage_bytes(ns) + 1024; }
+
+// ---------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Spin on the barrier; a pipeline bug must surface as a launch failure, never as a hung GPU:
+// after 2^22 failed polls (each poll suspends up to the hardware time limit: seconds) the kernel traps.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try(bar, parity)) {
+        if (++spins > (1u << 22)) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// K-major operand tile, SWIZZLE_128B: row r (128 bytes = 32 floats) lives at
+// (r/8)*1024 + (r%8)*128, its 16-byte chunk j at chunk position j ^ (r%8).
+__device__ __forceinline__ uint32_t sw128_off(int r, int j) {
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
+}
+// shared-memory matrix descriptor (tcgen05): start >> 4 | LBO(16 B, unused for swizzled K-major) |
+// SBO = 1024 B between 8-row groups | version 1 | layout SWIZZLE_128B (2)
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor: D = F32 (1 @ bit 4), A = B = TF32 (2 @ bits 7, 10), both K-major,
+// N >> 3 @ bit 17, M >> 4 @ bit 24
+__device__ __forceinline__ uint32_t tf32_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct TcRow {          // per output row of the CTA tile
+    long long base;     // element offset of the row's batch (or sequence) in x; -1: row beyond M
+    int r0;             // i*sr + roff0
+    int ab;             // windowed mode: f*win_stride - win_pad
+    int b, i;           // batch / row indices for the epilogue
+};
+
+template <int NS, bool VEC, bool C1>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const int cchunks) {
+    constexpr int STAGES = tc_stages(NS);
+    constexpr int STAGE_BYTES = tc_stage_bytes(NS);
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bars[2 * 4 + 1];
+    __shared__ uint32_t tmem_slot;
+    __shared__ TcRow rows[TC_BM];
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_full = smem_u32(&bars[0]);          // + 8*s
+    const uint32_t bar_empty = smem_u32(&bars[4]);         // + 8*s
+    const uint32_t bar_acc = smem_u32(&bars[8]);
+
+    const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BNMAX;
+    int bn = a.N - n0;
+    bn = bn > TC_BNMAX ? TC_BNMAX : ((bn + 15) & ~15);
+    const int tm_cols = bn <= 32 ? 32 : (bn <= 64 ? 64 : 128);
+    const int per = (nsteps + gridDim.z - 1) / gridDim.z;
+    const int s_begin = blockIdx.z * per;
+    const int s_end = min(nsteps, s_begin + per);
+    const int nk = max(0, s_end - s_begin);
+    const bool win = a.win_T > 0;
+
+    if (tid < TC_BM) {
+        int m = m0 + tid;
+        TcRow r;
+        if (m < M) {
+            r.b = m / a.y_rows;
+            r.i = m - r.b * a.y_rows;
+            r.r0 = r.i * a.sr + a.roff0;
+            if (win) {
+                int seq = r.b / a.win_T;
+                int f = r.b - seq * a.win_T;
+                r.ab = f * a.win_stride - a.win_pad;
+                r.base = (long long)seq * a.win_seq_len;
+            } else {
+                r.ab = 0;
+                r.base = (long long)r.b * a.x_bs;
+            }
+        } else {
+            r.b = r.i = r.r0 = r.ab = 0;
+            r.base = -1;
+        }
+        rows[tid] = r;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, TC_PRODUCERS);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_acc, 1);
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc(smem_u32(&tmem_slot), (uint32_t)tm_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp < 8) {
+        // ------------------------------------------------------------------ producers
+        const int j = tid & 7;                 // 16-byte chunk of the 128-byte K row
+        const int rsub = tid >> 3;             // 0..31
+        float4 ra[2][4], rb[2][4];
+
+        auto load = [&](int s, float4* pa, float4* pb) {
+            int t = 0, c = 0, k0 = 0;
+            if (C1) {
+                k0 = s * TC_BK + 4 * j;
+            } else {
+                t = s / cchunks;
+                c = (s - t * cchunks) * TC_BK + 4 * j;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const TcRow r = rows[rsub + 32 * q];
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r.base >= 0) {
+                    if (C1) {
+                        float e[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            int k = k0 + u;
+                            int rr = r.r0 + k * a.droff;
+                            bool ok = k < a.T && rr >= 0 && rr < a.x_rows;
+                            int pos = r.ab + rr;
+                            if (win) ok = ok && pos >= 0 && pos < a.win_seq_len;
+                            e[u] = ok ? __ldg(a.x + r.base + (long long)pos * a.x_ld) : 0.f;
+                        }
+                        v = make_float4(e[0], e[1], e[2], e[3]);
+                    } else {
+                        int rr = r.r0 + t * a.droff;
+                        if (rr >= 0 && rr < a.x_rows) {
+                            const float* p = a.x + r.base + (long long)rr * a.x_ld + c;
+                            if (VEC) {
+                                if (c < a.Cc) v = __ldg(reinterpret_cast<const float4*>(p));
+                            } else {
+                                float e[4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) e[u] = (c + u < a.Cc) ? __ldg(p + u) : 0.f;
+                                v = make_float4(e[0], e[1], e[2], e[3]);
+                            }
+                        }
+                    }
+                }
+                pa[q] = v;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int nl = rsub + 32 * q;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (nl < bn && n0 + nl < a.N) {
+                    const float* wrow = a.w + (long long)(n0 + nl) * a.w_ld;
+                    if (C1) {
+                        float e[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) e[u] = (k0 + u < a.T) ? __ldg(wrow + k0 + u) : 0.f;
+                        v = make_float4(e[0], e[1], e[2], e[3]);
+                    } else {
+                        const float* p = wrow + (long long)t * a.Cc + c;
+                        if (VEC) {
+                            if (c < a.Cc) v = __ldg(reinterpret_cast<const float4*>(p));
+                        } else {
+                            float e[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) e[u] = (c + u < a.Cc) ? __ldg(p + u) : 0.f;
+                            v = make_float4(e[0], e[1], e[2], e[3]);
+                        }
+                    }
+                }
+                pb[q] = v;
+            }
+        };
+
+        auto split_store = [&](uint8_t* hi_tile, uint8_t* lo_tile, int r, float4 v) {
+            const uint32_t off = sw128_off(r, j);
+            float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+            *reinterpret_cast<float4*>(hi_tile + off) = h;
+            if (NS == 3) {
+                float4 l = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+                *reinterpret_cast<float4*>(lo_tile + off) = l;
+            }
+        };
+
+        auto store = [&](int it, const float4* pa, const float4* pb) {
+            const int st = it % STAGES;
+            const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+            mbar_wait(bar_empty + 8 * st, ph ^ 1);
+            uint8_t* sA = smem + (size_t)st * STAGE_BYTES;
+            uint8_t* sB = sA + (NS == 3 ? 2 : 1) * TC_A_BYTES;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) split_store(sA, sA + TC_A_BYTES, rsub + 32 * q, pa[q]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (rsub + 32 * q < bn) split_store(sB, sB + TC_B_BYTES, rsub + 32 * q, pb[q]);
+            fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
+            mbar_arrive(bar_full + 8 * st);
+        };
+
+        if (nk > 0) load(s_begin, ra[0], rb[0]);
+        for (int it = 0; it < nk; it += 2) {
+            if (it + 1 < nk) load(s_begin + it + 1, ra[1], rb[1]);
+            store(it, ra[0], rb[0]);
+            if (it + 1 < nk) {
+                if (it + 2 < nk) load(s_begin + it + 2, ra[0], rb[0]);
+                store(it + 1, ra[1], rb[1]);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ MMA issuer (one elected lane)
+        if (lane == 0) {
+            const uint32_t idesc = tf32_idesc(TC_BM, bn);
+            for (int it = 0; it < nk; ++it) {
+                const int st = it % STAGES;
+                const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+                mbar_wait(bar_full + 8 * st, ph);
+                tc_fence_after();
+                const uint32_t sA = smem_base + (uint32_t)st * STAGE_BYTES;
+                const uint32_t sB = sA + (NS == 3 ? 2 : 1) * TC_A_BYTES;
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k) {
+                    const uint64_t ah = sw128_desc(sA + 32 * k), bh = sw128_desc(sB + 32 * k);
+                    if (NS == 3) {
+                        const uint64_t al = sw128_desc(sA + TC_A_BYTES + 32 * k);
+                        const uint64_t bl = sw128_desc(sB + TC_B_BYTES + 32 * k);
+                        umma_tf32(tmem, al, bh, idesc, (it | k) != 0);
+                        umma_tf32(tmem, ah, bl, idesc, 1);
+                        umma_tf32(tmem, ah, bh, idesc, 1);
+                    } else {
+                        umma_tf32(tmem, ah, bh, idesc, (it | k) != 0);
+                    }
+                }
+                umma_commit(bar_empty + 8 * st);     // stage reusable once these MMAs have read it
+            }
+            umma_commit(bar_acc);                    // accumulator complete
+        }
+        __syncwarp();
+    }
+
+    // ---------------------------------------------------------------------- epilogue
+    float* Cs = reinterpret_cast<float*>(smem);      // [128][129], reuses the (drained) stages
+    constexpr int CLD = TC_BNMAX + 1;
+    if (warp < 8) {
+        if (nk > 0) {
+            mbar_wait(bar_acc, 0);
+            tc_fence_after();
+            const int q = warp & 3, half = warp >> 2;      // TMEM lanes 32q..32q+31, column half
+            const int row = 32 * q + lane;
+            const int chunks = bn / 16;
+            for (int ch = half; ch < chunks; ch += 2) {
+                float v[16];
+                tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(16 * ch), v);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) Cs[row * CLD + 16 * ch + u] = v[u];
+            }
+        } else {
+            for (int idx = tid; idx < TC_BM * CLD; idx += TC_PRODUCERS) Cs[idx] = 0.f;
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem, (uint32_t)tm_cols);
+    } else {
+        const int ncols = min(bn, a.N - n0);
+        const bool split = gridDim.z > 1;
+        float* ws = split ? a.ws + (long long)blockIdx.z * M * a.N : nullptr;
+        // consecutive threads walk along n: coalesced stores / mask / residual loads
+        for (int idx = tid; idx < TC_BM * ncols; idx += TC_PRODUCERS) {
+            const int rl = idx / ncols, cl = idx - rl * ncols;
+            const TcRow r = rows[rl];
+            if (r.base < 0) continue;
+            float v = Cs[rl * CLD + cl];
+            const int n = n0 + cl;
+            if (split) {
+                ws[(long long)(m0 + rl) * a.N + n] = v;
+                continue;
+            }
+            if (a.bias) v += __ldg(a.bias + n);
+            v = apply_act(v, a.act);
+            if (a.add && a.add_before_mask) v += a.add[r.b * a.a_bs + (long long)r.i * a.a_ld + n];
+            if (a.y2) a.y2[r.b * a.y_bs + (long long)r.i * a.y_ld + n] = v;
+            if (a.mask_mode) v *= act_deriv(a.mask[r.b * a.m_bs + (long long)r.i * a.m_ld + n], a.mask_mode);
+            if (a.add && !a.add_before_mask) v += a.add[r.b * a.a_bs + (long long)r.i * a.a_ld + n];
+            a.y[r.b * a.y_bs + (long long)r.i * a.y_ld + n] = v;
+        }
+    }
+}
+
+template <int NS, bool VEC, bool C1>
+static int launch_tc(const m2d_rowconv_args& a, int M, int nsteps, int cchunks, int splits, cudaStream_t st) {
+    auto kern = rowconv_tc_kernel<NS, VEC, C1>;
+    static bool configured = false;
+    const int smem = tc_smem_bytes(NS);
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) {
+            set_error("rowconv_tc: smem attribute (%d B): %s", smem, cudaGetErrorString(e));
+            return M2D_ERR_CUDA;
+        }
+        configured = true;
+    }
+    dim3 grid((unsigned)cdiv(M, TC_BM), (unsigned)cdiv(a.N, TC_BNMAX), (unsigned)splits);
+    kern<<<grid, TC_THREADS, smem, st>>>(a, M, nsteps, cchunks);
+    return check_launch("rowconv_tc");
+}
+
+// Called by m2d_rowconv when the tensor-core path is selected.  Returns 1 if the shape is
+// not worth a tensor-core launch (caller falls through to the SIMT kernel), <= 0 otherwise.
+int rowconv_tc_dispatch(const m2d_rowconv_args& a, int M, int mode, cudaStream_t st, int* splits_out) {
+    const bool c1 = a.Cc == 1;
+    const long long K = (long long)a.T * a.Cc;
+    if (a.N < 8 || (long long)M * a.N * K < (1ll << 18)) return 1;
+    const bool vec = !c1 && a.Cc % 4 == 0 && a.x_ld % 4 == 0 && a.x_bs % 4 == 0 && a.w_ld % 4 == 0 &&
+                     aligned16(a.x) && aligned16(a.w);
+    const int cchunks = c1 ? 1 : (int)cdiv(a.Cc, TC_BK);
+    const int nsteps = c1 ? (int)cdiv(a.T, TC_BK) : a.T * cchunks;
+    const long long tiles = cdiv(M, TC_BM) * cdiv(a.N, TC_BNMAX);
+    int splits = 1;
+    if (a.ws && tiles < kNumSMs && nsteps >= 8) {
+        long long want = cdiv(kNumSMs, tiles);
+        long long cap = a.ws_floats / ((long long)M * a.N);
+        splits = (int)(want < nsteps / 4 ? want : nsteps / 4);
+        if (splits > cap) splits = (int)cap;
+        if (splits < 1) splits = 1;
+    }
+    *splits_out = splits;
+    int rc;
+    if (mode == 3) {
+        if (c1) rc = launch_tc<3, false, true>(a, M, nsteps, cchunks, splits, st);
+        else if (vec) rc = launch_tc<3, true, false>(a, M, nsteps, cchunks, splits, st);
+        else rc = launch_tc<3, false, false>(a, M, nsteps, cchunks, splits, st);
+    } else {
+        if (c1) rc = launch_tc<1, false, true>(a, M, nsteps, cchunks, splits, st);
+        else if (vec) rc = launch_tc<1, true, false>(a, M, nsteps, cchunks, splits, st);
+        else rc = launch_tc<1, false, false>(a, M, nsteps, cchunks, splits, st);
+    }
+    return rc;
+}
+
+// ============================================================================ weight gradient
+//   dW[co, (t,c)] = sum_{k=(b,l)} dy[k, co] * x[row(k, t), c]
+// as a GEMM with M = Cout, N = T*Cc, K = nb*dy_rows.  Both operands are contiguous along
+// their M / N index in memory (channels-last), so they are staged MN-major.  For 32-bit
+// (TF32) MN-major operands the tensor core accepts exactly one shared-memory layout,
+// SWIZZLE_128B_BASE32B: atoms of 4 K-rows x 128 bytes (32 contiguous M/N floats per row),
+// the 32-byte units of a row XOR-swizzled with the row index (byte-address Swizzle<2,5,2>).
+// A K-block of 32 rows is 8 such K-groups (SBO = 512 B apart); 32-wide M/N blocks are
+// LBO = 4096 B apart.  One tcgen05.mma (K = 8) consumes two K-groups.
+// Requires Cout % 4 == 0 and Cc % 4 == 0 (16-byte chunks never straddle a tap).
+__device__ __forceinline__ uint64_t sw128b32_desc_mn(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(4096 >> 4) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;          // SWIZZLE_128B_BASE32B
+    return d;
+}
+// tile [32 k][128 mn]; mn4 = index of the 4-float (16-byte) chunk along M/N (0..31)
+__device__ __forceinline__ uint32_t mn_off(int k, int mn4) {
+    const int kk = k & 3, j = mn4 & 7;
+    return (uint32_t)((mn4 >> 3) * 4096 + (k >> 2) * 512 + kk * 128 + ((((j >> 1) ^ kk) << 5) | ((j & 1) << 4)));
+}
+
+template <int NS>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad_tc_kernel(const m2d_wgrad_args a, const int Ktot, const int Ncols) {
+    constexpr int STAGES = tc_stages(NS);
+    constexpr int STAGE_BYTES = tc_stage_bytes(NS);
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bars[2 * 4 + 1];
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_full = smem_u32(&bars[0]);
+    const uint32_t bar_empty = smem_u32(&bars[4]);
+    const uint32_t bar_acc = smem_u32(&bars[8]);
+
+    const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BNMAX;
+    int bn = Ncols - n0;
+    bn = bn > TC_BNMAX ? TC_BNMAX : ((bn + 31) & ~31);           // MN-major B: whole 32-wide blocks
+    const int tm_cols = bn <= 32 ? 32 : (bn <= 64 ? 64 : 128);
+    const int nsteps = (Ktot + TC_BK - 1) / TC_BK;
+    const int per = (nsteps + gridDim.z - 1) / gridDim.z;
+    const int s_begin = blockIdx.z * per;
+    const int s_end = min(nsteps, s_begin + per);
+    const int nk = max(0, s_end - s_begin);
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, TC_PRODUCERS);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_acc, 1);
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc(smem_u32(&tmem_slot), (uint32_t)tm_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp < 8) {
+        const int j = tid & 7;                 // 16-byte chunk within a 32-wide block
+        const int kl = tid >> 3;               // K row of the block handled by this thread (0..31)
+        // the four (tap, channel) column chunks of the B operand are fixed over the K loop
+        int bt[4], bc[4];
+        bool bok[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int n = n0 + 32 * q + 4 * j;
+            bok[q] = n < Ncols;
+            int nn = bok[q] ? n : 0;
+            bt[q] = nn / a.Cc;
+            bc[q] = nn - bt[q] * a.Cc;
+        }
+        float4 ra[2][4], rb[2][4];
+        auto load = [&](int s, float4* pa, float4* pb) {
+            const int k = s * TC_BK + kl;
+            const bool kok = k < Ktot;
+            const int kc = kok ? k : 0;
+            const int b = kc / a.dy_rows;
+            const int l = kc - b * a.dy_rows;
+            const float* dyr = a.dy + (long long)b * a.dy_bs + (long long)l * a.dy_ld;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int co = m0 + 32 * q + 4 * j;
+                pa[q] = (kok && co < a.Cout) ? __ldg(reinterpret_cast<const float4*>(dyr + co))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const float* xb = a.x + (long long)b * a.x_bs;
+            const int rbase = l * a.sr + a.roff0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = rbase + bt[q] * a.droff;
+                const bool ok = kok && bok[q] && r >= 0 && r < a.x_rows;
+                pb[q] = ok ? __ldg(reinterpret_cast<const float4*>(xb + (long long)r * a.x_ld + bc[q]))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto split_store = [&](uint8_t* hi_tile, uint8_t* lo_tile, uint32_t off, float4 v) {
+            float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+            *reinterpret_cast<float4*>(hi_tile + off) = h;
+            if (NS == 3) {
+                float4 lo = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+                *reinterpret_cast<float4*>(lo_tile + off) = lo;
+            }
+        };
+        auto store = [&](int it, const float4* pa, const float4* pb) {
+            const int st = it % STAGES;
+            const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+            mbar_wait(bar_empty + 8 * st, ph ^ 1);
+            uint8_t* sA = smem + (size_t)st * STAGE_BYTES;
+            uint8_t* sB = sA + (NS == 3 ? 2 : 1) * TC_A_BYTES;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) split_store(sA, sA + TC_A_BYTES, mn_off(kl, 8 * q + j), pa[q]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (32 * q < bn) split_store(sB, sB + TC_B_BYTES, mn_off(kl, 8 * q + j), pb[q]);
+            fence_proxy_async_smem();
+            mbar_arrive(bar_full + 8 * st);
+        };
+        if (nk > 0) load(s_begin, ra[0], rb[0]);
+        for (int it = 0; it < nk; it += 2) {
+            if (it + 1 < nk) load(s_begin + it + 1, ra[1], rb[1]);
+            store(it, ra[0], rb[0]);
+            if (it + 1 < nk) {
+                if (it + 2 < nk) load(s_begin + it + 2, ra[0], rb[0]);
+                store(it + 1, ra[1], rb[1]);
+            }
+        }
+    } else {
+        if (lane == 0) {
+            // both operands MN-major: a_major (bit 15) = b_major (bit 16) = 1
+            const uint32_t idesc = tf32_idesc(TC_BM, bn) | (1u << 15) | (1u << 16);
+            for (int it = 0; it < nk; ++it) {
+                const int st = it % STAGES;
+                const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+                mbar_wait(bar_full + 8 * st, ph);
+                tc_fence_after();
+                const uint32_t sA = smem_base + (uint32_t)st * STAGE_BYTES;
+                const uint32_t sB = sA + (NS == 3 ? 2 : 1) * TC_A_BYTES;
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k) {
+                    const uint64_t ah = sw128b32_desc_mn(sA + 1024 * k), bh = sw128b32_desc_mn(sB + 1024 * k);
+                    if (NS == 3) {
+                        const uint64_t al = sw128b32_desc_mn(sA + TC_A_BYTES + 1024 * k);
+                        const uint64_t bl = sw128b32_desc_mn(sB + TC_B_BYTES + 1024 * k);
+                        umma_tf32(tmem, al, bh, idesc, (it | k) != 0);
+                        umma_tf32(tmem, ah, bl, idesc, 1);
+                        umma_tf32(tmem, ah, bh, idesc, 1);
+                    } else {
+                        umma_tf32(tmem, ah, bh, idesc, (it | k) != 0);
+                    }
+                }
+                umma_commit(bar_empty + 8 * st);
+            }
+            umma_commit(bar_acc);
+        }
+        __syncwarp();
+    }
+
+    float* Cs = reinterpret_cast<float*>(smem);
+    constexpr int CLD = TC_BNMAX + 1;
+    if (warp < 8) {
+        if (nk > 0) {
+            mbar_wait(bar_acc, 0);
+            tc_fence_after();
+            const int q = warp & 3, half = warp >> 2;
+            const int row = 32 * q + lane;
+            const int chunks = bn / 16;
+            for (int ch = half; ch < chunks; ch += 2) {
+                float v[16];
+                tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(16 * ch), v);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) Cs[row * CLD + 16 * ch + u] = v[u];
+            }
+        } else {
+            for (int idx = tid; idx < TC_BM * CLD; idx += TC_PRODUCERS) Cs[idx] = 0.f;
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem, (uint32_t)tm_cols);
+    } else {
+        const int ncols = min(bn, Ncols - n0);
+        float* ws = a.ws + (long long)blockIdx.z * a.Cout * Ncols;
+        for (int idx = tid; idx < TC_BM * ncols; idx += TC_PRODUCERS) {
+            const int rl = idx / ncols, cl = idx - rl * ncols;
+            if (m0 + rl < a.Cout) ws[(long long)(m0 + rl) * Ncols + n0 + cl] = Cs[rl * CLD + cl];
+        }
+    }
+}
+
+template <int NS>
+static int launch_wgrad_tc(const m2d_wgrad_args& a, int Ktot, int Ncols, int splits, cudaStream_t st) {
+    auto kern = wgrad_tc_kernel<NS>;
+    static bool configured = false;
+    const int smem = tc_smem_bytes(NS);
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) {
+            set_error("wgrad_tc: smem attribute (%d B): %s", smem, cudaGetErrorString(e));
+            return M2D_ERR_CUDA;
+        }
+        configured = true;
+    }
+    dim3 grid((unsigned)cdiv(a.Cout, TC_BM), (unsigned)cdiv(Ncols, TC_BNMAX), (unsigned)splits);
+    kern<<<grid, TC_THREADS, smem, st>>>(a, Ktot, Ncols);
+    return check_launch("wgrad_tc");
+}
+
+// Returns 1 when the shape does not qualify (caller uses the SIMT kernel); otherwise the
+// partial sums are in a.ws[splits][Cout][Ncols] and *splits_out is set.
+int wgrad_tc_dispatch(const m2d_wgrad_args& a, int Ktot, int Ncols, int mode, cudaStream_t st, int* splits_out) {
+    const bool ok = a.win_T == 0 && a.Cc % 4 == 0 && a.Cout % 4 == 0 && a.x_ld % 4 == 0 && a.x_bs % 4 == 0 &&
+                    a.dy_ld % 4 == 0 && a.dy_bs % 4 == 0 && aligned16(a.x) && aligned16(a.dy);
+    if (!ok || (long long)a.Cout * Ncols * Ktot < (1ll << 18)) return 1;
+    const long long per = (long long)a.Cout * Ncols;
+    const int nsteps = (int)cdiv(Ktot, TC_BK);
+    const long long tiles = cdiv(a.Cout, TC_BM) * cdiv(Ncols, TC_BNMAX);
+    long long want = cdiv(2 * kNumSMs, tiles);
+    long long cap = a.ws_floats / per;
+    int splits = (int)(want < nsteps / 2 ? want : nsteps / 2);
+    if (splits > cap) splits = (int)cap;
+    if (splits > 128) splits = 128;
+    if (splits < 1) splits = 1;
+    *splits_out = splits;
+    return mode == 3 ? launch_wgrad_tc<3>(a, Ktot, Ncols, splits, st) : launch_wgrad_tc<1>(a, Ktot, Ncols, splits, st);
+}
+
+}  // namespace m2d

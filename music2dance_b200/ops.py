@@ -292,6 +292,20 @@ def adam(p, g, m, v, n, step, lr, b1=0.9, b2=0.999, eps=1e-8, gscale=1.0):
     call("m2d_adam", _p(p), _p(g), _p(m), _p(v), n, _p(step), lr, b1, b2, eps, gscale, _stream())
 
 
+GEMM_MODES = {"fp32": 0, "tf32": 1, "tf32x3": 3}
+
+
+def set_gemm_mode(mode):
+    """Arithmetic of the GEMM family: 'fp32' (CUDA cores), 'tf32' (tcgen05, one TF32 product),
+    'tf32x3' (tcgen05, 3xTF32 split, fp32-grade; the default).  See include/m2d.h."""
+    call("m2d_set_gemm_mode", GEMM_MODES[mode] if isinstance(mode, str) else int(mode))
+
+
+def get_gemm_mode():
+    m = _lib.load().m2d_get_gemm_mode()
+    return {v: k for k, v in GEMM_MODES.items()}[m]
+
+
 def check_device(dev=0):
     call("m2d_check_device", dev)
     return _lib.load().m2d_version()

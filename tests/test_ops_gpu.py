@@ -10,7 +10,15 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+# tolerance floor of the GEMM arithmetic under test (relative to the tensor's max |x|):
+# fp32 CUDA-core kernels and the 3xTF32 tensor-core split differ from torch fp32 by summation
+# order only; single-pass TF32 rounds both operands to 10-bit mantissas (2^-11 relative each).
+MODE_TOL = {"fp32": 3e-5, "tf32x3": 3e-5, "tf32": 3e-3}
+CUR = {"mode": "tf32x3"}
+
+
 def close(a, b, tol=3e-5, what=""):
+    tol = max(tol, MODE_TOL[CUR["mode"]])
     a, b = a.detach().float().cpu(), b.detach().float().cpu()
     assert a.shape == b.shape, (what, a.shape, b.shape)
     scale = max(float(b.abs().max()), 1e-6)
@@ -26,11 +34,15 @@ def ncl(m, B, L, C):
     return m.t.view(B, L, C).permute(0, 2, 1).cpu()
 
 
-@pytest.fixture(scope="module")
-def lib():
+@pytest.fixture(scope="module", params=["fp32", "tf32x3", "tf32"])
+def lib(request):
     from music2dance_b200 import ops
     ops.check_device(0)
-    return ops
+    ops.set_gemm_mode(request.param)
+    CUR["mode"] = request.param
+    yield ops
+    ops.set_gemm_mode("tf32x3")
+    CUR["mode"] = "tf32x3"
 
 
 CONV_CASES = [
@@ -255,15 +267,18 @@ def test_gru(lib, case):
     out = wk.mat("out", 1, B * T, H + 6, None).cols_slice(3, 3 + H)     # strided output slice
     st.fwd(Mat.of(x.to(DEV).view(B * T, I), 1, B * T, I), out, B, T, wk, save=True)
     got = out.t.view(B * T, H + 6)[:, 3:3 + H].view(B, T, H)
-    close(got, y, tol=2e-5, what="gru fwd")
+    # weights ~N(0, 0.15) put the recurrence (spectral radius ~2) in its chaotic regime: single-pass
+    # TF32 rounding of the input projection is amplified ~30x over 50+ steps
+    rt = 10.0 if CUR["mode"] == "tf32" else 1.0
+    close(got, y, tol=2e-5 * rt if rt == 1.0 else 3e-2, what="gru fwd")
     e = wk.mat("e", 1, B * T, H + 6).cols_slice(3, 3 + H)
     e.t.view(B * T, H + 6)[:, 3:3 + H] = dy.view(B * T, H).to(DEV)
     ex = wk.mat("ex", 1, B * T, I)
     wk.acc_reset()
     st.bwd(e, B, T, wk, e_x=ex)
-    close(ex.t.view(B, T, I), xr.grad, tol=5e-5, what="gru dx")
+    close(ex.t.view(B, T, I), xr.grad, tol=5e-5 if rt == 1.0 else 5e-2, what="gru dx")
     for k, v in ref.named_parameters():
-        close(G["g." + k], v.grad, tol=5e-5, what="gru " + k)
+        close(G["g." + k], v.grad, tol=5e-5 if rt == 1.0 else 5e-2, what="gru " + k)
 
 
 @pytest.mark.parametrize("act", [1, 2])
