@@ -90,7 +90,8 @@ typedef struct {
     int act;
     const float* mask; long long m_bs; int m_ld; int mask_mode;
     const float* add; long long a_bs; int a_ld; int add_before_mask;
-    float* ws; long long ws_floats;      /* split-K workspace (may be NULL) */
+    float* ws; long long ws_floats;      /* split-K workspace of the FP32 kernels (may be NULL); the tensor-core
+                                            kernels reduce split-K partials over a thread-block cluster (DSMEM) */
 } m2d_rowconv_args;
 int m2d_rowconv(const m2d_rowconv_args* a, void* stream);
 
@@ -124,6 +125,17 @@ long long m2d_wgrad_min_ws(int Cout, int T, int Cc);
 int m2d_pack_conv_fwd(const float* w, float* wp, int Cout, int Cin, int k, void* stream);
 int m2d_pack_conv_bwd(const float* w, float* wd, int Cout, int Cin, int k, int stride, void* stream);
 
+/* All re-layouts of one network in a single launch.  `table` is an array of n descriptors in
+ * DEVICE memory (pointers are stable, so it is built once).  kind FWD / BWD as above; FULL_BWD is
+ * the backward layout of a convolution whose kernel spans its whole input (fconv, l6, encoder heads),
+ * used as a Linear over (tap, channel):  dst[(t*Cin + ci), co] = w[co, ci, t]. */
+enum { M2D_PACK_FWD = 0, M2D_PACK_BWD = 1, M2D_PACK_FULL_BWD = 2 };
+typedef struct {
+    const float* w; float* dst;
+    int Cout, Cin, k, stride, kind, reserved;
+} m2d_pack_desc;
+int m2d_pack_batch(const m2d_pack_desc* table, int n, void* stream);
+
 /* Backward-data of a Conv1d with ONE input channel (AudioDiscriminator.l1,
  * default.py:298): dx[b,i] = sum_{co,j} dy[b,(i+pad-j)/stride,co] * w[co,0,j]. */
 int m2d_conv_dgrad_c1(const float* dy, int nb, int Lout, int Cout, const float* w, int k,
@@ -136,6 +148,10 @@ int m2d_conv_dgrad_c1(const float* dy, int nb, int Lout, int Cout, const float* 
  * across the cluster's CTAs in shared memory, h exchanged through DSMEM.
  *   h_out[b,t,:H] (row stride ldh)   save[b,t,4H] = r|z|n|(W_hn h + b_hn)
  * ---------------------------------------------------------------------- */
+/* forward implementation: 2 (default) = recurrent weights resident in REGISTERS, warp-shuffle gate
+ * reductions, h pushed to the cluster with st.async + mbarrier transaction counts (one mbarrier wait per
+ * step); 1 = weights in shared memory, cluster barrier per step (any H up to the smem limit). */
+int m2d_set_gru_impl(int impl);
 int m2d_gru_forward(const float* gi, const float* w_hh, const float* b_hh,
                     float* h_out, int ldh, float* save, int B, int T, int H, void* stream);
 /* BPTT: dh_out[b,t,:H] (row stride ldd) upstream gradient; writes dgi, dgh [B,T,3H]. */

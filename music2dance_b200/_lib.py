@@ -62,7 +62,9 @@ SIGNATURES = {
     "m2d_wgrad_min_ws": [_I, _I, _I],
     "m2d_pack_conv_fwd": [_P, _P, _I, _I, _I, _P],
     "m2d_pack_conv_bwd": [_P, _P, _I, _I, _I, _I, _P],
+    "m2d_pack_batch": [_P, _I, _P],
     "m2d_conv_dgrad_c1": [_P, _I, _I, _I, _P, _I, _I, _I, _P, _I, _P],
+    "m2d_set_gru_impl": [_I],
     "m2d_gru_forward": [_P, _P, _P, _P, _I, _P, _I, _I, _I, _P],
     "m2d_gru_backward": [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _P],
     "m2d_colstats": [_P, _I, _L, _I, _P, _P],

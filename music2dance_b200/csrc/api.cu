@@ -1,5 +1,6 @@
 // Library-level entry points: error reporting, version, device check.
 #include "common.cuh"
+#include <cstdlib>
 #include <cstring>
 
 namespace m2d {
@@ -10,7 +11,15 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
-static int g_gemm_mode = M2D_GEMM_TF32X3;
+// default: 3xTF32 on the tensor cores; the environment variable M2D_GEMM (fp32 | tf32 | tf32x3),
+// read once at load, lets a whole test / bench run be repeated in another arithmetic
+static int initial_gemm_mode() {
+    const char* e = getenv("M2D_GEMM");
+    if (e && !strcmp(e, "fp32")) return M2D_GEMM_FP32;
+    if (e && !strcmp(e, "tf32")) return M2D_GEMM_TF32;
+    return M2D_GEMM_TF32X3;
+}
+static int g_gemm_mode = initial_gemm_mode();
 int gemm_mode() { return g_gemm_mode; }
 }  // namespace m2d
 

@@ -201,6 +201,170 @@ gru_bwd_kernel(const float* __restrict__ dh_out, int ldd, const float* __restric
     }
 }
 
+// ---------------------------------------------------------------------------- forward, v2
+// Register-resident recurrence.  Cluster of NC CTAs per batch group; CTA `rank` owns
+// nu <= 32 hidden units.  Thread (unit ul = tid/8, k-part kp = tid%8) keeps the three gate
+// rows of its unit restricted to k in [kp*KS, (kp+1)*KS) in REGISTERS for the whole
+// sequence (3*KS floats), so a step reads only h_{t-1} from shared memory.  Partial dot
+// products are reduced over the 8 k-parts with warp shuffles; lane kp == b then finishes
+// batch entry b of its unit (gates, h_t), stores it, and pushes h_t into every CTA of the
+// cluster with st.async (DSMEM store that completes transaction bytes on the destination's
+// mbarrier).  A CTA starts step t as soon as its own mbarrier has received all H*nb floats
+// of h_{t-1}: one mbarrier wait per step, no cluster barrier, no __syncthreads.
+__device__ __forceinline__ uint32_t gru_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t gru_mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void gru_st_async(uint32_t raddr, float v, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr),
+                 "r"(__float_as_uint(v)), "r"(rbar)
+                 : "memory");
+}
+__device__ __forceinline__ void gru_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void gru_mbar_expect(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gru_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        if (++spins > (1u << 22)) __trap();      // never hang the GPU on a protocol bug
+    }
+}
+
+constexpr int GRU2_BGMAX = 8;
+
+template <int KS, bool SAVE>
+__global__ void __launch_bounds__(256)
+gru_fwd2_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
+                float* __restrict__ h_out, int ldh, float* __restrict__ save, int B, int T, int H, int nu,
+                int BG) {
+    constexpr int KSP = ((KS + 3) / 4) * 4 + 4;          // padded k-part stride: conflict-free float4 reads
+    cg::cluster_group cluster = cg::this_cluster();
+    const int NC = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int b0 = (blockIdx.x / NC) * BG;
+    const int nb = min(BG, B - b0);
+    const int u0 = rank * nu;
+    const int nown = max(0, min(nu, H - u0));
+    __shared__ __align__(16) float hs[2][GRU2_BGMAX][8 * KSP];
+    __shared__ __align__(8) uint64_t bars[2];
+    const int tid = threadIdx.x;
+    const int kp = tid & 7, ul = tid >> 3;
+    const bool active = ul < nown;
+    const int uu = u0 + ul;
+
+    for (int i = tid; i < 2 * GRU2_BGMAX * 8 * KSP; i += 256) (&hs[0][0][0])[i] = 0.f;
+    const uint32_t bar0 = gru_smem_u32(&bars[0]);
+    const uint32_t tx_bytes = 4u * (uint32_t)H * (uint32_t)nb;
+    if (tid == 0) {
+        gru_mbar_init(bar0, 1);
+        gru_mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (T > 1) gru_mbar_expect(bar0 + 8, tx_bytes);      // filled by the sends of step 0
+        if (T > 2) gru_mbar_expect(bar0, tx_bytes);          // filled by the sends of step 1
+    }
+    // recurrent weights -> registers
+    float w[3][KS];
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int i = 0; i < KS; ++i) {
+            const int k = kp * KS + i;
+            w[g][i] = (active && k < H) ? __ldg(w_hh + ((long long)g * H + uu) * H + k) : 0.f;
+        }
+    const bool fin = active && kp < nb;                  // this lane finishes batch entry kp of unit uu
+    float bhr = 0.f, bhz = 0.f, bhn = 0.f;
+    long long row0 = 0;
+    float gir = 0.f, giz = 0.f, gin = 0.f, hprev = 0.f;
+    if (fin) {
+        bhr = b_hh[uu]; bhz = b_hh[H + uu]; bhn = b_hh[2 * H + uu];
+        row0 = (long long)(b0 + kp) * T;
+        const float* g0 = gi + row0 * 3 * H;
+        gir = g0[uu]; giz = g0[H + uu]; gin = g0[2 * H + uu];
+    }
+    const uint32_t hs_addr = gru_smem_u32(&hs[0][0][0]);
+    const uint32_t dst_off = (uint32_t)(((uu / KS) * KSP + (uu % KS)) * 4);   // position of unit uu inside a row of hs
+    __syncthreads();
+    cluster.sync();                                      // every CTA's buffers / barriers are ready
+
+    for (int t = 0; t < T; ++t) {
+        const int cur = t & 1;
+        if (t > 0) {
+            const uint32_t parity = (cur ? (uint32_t)(t >> 1) : (uint32_t)((t >> 1) - 1)) & 1u;
+            gru_mbar_wait(bar0 + 8 * cur, parity);
+            if (tid == 0 && t + 2 <= T - 1) gru_mbar_expect(bar0 + 8 * cur, tx_bytes);
+        }
+        float nr = 0.f, nz = 0.f, nn = 0.f;
+        if (fin && t + 1 < T) {                          // prefetch next step's input projection
+            const float* g1 = gi + (row0 + t + 1) * 3 * H;
+            nr = g1[uu]; nz = g1[H + uu]; nn = g1[2 * H + uu];
+        }
+        float ar = 0.f, az = 0.f, an = 0.f;
+        {   // every lane takes part (full-mask shuffles); lanes without a unit hold zero weights
+            for (int b = 0; b < nb; ++b) {
+                const float4* hv = reinterpret_cast<const float4*>(&hs[cur][b][kp * KSP]);
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f;
+#pragma unroll
+                for (int i4 = 0; i4 < (KS + 3) / 4; ++i4) {
+                    const float4 h4 = hv[i4];
+                    const float hh[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int i = 4 * i4 + e;
+                        if (i < KS) {
+                            if (e & 1) {
+                                q0 = fmaf(w[0][i], hh[e], q0); q1 = fmaf(w[1][i], hh[e], q1); q2 = fmaf(w[2][i], hh[e], q2);
+                            } else {
+                                s0 = fmaf(w[0][i], hh[e], s0); s1 = fmaf(w[1][i], hh[e], s1); s2 = fmaf(w[2][i], hh[e], s2);
+                            }
+                        }
+                    }
+                }
+                s0 += q0; s1 += q1; s2 += q2;
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) {
+                    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                }
+                if (kp == b) { ar = s0; az = s1; an = s2; }
+            }
+        }
+        if (fin) {
+            const float r = sigmoidf_(gir + (ar + bhr));
+            const float z = sigmoidf_(giz + (az + bhz));
+            const float ghn = an + bhn;
+            const float n = tanhf(gin + r * ghn);
+            const float h = (1.f - z) * n + z * hprev;
+            hprev = h;
+            if (t + 1 < T) {
+                const uint32_t off = (uint32_t)((((cur ^ 1) * GRU2_BGMAX + kp) * 8 * KSP) * 4) + dst_off;
+                for (int rk = 0; rk < NC; ++rk)
+                    gru_st_async(gru_mapa(hs_addr + off, (uint32_t)rk), h, gru_mapa(bar0 + 8 * (cur ^ 1), (uint32_t)rk));
+            }
+            const long long row = row0 + t;
+            h_out[row * ldh + uu] = h;
+            if (SAVE) {
+                float* sv = save + row * 4 * H;
+                sv[uu] = r; sv[H + uu] = z; sv[2 * H + uu] = n; sv[3 * H + uu] = ghn;
+            }
+            gir = nr; giz = nz; gin = nn;
+        }
+    }
+    cluster.sync();      // no CTA leaves while a peer could still address its shared memory
+}
+
 template <typename K, typename... Args>
 static int launch_cluster(K kernel, int nblocks, int NC, size_t smem, cudaStream_t st, Args... args) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -232,9 +396,38 @@ static int launch_cluster(K kernel, int nblocks, int NC, size_t smem, cudaStream
 
 using namespace m2d;
 
+template <int KS>
+static int launch_gru2(const float* gi, const float* w_hh, const float* b_hh, float* h_out, int ldh, float* save,
+                       int B, int T, int H, int NC, int nu, int BG, cudaStream_t st) {
+    int groups = (B + BG - 1) / BG;
+    if (save)
+        return launch_cluster(gru_fwd2_kernel<KS, true>, groups * NC, NC, 0, st, gi, w_hh, b_hh, h_out, ldh, save,
+                              B, T, H, nu, BG);
+    return launch_cluster(gru_fwd2_kernel<KS, false>, groups * NC, NC, 0, st, gi, w_hh, b_hh, h_out, ldh, save, B,
+                          T, H, nu, BG);
+}
+
+namespace m2d { int g_gru_impl = 2; }
+extern "C" int m2d_set_gru_impl(int v) { m2d::g_gru_impl = v; return M2D_OK; }
+
 extern "C" int m2d_gru_forward(const float* gi, const float* w_hh, const float* b_hh, float* h_out,
                                int ldh, float* save, int B, int T, int H, void* stream) {
     M2D_REQUIRE(gi && w_hh && b_hh && h_out && B > 0 && T > 0 && H > 0 && ldh >= H, "gru_forward: bad args");
+    if (m2d::g_gru_impl == 2 && H <= 256) {
+        const int NC = H <= 32 ? 1 : (H <= 64 ? 2 : (H <= 128 ? 4 : 8));
+        const int nu = (H + NC - 1) / NC;
+        int BG = B <= 18 ? 1 : (B + 17) / 18;
+        if (BG > GRU2_BGMAX) BG = GRU2_BGMAX;
+        const int ks = (H + 7) / 8;
+        cudaStream_t st = (cudaStream_t)stream;
+        if (ks <= 2) return launch_gru2<2>(gi, w_hh, b_hh, h_out, ldh, save, B, T, H, NC, nu, BG, st);
+        if (ks <= 4) return launch_gru2<4>(gi, w_hh, b_hh, h_out, ldh, save, B, T, H, NC, nu, BG, st);
+        if (ks <= 8) return launch_gru2<8>(gi, w_hh, b_hh, h_out, ldh, save, B, T, H, NC, nu, BG, st);
+        if (ks <= 16) return launch_gru2<16>(gi, w_hh, b_hh, h_out, ldh, save, B, T, H, NC, nu, BG, st);
+        if (ks <= 20) return launch_gru2<20>(gi, w_hh, b_hh, h_out, ldh, save, B, T, H, NC, nu, BG, st);
+        if (ks <= 24) return launch_gru2<24>(gi, w_hh, b_hh, h_out, ldh, save, B, T, H, NC, nu, BG, st);
+        return launch_gru2<32>(gi, w_hh, b_hh, h_out, ldh, save, B, T, H, NC, nu, BG, st);
+    }
     GruPlan p = make_plan(H);
     size_t smem = (size_t)(3 * p.nu * p.HP + 2 * p.BG * p.HP) * sizeof(float);
     M2D_REQUIRE(smem <= 220 * 1024, "gru_forward: hidden size %d needs %zu B of shared memory", H, smem);

@@ -408,6 +408,47 @@ __global__ void pack_bwd_kernel(const float* __restrict__ w, float* __restrict__
     }
 }
 
+// all weight re-layouts of one network in ONE launch: blockIdx.y selects the table entry
+__global__ void __launch_bounds__(256) pack_batch_kernel(const m2d_pack_desc* __restrict__ table) {
+    const m2d_pack_desc d = table[blockIdx.y];
+    const float* __restrict__ w = d.w;
+    float* __restrict__ dst = d.dst;
+    const int Cout = d.Cout, Cin = d.Cin, k = d.k, stride = d.stride;
+    const long long total = (long long)Cout * Cin * k;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        if (d.kind == M2D_PACK_FWD) {                 // dst[co, t*Cin + ci]
+            int ci = (int)(idx % Cin);
+            long long r = idx / Cin;
+            int t = (int)(r % k);
+            int co = (int)(r / k);
+            dst[idx] = w[((long long)co * Cin + ci) * k + t];
+        } else if (d.kind == M2D_PACK_FULL_BWD) {     // dst[(t*Cin + ci), co]
+            int co = (int)(idx % Cout);
+            long long r = idx / Cout;
+            int ci = (int)(r % Cin);
+            int t = (int)(r / Cin);
+            dst[idx] = w[((long long)co * Cin + ci) * k + t];
+        } else {                                      // per stride residue rho: dst_rho[ci, q*Cout + co]
+            long long off = 0;
+            int rho = 0, Trho = 0;
+            for (rho = 0; rho < stride; ++rho) {
+                Trho = (k - rho + stride - 1) / stride;
+                if (Trho < 0) Trho = 0;
+                long long sz = (long long)Cin * Cout * Trho;
+                if (idx < off + sz) break;
+                off += sz;
+            }
+            long long loc = idx - off;
+            int co = (int)(loc % Cout);
+            long long r = loc / Cout;
+            int q = (int)(r % Trho);
+            int ci = (int)(r / Trho);
+            dst[idx] = w[((long long)co * Cin + ci) * k + stride * q + rho];
+        }
+    }
+}
+
 // ------------------------------------------------------------------ dgrad, Cin == 1
 __global__ void __launch_bounds__(256)
 conv_dgrad_c1_kernel(const float* __restrict__ dy, int Lout, int Cout, const float* __restrict__ w,
@@ -440,8 +481,8 @@ conv_dgrad_c1_kernel(const float* __restrict__ dy, int Lout, int Cout, const flo
 }  // namespace m2d
 
 namespace m2d {
-int rowconv_tc_dispatch(const m2d_rowconv_args& a, int M, int mode, cudaStream_t st, int* splits_out);
-int wgrad_tc_dispatch(const m2d_wgrad_args& a, int Ktot, int Ncols, int mode, cudaStream_t st, int* splits_out);
+int rowconv_tc_dispatch(const m2d_rowconv_args& a, int M, int mode, cudaStream_t st);
+int wgrad_tc_dispatch(const m2d_wgrad_args& a, int Ktot, int Ncols, int mode, cudaStream_t st);
 int gemm_mode();
 }  // namespace m2d
 
@@ -466,12 +507,8 @@ extern "C" int m2d_rowconv(const m2d_rowconv_args* ap, void* stream) {
     const int M = (int)Mll;
     const int mode = gemm_mode();
     if (mode != M2D_GEMM_FP32) {
-        int tc_splits = 1;
-        int rc = rowconv_tc_dispatch(a, M, mode, st, &tc_splits);
-        if (rc <= 0) {
-            if (rc == 0 && tc_splits > 1) rc = run_splitk_epilogue(a, M, tc_splits, st);
-            return rc;
-        }
+        int rc = rowconv_tc_dispatch(a, M, mode, st);
+        if (rc <= 0) return rc;
     }
     const bool c1 = a.Cc == 1;
     const bool vec = !c1 && a.Cc % 4 == 0 && a.x_ld % 4 == 0 && a.x_bs % 4 == 0 && a.w_ld % 4 == 0 &&
@@ -525,14 +562,8 @@ extern "C" int m2d_wgrad(const m2d_wgrad_args* ap, void* stream) {
     const int Ktot = (int)Kll;
     const int mode = gemm_mode();
     if (mode != M2D_GEMM_FP32) {
-        int tc_splits = 1;
-        int rc = wgrad_tc_dispatch(a, Ktot, Ncols, mode, st, &tc_splits);
-        if (rc < 0) return rc;
-        if (rc == 0) {
-            int blocks = (int)(cdiv(per, 256) < 8 * kNumSMs ? cdiv(per, 256) : 8 * kNumSMs);
-            wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(a, Ncols, tc_splits);
-            return check_launch("wgrad_reduce");
-        }
+        int rc = wgrad_tc_dispatch(a, Ktot, Ncols, mode, st);
+        if (rc <= 0) return rc;
     }
     const int nsteps = (int)cdiv(Ktot, BK);
     long long tiles = cdiv(a.Cout, 64) * cdiv(Ncols, BN);
@@ -570,6 +601,13 @@ extern "C" int m2d_pack_conv_bwd(const float* w, float* wd, int Cout, int Cin, i
     int blocks = (int)(cdiv(total, 256) < 8 * kNumSMs ? cdiv(total, 256) : 8 * kNumSMs);
     pack_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, wd, Cout, Cin, k, stride);
     return check_launch("pack_conv_bwd");
+}
+
+extern "C" int m2d_pack_batch(const m2d_pack_desc* table, int n, void* stream) {
+    M2D_REQUIRE(table && n > 0, "pack_batch: bad args");
+    dim3 grid(64, (unsigned)n);
+    pack_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table);
+    return check_launch("pack_batch");
 }
 
 extern "C" int m2d_conv_dgrad_c1(const float* dy, int nb, int Lout, int Cout, const float* w, int k,

@@ -113,6 +113,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ bool aligned16d(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 __device__ __forceinline__ float to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -141,6 +142,56 @@ __device__ __forceinline__ uint32_t tf32_idesc(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+constexpr int TC_CLD = TC_BNMAX + 4;      // C staging tile row stride (floats): 16-byte aligned rows, conflict-free float4 access
+
+// TMEM accumulator (128 lanes x bn columns) -> shared C tile.  Warp w reads lanes 32*(w%4)..+31
+// (the tcgen05.ld lane-quarter rule); warps 0-3 take the even 16-column chunks, warps 4-7 the odd ones.
+__device__ __forceinline__ void tmem_to_smem(uint32_t tmem, float* Cs, int warp, int lane, int bn) {
+    const int q = warp & 3, half = warp >> 2;
+    const int row = 32 * q + lane;
+    const int chunks = bn / 16;
+    for (int ch = half; ch < chunks; ch += 2) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(16 * ch), v);
+        float4* dst = reinterpret_cast<float4*>(Cs + row * TC_CLD + 16 * ch);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dst[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+    }
+}
+// named barrier over the 256 producer / epilogue threads (warp 8 does not take part)
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// Split-K over a thread-block cluster: the gridDim.z CTAs of one (m,n) tile form a cluster (1,1,Z).
+// Each keeps its partial C tile in shared memory; after a cluster barrier CTA `rank` sums rows
+// [rank*128/Z, (rank+1)*128/Z) over all Z tiles through distributed shared memory (fixed order:
+// deterministic), applies the epilogue and stores.  No global workspace, no second launch.
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ float4 dsmem_ld4(uint32_t local_addr, uint32_t rank) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
+    return v;
+}
+// sum of the 4-float chunk at (row, c4) of the C tiles of all Z CTAs of the cluster
+__device__ __forceinline__ void cluster_reduce4(const float* Cs, int rl, int c4, int Z, float* v) {
+    const uint32_t addr = smem_u32(Cs + rl * TC_CLD + c4);
+    v[0] = v[1] = v[2] = v[3] = 0.f;
+    for (int z = 0; z < Z; ++z) {
+        const float4 t = dsmem_ld4(addr, (uint32_t)z);
+        v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+    }
+}
+
 struct TcRow {          // per output row of the CTA tile
     long long base;     // element offset of the row's batch (or sequence) in x; -1: row beyond M
     int r0;             // i*sr + roff0
@@ -160,7 +211,7 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms need 1 KiB alignment
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_full = smem_u32(&bars[0]);          // + 8*s
     const uint32_t bar_empty = smem_u32(&bars[4]);         // + 8*s
@@ -353,60 +404,156 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
     }
 
     // ---------------------------------------------------------------------- epilogue
-    float* Cs = reinterpret_cast<float*>(smem);      // [128][129], reuses the (drained) stages
-    constexpr int CLD = TC_BNMAX + 1;
+    float* Cs = reinterpret_cast<float*>(smem);      // [128][TC_CLD], reuses the (drained) stages
     if (warp < 8) {
         if (nk > 0) {
             mbar_wait(bar_acc, 0);
             tc_fence_after();
-            const int q = warp & 3, half = warp >> 2;      // TMEM lanes 32q..32q+31, column half
-            const int row = 32 * q + lane;
-            const int chunks = bn / 16;
-            for (int ch = half; ch < chunks; ch += 2) {
-                float v[16];
-                tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(16 * ch), v);
-#pragma unroll
-                for (int u = 0; u < 16; ++u) Cs[row * CLD + 16 * ch + u] = v[u];
-            }
+            tmem_to_smem(tmem, Cs, warp, lane, bn);
         } else {
-            for (int idx = tid; idx < TC_BM * CLD; idx += TC_PRODUCERS) Cs[idx] = 0.f;
+            for (int idx = tid; idx < TC_BM * TC_CLD; idx += TC_PRODUCERS) Cs[idx] = 0.f;
         }
         tc_fence_before();
     }
     __syncthreads();
+    const int Z = (int)gridDim.z;                    // == cluster size along z
     if (warp == 8) {
         tc_fence_after();
         tmem_dealloc(tmem, (uint32_t)tm_cols);
-    } else {
-        const int ncols = min(bn, a.N - n0);
-        const bool split = gridDim.z > 1;
-        float* ws = split ? a.ws + (long long)blockIdx.z * M * a.N : nullptr;
-        // consecutive threads walk along n: coalesced stores / mask / residual loads
-        for (int idx = tid; idx < TC_BM * ncols; idx += TC_PRODUCERS) {
-            const int rl = idx / ncols, cl = idx - rl * ncols;
-            const TcRow r = rows[rl];
-            if (r.base < 0) continue;
-            float v = Cs[rl * CLD + cl];
-            const int n = n0 + cl;
-            if (split) {
-                ws[(long long)(m0 + rl) * a.N + n] = v;
-                continue;
+        if (Z > 1) {
+            cluster_sync_all();                       // partial tiles ready
+            cluster_sync_all();                       // peers done reading this CTA's tile
+        }
+        return;
+    }
+    const int ncols = min(bn, a.N - n0);
+    // thread -> (row group, 4-column chunk): P lanes per row, P = pow2 >= ncols/4
+    const int cpr = (ncols + 3) >> 2;
+    int P = 1;
+    while (P < cpr) P <<= 1;
+    const int rpi = TC_PRODUCERS / P;                 // rows per iteration over the CTA
+    const int c4 = (tid & (P - 1)) * 4, rsub0 = tid / P;
+    const bool cvalid = c4 < ncols;
+    const bool vecN = (a.N & 3) == 0 && ncols - c4 >= 4;
+    int row_lo = 0, row_hi = TC_BM;
+    if (Z > 1) {
+        cluster_sync_all();
+        const int RB = TC_BM / Z;
+        row_lo = (int)cluster_rank() * RB;
+        row_hi = row_lo + RB;
+    }
+    const bool vy = vecN && (a.y_ld & 3) == 0 && (a.y_bs & 3) == 0 && aligned16d(a.y) &&
+                    (!a.y2 || aligned16d(a.y2)) &&
+                    (!a.mask_mode || ((a.m_ld & 3) == 0 && (a.m_bs & 3) == 0 && aligned16d(a.mask))) &&
+                    (!a.add || ((a.a_ld & 3) == 0 && (a.a_bs & 3) == 0 && aligned16d(a.add)));
+    for (int rl = row_lo + rsub0; rl < row_hi; rl += rpi) {
+        if (!cvalid) continue;
+        const TcRow r = rows[rl];
+        if (r.base < 0) continue;
+        const int n = n0 + c4;
+        float v[4];
+        if (Z > 1) {
+            cluster_reduce4(Cs, rl, c4, Z, v);
+        } else {
+            const float4 t = *reinterpret_cast<const float4*>(Cs + rl * TC_CLD + c4);
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        }
+        const long long yo = r.b * a.y_bs + (long long)r.i * a.y_ld + n;
+        const long long mo = a.mask_mode ? r.b * a.m_bs + (long long)r.i * a.m_ld + n : 0;
+        const long long ao = a.add ? r.b * a.a_bs + (long long)r.i * a.a_ld + n : 0;
+        if (vy) {
+            float ad[4] = {0.f, 0.f, 0.f, 0.f}, mk[4] = {1.f, 1.f, 1.f, 1.f};
+            if (a.add) {
+                float4 t = *reinterpret_cast<const float4*>(a.add + ao);
+                ad[0] = t.x; ad[1] = t.y; ad[2] = t.z; ad[3] = t.w;
             }
-            if (a.bias) v += __ldg(a.bias + n);
-            v = apply_act(v, a.act);
-            if (a.add && a.add_before_mask) v += a.add[r.b * a.a_bs + (long long)r.i * a.a_ld + n];
-            if (a.y2) a.y2[r.b * a.y_bs + (long long)r.i * a.y_ld + n] = v;
-            if (a.mask_mode) v *= act_deriv(a.mask[r.b * a.m_bs + (long long)r.i * a.m_ld + n], a.mask_mode);
-            if (a.add && !a.add_before_mask) v += a.add[r.b * a.a_bs + (long long)r.i * a.a_ld + n];
-            a.y[r.b * a.y_bs + (long long)r.i * a.y_ld + n] = v;
+            if (a.mask_mode) {
+                float4 t = *reinterpret_cast<const float4*>(a.mask + mo);
+                mk[0] = act_deriv(t.x, a.mask_mode); mk[1] = act_deriv(t.y, a.mask_mode);
+                mk[2] = act_deriv(t.z, a.mask_mode); mk[3] = act_deriv(t.w, a.mask_mode);
+            }
+            float w2[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float x = v[u];
+                if (a.bias) x += __ldg(a.bias + n + u);
+                x = apply_act(x, a.act);
+                if (a.add && a.add_before_mask) x += ad[u];
+                w2[u] = x;
+                x *= mk[u];
+                if (a.add && !a.add_before_mask) x += ad[u];
+                v[u] = x;
+            }
+            if (a.y2) *reinterpret_cast<float4*>(a.y2 + yo) = make_float4(w2[0], w2[1], w2[2], w2[3]);
+            *reinterpret_cast<float4*>(a.y + yo) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+            for (int u = 0; u < 4 && c4 + u < ncols; ++u) {
+                float x = v[u];
+                if (a.bias) x += __ldg(a.bias + n + u);
+                x = apply_act(x, a.act);
+                if (a.add && a.add_before_mask) x += a.add[ao + u];
+                if (a.y2) a.y2[yo + u] = x;
+                if (a.mask_mode) x *= act_deriv(a.mask[mo + u], a.mask_mode);
+                if (a.add && !a.add_before_mask) x += a.add[ao + u];
+                a.y[yo + u] = x;
+            }
         }
     }
+    if (Z > 1) cluster_sync_all();                   // keep this CTA's tile alive until every peer has read it
+}
+
+// Launch with the split-K CTAs of a tile grouped into a (1,1,Z) thread-block cluster.
+template <typename K, typename... Args>
+static int launch_clustered(const char* what, K kern, dim3 grid, int smem, int Z, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = (unsigned)Z;
+    cfg.attrs = attr;
+    cfg.numAttrs = Z > 1 ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
+    if (e != cudaSuccess) {
+        set_error("%s: launch (grid %u,%u,%u cluster z=%d): %s", what, grid.x, grid.y, grid.z, Z, cudaGetErrorString(e));
+        return M2D_ERR_CUDA;
+    }
+    return M2D_OK;
+}
+
+// largest power-of-two split <= want that the device can co-schedule as one cluster of this kernel
+template <typename K>
+static int max_cluster_z(K kern, int smem, int want, bool allow16) {
+    int z = 1;
+    while (z * 2 <= want && z * 2 <= (allow16 ? 16 : 8)) z *= 2;
+    for (; z > 1; z /= 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(1, 1, (unsigned)z);
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = (unsigned)z;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) break;
+        (void)cudaGetLastError();
+    }
+    return z;
 }
 
 template <int NS, bool VEC, bool C1>
-static int launch_tc(const m2d_rowconv_args& a, int M, int nsteps, int cchunks, int splits, cudaStream_t st) {
+static int launch_tc(const m2d_rowconv_args& a, int M, int nsteps, int cchunks, int want_splits, cudaStream_t st) {
     auto kern = rowconv_tc_kernel<NS, VEC, C1>;
     static bool configured = false;
+    static int zmax = 1;
     const int smem = tc_smem_bytes(NS);
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -414,16 +561,18 @@ static int launch_tc(const m2d_rowconv_args& a, int M, int nsteps, int cchunks, 
             set_error("rowconv_tc: smem attribute (%d B): %s", smem, cudaGetErrorString(e));
             return M2D_ERR_CUDA;
         }
+        zmax = max_cluster_z(kern, smem, 8, false);
         configured = true;
     }
-    dim3 grid((unsigned)cdiv(M, TC_BM), (unsigned)cdiv(a.N, TC_BNMAX), (unsigned)splits);
-    kern<<<grid, TC_THREADS, smem, st>>>(a, M, nsteps, cchunks);
-    return check_launch("rowconv_tc");
+    int Z = 1;
+    while (Z * 2 <= want_splits && Z * 2 <= zmax) Z *= 2;
+    dim3 grid((unsigned)cdiv(M, TC_BM), (unsigned)cdiv(a.N, TC_BNMAX), (unsigned)Z);
+    return launch_clustered("rowconv_tc", kern, grid, smem, Z, st, a, M, nsteps, cchunks);
 }
 
 // Called by m2d_rowconv when the tensor-core path is selected.  Returns 1 if the shape is
 // not worth a tensor-core launch (caller falls through to the SIMT kernel), <= 0 otherwise.
-int rowconv_tc_dispatch(const m2d_rowconv_args& a, int M, int mode, cudaStream_t st, int* splits_out) {
+int rowconv_tc_dispatch(const m2d_rowconv_args& a, int M, int mode, cudaStream_t st) {
     const bool c1 = a.Cc == 1;
     const long long K = (long long)a.T * a.Cc;
     if (a.N < 8 || (long long)M * a.N * K < (1ll << 18)) return 1;
@@ -433,14 +582,11 @@ int rowconv_tc_dispatch(const m2d_rowconv_args& a, int M, int mode, cudaStream_t
     const int nsteps = c1 ? (int)cdiv(a.T, TC_BK) : a.T * cchunks;
     const long long tiles = cdiv(M, TC_BM) * cdiv(a.N, TC_BNMAX);
     int splits = 1;
-    if (a.ws && tiles < kNumSMs && nsteps >= 8) {
+    if (tiles < kNumSMs && nsteps >= 8) {          // few tiles, long K: split K over a cluster
         long long want = cdiv(kNumSMs, tiles);
-        long long cap = a.ws_floats / ((long long)M * a.N);
         splits = (int)(want < nsteps / 4 ? want : nsteps / 4);
-        if (splits > cap) splits = (int)cap;
         if (splits < 1) splits = 1;
     }
-    *splits_out = splits;
     int rc;
     if (mode == 3) {
         if (c1) rc = launch_tc<3, false, true>(a, M, nsteps, cchunks, splits, st);
@@ -490,7 +636,7 @@ wgrad_tc_kernel(const m2d_wgrad_args a, const int Ktot, const int Ncols) {
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms need 1 KiB alignment
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_full = smem_u32(&bars[0]);
     const uint32_t bar_empty = smem_u32(&bars[4]);
@@ -621,43 +767,73 @@ wgrad_tc_kernel(const m2d_wgrad_args a, const int Ktot, const int Ncols) {
     }
 
     float* Cs = reinterpret_cast<float*>(smem);
-    constexpr int CLD = TC_BNMAX + 1;
     if (warp < 8) {
         if (nk > 0) {
             mbar_wait(bar_acc, 0);
             tc_fence_after();
-            const int q = warp & 3, half = warp >> 2;
-            const int row = 32 * q + lane;
-            const int chunks = bn / 16;
-            for (int ch = half; ch < chunks; ch += 2) {
-                float v[16];
-                tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(16 * ch), v);
-#pragma unroll
-                for (int u = 0; u < 16; ++u) Cs[row * CLD + 16 * ch + u] = v[u];
-            }
+            tmem_to_smem(tmem, Cs, warp, lane, bn);
         } else {
-            for (int idx = tid; idx < TC_BM * CLD; idx += TC_PRODUCERS) Cs[idx] = 0.f;
+            for (int idx = tid; idx < TC_BM * TC_CLD; idx += TC_PRODUCERS) Cs[idx] = 0.f;
         }
         tc_fence_before();
     }
     __syncthreads();
+    const int Z = (int)gridDim.z;
     if (warp == 8) {
         tc_fence_after();
         tmem_dealloc(tmem, (uint32_t)tm_cols);
-    } else {
-        const int ncols = min(bn, Ncols - n0);
-        float* ws = a.ws + (long long)blockIdx.z * a.Cout * Ncols;
-        for (int idx = tid; idx < TC_BM * ncols; idx += TC_PRODUCERS) {
-            const int rl = idx / ncols, cl = idx - rl * ncols;
-            if (m0 + rl < a.Cout) ws[(long long)(m0 + rl) * Ncols + n0 + cl] = Cs[rl * CLD + cl];
+        if (Z > 1) {
+            cluster_sync_all();
+            cluster_sync_all();
+        }
+        return;
+    }
+    // Ncols = T*Cc is a multiple of 4 here (Cc % 4 == 0), so 4-column chunks never straddle the tile edge
+    const int ncols = min(bn, Ncols - n0);
+    const int cpr = ncols >> 2;
+    int P = 1;
+    while (P < cpr) P <<= 1;
+    const int rpi = TC_PRODUCERS / P;
+    const int c4 = (tid & (P - 1)) * 4, rsub0 = tid / P;
+    const bool cvalid = c4 < ncols;
+    int row_lo = 0, row_hi = TC_BM;
+    if (Z > 1) {
+        cluster_sync_all();
+        const int RB = TC_BM / Z;
+        row_lo = (int)cluster_rank() * RB;
+        row_hi = row_lo + RB;
+    }
+    // final values -> PyTorch parameter layout (Cout, Cc, T):  dw = beta*dw + scale*sum
+    const int n = n0 + c4;
+    const int t = cvalid ? n / a.Cc : 0;
+    const int c = n - t * a.Cc;
+    for (int rl = row_lo + rsub0; rl < row_hi; rl += rpi) {
+        const int co = m0 + rl;
+        if (!cvalid || co >= a.Cout) continue;
+        float v[4];
+        if (Z > 1) {
+            cluster_reduce4(Cs, rl, c4, Z, v);
+        } else {
+            const float4 q = *reinterpret_cast<const float4*>(Cs + rl * TC_CLD + c4);
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        }
+        float* d = a.dw + ((long long)co * a.Cc + c) * a.T + t;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float x = v[u] * a.scale;
+            float* du = d + (long long)u * a.T;
+            if (a.beta != 0.f) x += a.beta * *du;
+            *du = x;
         }
     }
+    if (Z > 1) cluster_sync_all();
 }
 
 template <int NS>
-static int launch_wgrad_tc(const m2d_wgrad_args& a, int Ktot, int Ncols, int splits, cudaStream_t st) {
+static int launch_wgrad_tc(const m2d_wgrad_args& a, int Ktot, int Ncols, int want_splits, cudaStream_t st) {
     auto kern = wgrad_tc_kernel<NS>;
     static bool configured = false;
+    static int zmax = 1;
     const int smem = tc_smem_bytes(NS);
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -665,29 +841,29 @@ static int launch_wgrad_tc(const m2d_wgrad_args& a, int Ktot, int Ncols, int spl
             set_error("wgrad_tc: smem attribute (%d B): %s", smem, cudaGetErrorString(e));
             return M2D_ERR_CUDA;
         }
+        // weight gradients have few output tiles and a long K: allow the non-portable cluster size 16
+        bool np = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+        (void)cudaGetLastError();
+        zmax = max_cluster_z(kern, smem, 16, np);
         configured = true;
     }
-    dim3 grid((unsigned)cdiv(a.Cout, TC_BM), (unsigned)cdiv(Ncols, TC_BNMAX), (unsigned)splits);
-    kern<<<grid, TC_THREADS, smem, st>>>(a, Ktot, Ncols);
-    return check_launch("wgrad_tc");
+    int Z = 1;
+    while (Z * 2 <= want_splits && Z * 2 <= zmax) Z *= 2;
+    dim3 grid((unsigned)cdiv(a.Cout, TC_BM), (unsigned)cdiv(Ncols, TC_BNMAX), (unsigned)Z);
+    return launch_clustered("wgrad_tc", kern, grid, smem, Z, st, a, Ktot, Ncols);
 }
 
-// Returns 1 when the shape does not qualify (caller uses the SIMT kernel); otherwise the
-// partial sums are in a.ws[splits][Cout][Ncols] and *splits_out is set.
-int wgrad_tc_dispatch(const m2d_wgrad_args& a, int Ktot, int Ncols, int mode, cudaStream_t st, int* splits_out) {
+// Returns 1 when the shape does not qualify (caller uses the SIMT kernel); otherwise dw is final
+// (split-K partials are reduced across the cluster inside the kernel).
+int wgrad_tc_dispatch(const m2d_wgrad_args& a, int Ktot, int Ncols, int mode, cudaStream_t st) {
     const bool ok = a.win_T == 0 && a.Cc % 4 == 0 && a.Cout % 4 == 0 && a.x_ld % 4 == 0 && a.x_bs % 4 == 0 &&
                     a.dy_ld % 4 == 0 && a.dy_bs % 4 == 0 && aligned16(a.x) && aligned16(a.dy);
     if (!ok || (long long)a.Cout * Ncols * Ktot < (1ll << 18)) return 1;
-    const long long per = (long long)a.Cout * Ncols;
     const int nsteps = (int)cdiv(Ktot, TC_BK);
     const long long tiles = cdiv(a.Cout, TC_BM) * cdiv(Ncols, TC_BNMAX);
     long long want = cdiv(2 * kNumSMs, tiles);
-    long long cap = a.ws_floats / per;
     int splits = (int)(want < nsteps / 2 ? want : nsteps / 2);
-    if (splits > cap) splits = (int)cap;
-    if (splits > 128) splits = 128;
     if (splits < 1) splits = 1;
-    *splits_out = splits;
     return mode == 3 ? launch_wgrad_tc<3>(a, Ktot, Ncols, splits, st) : launch_wgrad_tc<1>(a, Ktot, Ncols, splits, st);
 }
 

@@ -47,6 +47,15 @@ class FlatParams:
                 self.params[n] = p
                 if not _DEAD.search(n):
                     self.G[n] = self.grad[off:off + p.numel()].view(p.shape)
+        # BatchNorm step counters: views of one int64 buffer so that a forward bumps them all at once
+        nbt = [(n, b) for n, b in module.named_buffers() if n.endswith("num_batches_tracked")]
+        if nbt:
+            flat_nbt = torch.zeros(len(nbt), dtype=torch.int64, device=dev)
+            with torch.no_grad():
+                for i, (n, b) in enumerate(nbt):
+                    flat_nbt[i] = b
+                    b.data = flat_nbt[i]
+            self.P["__nbt_flat__"] = flat_nbt
         for n, b in module.named_buffers():
             self.P[n] = b
         self.names = [n for n, _ in named]             # original parameter order

@@ -87,6 +87,20 @@ class ConvLayer:
     def wf(self):
         return self.w if self.wp is None else self.wp
 
+    def pack_entries(self):
+        """(w, dst, Cout, Cin, k, stride, kind) rows of the batched re-layout table (ops.pack_batch)."""
+        e = []
+        if self.wp is not None:
+            e.append((self.w, self.wp, self.Cout, self.Cin, self.k, 1, ops.PACK_FWD))
+        if self.wd is not None:
+            if self.k == 1:
+                e.append((self.w, self.wd, self.Cout, self.Cin, 1, 1, ops.PACK_BWD))
+            elif self.full:
+                e.append((self.w, self.wd, self.Cout, self.Cin, self.k, 1, ops.PACK_FULL_BWD))
+            else:
+                e.append((self.w, self.wd, self.Cout, self.Cin, self.k, self.s, ops.PACK_BWD))
+        return e
+
     def pack(self):
         if self.wp is not None:
             ops.pack_conv_fwd(self.w, self.wp, self.Cout, self.Cin, self.k)
@@ -204,6 +218,18 @@ class ConvBNAct:
         cv.wgrad(dc, self.x, wk.scratch, win=win, acc=wk.acc_slot(cv.Cout))
         if e_x is not None:
             cv.dgrad(dc, e_x, ws=wk.scratch, **dg)
+
+
+def _pack_net(net):
+    """Refresh every packed weight copy of a network with ONE kernel launch (the table of
+    (source, destination, shape, kind) rows lives in device memory and is built once)."""
+    tab = getattr(net, "_pack_tab", None)
+    if tab is None:
+        entries = [e for c in net.convs() for e in c.pack_entries()]
+        tab = ops.pack_table(entries, net.dev) if entries else (None, 0)
+        net._pack_tab = tab
+    if tab[1]:
+        ops.pack_batch(tab[0], tab[1])
 
 
 # ===========================================================================
@@ -468,6 +494,7 @@ class GeneratorNet:
         self.last = _conv_from(P, G, "decoder.lastfc", S, O, 1, 1, 0, 1)
         self.wk = Workspace(self.dev)
         self.nbt = [v for k, v in P.items() if k.endswith("num_batches_tracked")]
+        self.nbt_flat = P.get("__nbt_flat__")
 
     def convs(self):
         c = self.enc.convs() + self.rnn.convs() + self.nrnn.convs() + [self.fc1, self.last]
@@ -476,8 +503,7 @@ class GeneratorNet:
         return c
 
     def pack(self):
-        for c in self.convs():
-            c.pack()
+        _pack_net(self)
 
     def window(self, T):
         cfg = self.cfg
@@ -523,8 +549,11 @@ class GeneratorNet:
         self.last.fwd(d, fake, ws=wk.scratch)
         self.d_last = d
         if train:
-            for t in self.nbt:
-                t.add_(1)
+            if self.nbt_flat is not None:
+                self.nbt_flat.add_(1)            # every num_batches_tracked is a view of this buffer
+            else:
+                for t in self.nbt:
+                    t.add_(1)
         return fake
 
     def backward(self, dfake):
@@ -602,8 +631,7 @@ class CriticNet:
         return c + [self.fc1, self.fc2]
 
     def pack(self):
-        for c in self.convs():
-            c.pack()
+        _pack_net(self)
 
     # ---------------------------------------------------------------- pose branch
     def pose_fwd(self, X, n, tag):

@@ -136,7 +136,7 @@ def wgrad(dy, x, dw, *, Cout, T, Cc, sr=1, roff0=0, droff=1, scale=1.0, beta=0.0
     a.dw = _p(dw)
     a.scale, a.beta = scale, beta
     a.ws, a.ws_floats = ws.data_ptr(), ws.numel()
-    LAUNCHES[0] += 2
+    LAUNCHES[0] += 1
     call("m2d_wgrad", C.byref(a), _stream())
 
 
@@ -148,6 +148,26 @@ def pack_conv_fwd(w, wp, Cout, Cin, k):
 def pack_conv_bwd(w, wd, Cout, Cin, k, stride):
     LAUNCHES[0] += 1
     call("m2d_pack_conv_bwd", _p(w), _p(wd), Cout, Cin, k, stride, _stream())
+
+
+PACK_FWD, PACK_BWD, PACK_FULL_BWD = 0, 1, 2
+
+
+def pack_table(entries, device):
+    """entries: (w tensor, dst tensor, Cout, Cin, k, stride, kind) -> device table for pack_batch."""
+    import numpy as np
+    dt = np.dtype([("w", "<u8"), ("dst", "<u8"), ("Cout", "<i4"), ("Cin", "<i4"), ("k", "<i4"), ("stride", "<i4"),
+                   ("kind", "<i4"), ("reserved", "<i4")])
+    arr = np.zeros(len(entries), dtype=dt)
+    for i, (w, dst, Cout, Cin, k, stride, kind) in enumerate(entries):
+        arr[i] = (w.data_ptr(), dst.data_ptr(), Cout, Cin, k, stride, kind, 0)
+    t = torch.from_numpy(arr.view(np.uint8).copy()).to(device)
+    return t, len(entries)
+
+
+def pack_batch(table, n):
+    LAUNCHES[0] += 1
+    call("m2d_pack_batch", _p(table), n, _stream())
 
 
 def conv_dgrad_c1(dy, w, dx, *, nb, Lout, Cout, k, stride, pad, Lin):
@@ -304,6 +324,10 @@ def set_gemm_mode(mode):
 def get_gemm_mode():
     m = _lib.load().m2d_get_gemm_mode()
     return {v: k for k, v in GEMM_MODES.items()}[m]
+
+
+def set_gru_impl(v):
+    call("m2d_set_gru_impl", int(v))
 
 
 def check_device(dev=0):

@@ -19,7 +19,7 @@ from __future__ import annotations
 
 import torch
 
-from . import ops
+from . import dp, ops
 from .ops import Mat
 from .wgan import critic_forward, gradient_penalty_pass, rows, wasserstein_backward
 
@@ -44,9 +44,7 @@ class Phase3Trainer:
             self.de.net.pack()
         self.ge.packed_version, self.de.packed_version = self.ge.fp.version(), self.de.fp.version()
         self.pg = process_group
-        self.world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            self.world = torch.distributed.get_world_size(process_group)
+        self.world = dp.world_size(process_group)
         B, T, O, A, Nz, nc = self.B, self.T, self.O, self.A, self.Nz, self.nc
         f = dict(dtype=torch.float32, device=dev)
         # staged inputs of one train step (device resident)
@@ -72,7 +70,7 @@ class Phase3Trainer:
     # ------------------------------------------------------------------ pieces
     def _all_reduce(self, flat):
         if self.world > 1:
-            torch.distributed.all_reduce(flat, group=self.pg)
+            dp.all_reduce_sum_(flat, self.pg)
 
     def _adam(self, eng, m, v, step, lr):
         n = eng.fp.n_live_padded

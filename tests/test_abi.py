@@ -1,0 +1,69 @@
+"""CPU: the C-ABI shared library builds, loads, and exports every symbol include/m2d.h declares;
+the ctypes signature table covers exactly that set.  No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "m2d.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(m2d_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    path = ge.build()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    names = declared_symbols()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/m2d.h but not exported by libm2d_b200.so"
+
+
+def test_ctypes_table_matches_header():
+    from music2dance_b200 import _lib
+    table = set(_lib.SIGNATURES) | {"m2d_last_error"}
+    assert table == set(declared_symbols())
+
+
+def test_struct_layouts_match_header():
+    """Field order of the two argument structs must follow the header (ctypes mirrors it by hand)."""
+    from music2dance_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "m2d.h")).read()
+    for cname, cls in (("m2d_rowconv_args", _lib.RowConvArgs), ("m2d_wgrad_args", _lib.WgradArgs)):
+        end = src.index("} " + cname + ";")
+        body = src[src.rindex("typedef struct {", 0, end) + len("typedef struct {"):end]
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            # "const float* x" / "long long x_bs" / "int N, T, Cc"
+            names = re.sub(r"^(const\s+)?(float\s*\*|double\s*\*|long long|int|float)\s*", "", decl)
+            fields += [n.strip().lstrip("*").strip() for n in names.split(",")]
+        assert fields == [f[0] for f in cls._fields_], (cname, fields)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "music2dance_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith(".py"):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), os.path.join(dp, f)
+
+
+def test_cpu_inputs_fail_loudly():
+    import pytest
+    import torch
+    from music2dance_b200 import losses, utils
+    with pytest.raises(RuntimeError):
+        losses.tv_loss(torch.zeros(1, 3, 4))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            utils.slice_audio_batch(torch.zeros(2, 6400), 3200, 640, 2560)

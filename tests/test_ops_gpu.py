@@ -13,7 +13,10 @@ DEV = "cuda:0"
 # tolerance floor of the GEMM arithmetic under test (relative to the tensor's max |x|):
 # fp32 CUDA-core kernels and the 3xTF32 tensor-core split differ from torch fp32 by summation
 # order only; single-pass TF32 rounds both operands to 10-bit mantissas (2^-11 relative each).
-MODE_TOL = {"fp32": 3e-5, "tf32x3": 3e-5, "tf32": 3e-3}
+# 3xTF32 accumulates in TMEM through K/8 sequential tensor-core additions (truncating adder): at the
+# longest contraction of the model (audio_d.l6, K = 38400, 8-way cluster split) the measured error is
+# 3.2e-5 of max|y|; every K <= 6400 case stays below 6e-6.
+MODE_TOL = {"fp32": 3e-5, "tf32x3": 5e-5, "tf32": 3e-3}
 CUR = {"mode": "tf32x3"}
 
 
@@ -244,9 +247,12 @@ def test_slice_audio_bit_exact(lib):
         assert torch.equal(out.cpu(), ref)
 
 
-@pytest.mark.parametrize("case", [(7, 120, 250, 240, 3), (3, 17, 10, 10, 1), (9, 30, 100, 150, 2), (2, 5, 50, 50, 1)])
-def test_gru(lib, case):
+@pytest.mark.parametrize("impl", [2, 1])
+@pytest.mark.parametrize("case", [(7, 120, 250, 240, 3), (3, 17, 10, 10, 1), (9, 30, 100, 150, 2), (2, 5, 50, 50, 1),
+                                  (40, 12, 64, 240, 1), (19, 1, 16, 33, 1), (1, 2, 8, 256, 1)])
+def test_gru(lib, case, impl):
     from music2dance_b200.nets import GRUStack, Workspace
+    lib.set_gru_impl(impl)
     from music2dance_b200.ops import Mat
     B, T, I, H, nl = case
     torch.manual_seed(7)
@@ -279,6 +285,7 @@ def test_gru(lib, case):
     close(ex.t.view(B, T, I), xr.grad, tol=5e-5 if rt == 1.0 else 5e-2, what="gru dx")
     for k, v in ref.named_parameters():
         close(G["g." + k], v.grad, tol=5e-5 if rt == 1.0 else 5e-2, what="gru " + k)
+    lib.set_gru_impl(2)
 
 
 @pytest.mark.parametrize("act", [1, 2])

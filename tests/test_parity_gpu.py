@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import phase3_oracle as O
-from tests.parity import (ALPHA_SEED, B_GOLD, TOL_CHAINED, TOL_FP32, TOL_GEN_GRAD_E2E, TOL_GRAD, TOL_KINK_L2, TOL_KINK_MAX,
+from tests.parity import (ALPHA_SEED, B_GOLD, TOL_CHAINED, TOL_DRIFT_BUF, TOL_DRIFT_LR, TOL_FP32, TOL_GRAD_BIAS, TOL_GEN_GRAD_E2E, TOL_GRAD, TOL_KINK_L2, TOL_KINK_MAX,
                           TOL_NORTH_STAR, VARIANTS,
                           digest_check, load_golden, scalar_check)
 
@@ -80,7 +80,8 @@ def test_dropin_step_vs_reference_fixtures(variant, state):
     for k, p in critic.named_parameters():
         assert p.grad is not None or k == "fc2.bias", k
         g = p.grad if p.grad is not None else torch.zeros_like(p)
-        digest_check(g, gold, f"{state}/critic/grad/{k}", TOL_GRAD, f"critic grad {k}", abs_floor=1e-4, kinks=True)
+        digest_check(g, gold, f"{state}/critic/grad/{k}", TOL_GRAD_BIAS if k.endswith(".bias") else TOL_GRAD,
+                     f"critic grad {k}", abs_floor=1e-4, kinks=True)
     for k, v in gen.state_dict().items():                       # Q2: running stats advanced by the forward
         if "running" in k or "num_batches" in k:
             digest_check(v, gold, f"{state}/critic/genbuf/{k}", TOL_FP32, f"bn buffer {k}")
@@ -224,7 +225,10 @@ def test_fused_trainer_vs_oracle(variant, B, nc, graphs):
                 assert int(v) == int(P[k]), k
                 continue
             d = (v.cpu() - P[k]).abs()
-            assert float(d.mean()) < 0.05 * lr * steps + 1e-6 * float(P[k].abs().max()), (k, float(d.mean()))
+            if "running_" in k:
+                assert float(d.max()) < TOL_DRIFT_BUF * max(float(P[k].abs().max()), 0.1), (k, float(d.max()))
+            else:
+                assert float(d.mean()) < TOL_DRIFT_LR * lr * steps + 1e-6 * float(P[k].abs().max()), (k, float(d.mean()))
 
 
 def test_critic_batch_additivity():
