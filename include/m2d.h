@@ -82,6 +82,10 @@ typedef struct {
     int nb;
     int win_T, win_stride, win_pad, win_seq_len;
     const float* w; int w_ld;
+    const float* w_hi; const float* w_lo; int ws_ld;   /* optional pre-split copies of w for the tensor-core path:
+                                            w_hi = tf32_rn(w), w_lo = tf32_rn(w - w_hi); element (n, t, c) at
+                                            n*ws_ld + t*roundup4(Cc) + c (Cc == 1: n*ws_ld + t), pad zero; loaded by TMA
+                                            (every tap 16-byte aligned).  NULL: operands are split on the fly */
     int N, T, Cc;
     int sr, roff0, droff;
     float* y; long long y_bs; int y_ld; int y_rows;
@@ -131,7 +135,10 @@ int m2d_pack_conv_bwd(const float* w, float* wd, int Cout, int Cin, int k, int s
  * used as a Linear over (tap, channel):  dst[(t*Cin + ci), co] = w[co, ci, t]. */
 enum { M2D_PACK_FWD = 0, M2D_PACK_BWD = 1, M2D_PACK_FULL_BWD = 2 };
 typedef struct {
-    const float* w; float* dst;
+    const float* w; float* dst;           /* dst may be NULL (no exact copy wanted) */
+    float* dst_hi; float* dst_lo;         /* optional 3xTF32 split copies in the m2d_rowconv_args.w_hi layout: the
+                                             contraction channel count of every tap padded to a multiple of 4 floats
+                                             (pad never written: allocate zeroed); BWD blocks follow each other */
     int Cout, Cin, k, stride, kind, reserved;
 } m2d_pack_desc;
 int m2d_pack_batch(const m2d_pack_desc* table, int n, void* stream);

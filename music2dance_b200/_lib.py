@@ -23,6 +23,7 @@ class RowConvArgs(C.Structure):
         ("nb", C.c_int),
         ("win_T", C.c_int), ("win_stride", C.c_int), ("win_pad", C.c_int), ("win_seq_len", C.c_int),
         ("w", f32p), ("w_ld", C.c_int),
+        ("w_hi", f32p), ("w_lo", f32p), ("ws_ld", C.c_int),
         ("N", C.c_int), ("T", C.c_int), ("Cc", C.c_int),
         ("sr", C.c_int), ("roff0", C.c_int), ("droff", C.c_int),
         ("y", f32p), ("y_bs", i64), ("y_ld", C.c_int), ("y_rows", C.c_int),

@@ -408,43 +408,66 @@ __global__ void pack_bwd_kernel(const float* __restrict__ w, float* __restrict__
     }
 }
 
-// all weight re-layouts of one network in ONE launch: blockIdx.y selects the table entry
+// all weight re-layouts of one network in ONE launch: blockIdx.y selects the table entry.  Besides
+// the exact fp32 copy (dst), each entry may request the 3xTF32 operand split of the same matrix
+// (dst_hi / dst_lo, rows padded to a multiple of 4 floats for TMA) consumed by the tensor-core kernels.
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
 __global__ void __launch_bounds__(256) pack_batch_kernel(const m2d_pack_desc* __restrict__ table) {
     const m2d_pack_desc d = table[blockIdx.y];
     const float* __restrict__ w = d.w;
-    float* __restrict__ dst = d.dst;
     const int Cout = d.Cout, Cin = d.Cin, k = d.k, stride = d.stride;
     const long long total = (long long)Cout * Cin * k;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
+        float v;
+        long long pidx;                               // index in the padded split copies
         if (d.kind == M2D_PACK_FWD) {                 // dst[co, t*Cin + ci]
             int ci = (int)(idx % Cin);
             long long r = idx / Cin;
             int t = (int)(r % k);
             int co = (int)(r / k);
-            dst[idx] = w[((long long)co * Cin + ci) * k + t];
+            v = w[((long long)co * Cin + ci) * k + t];
+            // every tap starts on a 16-byte boundary (TMA source alignment); Cin == 1: plain [co][tap] rows
+            const int cp = Cin == 1 ? 1 : ((Cin + 3) & ~3);
+            const int ld = Cin == 1 ? ((k + 3) & ~3) : k * cp;
+            pidx = (long long)co * ld + t * cp + ci;
         } else if (d.kind == M2D_PACK_FULL_BWD) {     // dst[(t*Cin + ci), co]
             int co = (int)(idx % Cout);
             long long r = idx / Cout;
             int ci = (int)(r % Cin);
             int t = (int)(r / Cin);
-            dst[idx] = w[((long long)co * Cin + ci) * k + t];
+            v = w[((long long)co * Cin + ci) * k + t];
+            const int ld = (Cout + 3) & ~3;
+            pidx = r * ld + co;
         } else {                                      // per stride residue rho: dst_rho[ci, q*Cout + co]
-            long long off = 0;
-            int rho = 0, Trho = 0;
+            long long off = 0, poff = 0;
+            int rho = 0, Trho = 0, ld = 0;
             for (rho = 0; rho < stride; ++rho) {
                 Trho = (k - rho + stride - 1) / stride;
                 if (Trho < 0) Trho = 0;
+                ld = Trho * ((Cout + 3) & ~3);
                 long long sz = (long long)Cin * Cout * Trho;
                 if (idx < off + sz) break;
                 off += sz;
+                poff += (long long)Cin * ld;
             }
             long long loc = idx - off;
             int co = (int)(loc % Cout);
             long long r = loc / Cout;
             int q = (int)(r % Trho);
             int ci = (int)(r / Trho);
-            dst[idx] = w[((long long)co * Cin + ci) * k + stride * q + rho];
+            v = w[((long long)co * Cin + ci) * k + stride * q + rho];
+            pidx = poff + (long long)ci * ld + q * ((Cout + 3) & ~3) + co;
+        }
+        if (d.dst) d.dst[idx] = v;
+        if (d.dst_hi) {
+            const float h = rna_tf32(v);
+            d.dst_hi[pidx] = h;
+            d.dst_lo[pidx] = rna_tf32(v - h);
         }
     }
 }

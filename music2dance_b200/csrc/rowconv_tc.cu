@@ -20,6 +20,9 @@
 // Epilogue: tcgen05.ld (32x32b.x16) -> shared memory -> coalesced global stores with
 // the fused bias / activation / mask / residual epilogue of m2d_rowconv, or split-K
 // partials into the workspace.
+#include <cuda.h>
+#include <map>
+#include <tuple>
 #include "common.cuh"
 
 namespace m2d {
@@ -28,7 +31,7 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;
 constexpr int TC_BNMAX = 128;
 constexpr int TC_PRODUCERS = 256;
-constexpr int TC_THREADS = TC_PRODUCERS + 32;
+constexpr int TC_THREADS = TC_PRODUCERS + 64;   // + warp 8 (MMA issuer) + warp 9 (TMA issuer)
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;        // 16 KiB
 constexpr int TC_B_BYTES = TC_BNMAX * TC_BK * 4;     // 16 KiB
 
@@ -199,9 +202,25 @@ struct TcRow {          // per output row of the CTA tile
     int b, i;           // batch / row indices for the epilogue
 };
 
-template <int NS, bool VEC, bool C1>
+// TMA: one box of [128 weight rows][32 floats] lands in shared memory already in the SWIZZLE_128B
+// K-major layout the tensor core reads; completion is signalled on the stage's mbarrier.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+// BTMA: the weight operand comes from the pre-split packed copies (w_hi = rna_tf32(w), w_lo =
+// rna_tf32(w - w_hi), written by the re-layout kernel after each optimizer step) through TMA
+// (warp 9); the producer warps then only stage the activation operand.
+template <int NS, bool VEC, bool C1, bool BTMA>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const int cchunks) {
+rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const int cchunks,
+                  const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
     constexpr int STAGES = tc_stages(NS);
     constexpr int STAGE_BYTES = tc_stage_bytes(NS);
     extern __shared__ uint8_t smem_raw[];
@@ -251,7 +270,7 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
     }
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(bar_full + 8 * s, TC_PRODUCERS);
+            mbar_init(bar_full + 8 * s, TC_PRODUCERS + (BTMA ? 1 : 0));
             mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_acc, 1);
@@ -267,7 +286,17 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
         // ------------------------------------------------------------------ producers
         const int j = tid & 7;                 // 16-byte chunk of the 128-byte K row
         const int rsub = tid >> 3;             // 0..31
-        float4 ra[2][4], rb[2][4];
+        constexpr int NB = BTMA ? 1 : 4;
+        float4 ra[2][4], rb[2][NB];
+        // the four A rows of this thread stay in registers (no table lookups in the K loop)
+        const float* arow[4];
+        int ar0[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const TcRow r = rows[rsub + 32 * q];
+            ar0[q] = r.base >= 0 ? r.r0 : (1 << 29);          // beyond every x_rows: row reads as zero
+            arow[q] = a.x + (r.base >= 0 ? r.base : 0) + (long long)r.r0 * a.x_ld;
+        }
 
         auto load = [&](int s, float4* pa, float4* pb) {
             int t = 0, c = 0, k0 = 0;
@@ -279,10 +308,10 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const TcRow r = rows[rsub + 32 * q];
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r.base >= 0) {
-                    if (C1) {
+                if (C1) {
+                    const TcRow r = rows[rsub + 32 * q];
+                    if (r.base >= 0) {
                         float e[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
@@ -294,36 +323,11 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
                             e[u] = ok ? __ldg(a.x + r.base + (long long)pos * a.x_ld) : 0.f;
                         }
                         v = make_float4(e[0], e[1], e[2], e[3]);
-                    } else {
-                        int rr = r.r0 + t * a.droff;
-                        if (rr >= 0 && rr < a.x_rows) {
-                            const float* p = a.x + r.base + (long long)rr * a.x_ld + c;
-                            if (VEC) {
-                                if (c < a.Cc) v = __ldg(reinterpret_cast<const float4*>(p));
-                            } else {
-                                float e[4];
-#pragma unroll
-                                for (int u = 0; u < 4; ++u) e[u] = (c + u < a.Cc) ? __ldg(p + u) : 0.f;
-                                v = make_float4(e[0], e[1], e[2], e[3]);
-                            }
-                        }
                     }
-                }
-                pa[q] = v;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int nl = rsub + 32 * q;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (nl < bn && n0 + nl < a.N) {
-                    const float* wrow = a.w + (long long)(n0 + nl) * a.w_ld;
-                    if (C1) {
-                        float e[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) e[u] = (k0 + u < a.T) ? __ldg(wrow + k0 + u) : 0.f;
-                        v = make_float4(e[0], e[1], e[2], e[3]);
-                    } else {
-                        const float* p = wrow + (long long)t * a.Cc + c;
+                } else {
+                    const int dr = t * a.droff;
+                    if ((unsigned)(ar0[q] + dr) < (unsigned)a.x_rows) {
+                        const float* p = arow[q] + (long long)dr * a.x_ld + c;
                         if (VEC) {
                             if (c < a.Cc) v = __ldg(reinterpret_cast<const float4*>(p));
                         } else {
@@ -334,7 +338,34 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
                         }
                     }
                 }
-                pb[q] = v;
+                pa[q] = v;
+            }
+            if (!BTMA) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int nl = rsub + 32 * q;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (nl < bn && n0 + nl < a.N) {
+                        const float* wrow = a.w + (long long)(n0 + nl) * a.w_ld;
+                        if (C1) {
+                            float e[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) e[u] = (k0 + u < a.T) ? __ldg(wrow + k0 + u) : 0.f;
+                            v = make_float4(e[0], e[1], e[2], e[3]);
+                        } else {
+                            const float* p = wrow + (long long)t * a.Cc + c;
+                            if (VEC) {
+                                if (c < a.Cc) v = __ldg(reinterpret_cast<const float4*>(p));
+                            } else {
+                                float e[4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) e[u] = (c + u < a.Cc) ? __ldg(p + u) : 0.f;
+                                v = make_float4(e[0], e[1], e[2], e[3]);
+                            }
+                        }
+                    }
+                    pb[q] = v;
+                }
             }
         };
 
@@ -356,23 +387,25 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
             uint8_t* sB = sA + (NS == 3 ? 2 : 1) * TC_A_BYTES;
 #pragma unroll
             for (int q = 0; q < 4; ++q) split_store(sA, sA + TC_A_BYTES, rsub + 32 * q, pa[q]);
+            if (!BTMA) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (rsub + 32 * q < bn) split_store(sB, sB + TC_B_BYTES, rsub + 32 * q, pb[q]);
+                for (int q = 0; q < 4; ++q)
+                    if (rsub + 32 * q < bn) split_store(sB, sB + TC_B_BYTES, rsub + 32 * q, pb[q]);
+            }
             fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
             mbar_arrive(bar_full + 8 * st);
         };
 
         if (nk > 0) load(s_begin, ra[0], rb[0]);
         for (int it = 0; it < nk; it += 2) {
-            if (it + 1 < nk) load(s_begin + it + 1, ra[1], rb[1]);
+            if (it + 1 < nk) load(s_begin + it + 1, ra[1], rb[BTMA ? 0 : 1]);
             store(it, ra[0], rb[0]);
             if (it + 1 < nk) {
                 if (it + 2 < nk) load(s_begin + it + 2, ra[0], rb[0]);
-                store(it + 1, ra[1], rb[1]);
+                store(it + 1, ra[1], rb[BTMA ? 0 : 1]);
             }
         }
-    } else {
+    } else if (warp == 8) {
         // ------------------------------------------------------------------ MMA issuer (one elected lane)
         if (lane == 0) {
             const uint32_t idesc = tf32_idesc(TC_BM, bn);
@@ -401,6 +434,28 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
             umma_commit(bar_acc);                    // accumulator complete
         }
         __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ weight-tile TMA issuer
+        if (BTMA && lane == 0) {
+            for (int it = 0; it < nk; ++it) {
+                const int st = it % STAGES;
+                const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+                const int s = s_begin + it;
+                int kcol;
+                if (C1) {
+                    kcol = s * TC_BK;
+                } else {
+                    const int t = s / cchunks;
+                    kcol = t * ((a.Cc + 3) & ~3) + (s - t * cchunks) * TC_BK;   // taps padded to 4 floats in the split copies
+                }
+                mbar_wait(bar_empty + 8 * st, ph ^ 1);
+                const uint32_t sB = smem_base + (uint32_t)st * STAGE_BYTES + (NS == 3 ? 2 : 1) * TC_A_BYTES;
+                mbar_arrive_expect_tx(bar_full + 8 * st, (NS == 3 ? 2u : 1u) * TC_B_BYTES);
+                tma_load_2d(sB, &map_hi, kcol, n0, bar_full + 8 * st);
+                if (NS == 3) tma_load_2d(sB + TC_B_BYTES, &map_lo, kcol, n0, bar_full + 8 * st);
+            }
+        }
+        __syncwarp();
     }
 
     // ---------------------------------------------------------------------- epilogue
@@ -417,9 +472,11 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
     }
     __syncthreads();
     const int Z = (int)gridDim.z;                    // == cluster size along z
-    if (warp == 8) {
-        tc_fence_after();
-        tmem_dealloc(tmem, (uint32_t)tm_cols);
+    if (warp >= 8) {
+        if (warp == 8) {
+            tc_fence_after();
+            tmem_dealloc(tmem, (uint32_t)tm_cols);
+        }
         if (Z > 1) {
             cluster_sync_all();                       // partial tiles ready
             cluster_sync_all();                       // peers done reading this CTA's tile
@@ -549,9 +606,48 @@ static int max_cluster_z(K kern, int smem, int want, bool allow16) {
     return z;
 }
 
-template <int NS, bool VEC, bool C1>
-static int launch_tc(const m2d_rowconv_args& a, int M, int nsteps, int cchunks, int want_splits, cudaStream_t st) {
-    auto kern = rowconv_tc_kernel<NS, VEC, C1>;
+// ---- TMA descriptors for the packed, pre-split weight matrices [N rows][ld floats] -------------
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn tmap_encoder() {
+    static tmap_encode_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<tmap_encode_fn>(p);
+        (void)cudaGetLastError();
+    }
+    return fn;
+}
+// box = 32 floats (one 128-byte swizzle row) x 128 weight rows; rows / columns beyond the matrix read as zero
+static const CUtensorMap* weight_tmap(const float* w, int N, int ld) {
+    static std::map<std::tuple<const void*, int, int>, CUtensorMap> cache;
+    auto key = std::make_tuple((const void*)w, N, ld);
+    auto it = cache.find(key);
+    if (it != cache.end()) return &it->second;
+    tmap_encode_fn enc = tmap_encoder();
+    if (!enc) return nullptr;
+    CUtensorMap m;
+    cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {TC_BK, TC_BNMAX};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return nullptr;
+    return &cache.emplace(key, m).first->second;
+}
+
+template <int NS, bool VEC, bool C1, bool BTMA>
+static int launch_tc(const m2d_rowconv_args& a, int M, int nsteps, int cchunks, int want_splits, cudaStream_t st,
+                     const CUtensorMap* mh, const CUtensorMap* ml) {
+    auto kern = rowconv_tc_kernel<NS, VEC, C1, BTMA>;
     static bool configured = false;
     static int zmax = 1;
     const int smem = tc_smem_bytes(NS);
@@ -567,7 +663,17 @@ static int launch_tc(const m2d_rowconv_args& a, int M, int nsteps, int cchunks, 
     int Z = 1;
     while (Z * 2 <= want_splits && Z * 2 <= zmax) Z *= 2;
     dim3 grid((unsigned)cdiv(M, TC_BM), (unsigned)cdiv(a.N, TC_BNMAX), (unsigned)Z);
-    return launch_clustered("rowconv_tc", kern, grid, smem, Z, st, a, M, nsteps, cchunks);
+    static const CUtensorMap dummy = {};
+    return launch_clustered("rowconv_tc", kern, grid, smem, Z, st, a, M, nsteps, cchunks, mh ? *mh : dummy,
+                            ml ? *ml : dummy);
+}
+
+template <int NS, bool BTMA>
+static int launch_tc_shape(const m2d_rowconv_args& a, int M, int nsteps, int cchunks, int splits, cudaStream_t st,
+                           bool c1, bool vec, const CUtensorMap* mh, const CUtensorMap* ml) {
+    if (c1) return launch_tc<NS, false, true, BTMA>(a, M, nsteps, cchunks, splits, st, mh, ml);
+    if (vec) return launch_tc<NS, true, false, BTMA>(a, M, nsteps, cchunks, splits, st, mh, ml);
+    return launch_tc<NS, false, false, BTMA>(a, M, nsteps, cchunks, splits, st, mh, ml);
 }
 
 // Called by m2d_rowconv when the tensor-core path is selected.  Returns 1 if the shape is
@@ -587,17 +693,20 @@ int rowconv_tc_dispatch(const m2d_rowconv_args& a, int M, int mode, cudaStream_t
         splits = (int)(want < nsteps / 4 ? want : nsteps / 4);
         if (splits < 1) splits = 1;
     }
-    int rc;
-    if (mode == 3) {
-        if (c1) rc = launch_tc<3, false, true>(a, M, nsteps, cchunks, splits, st);
-        else if (vec) rc = launch_tc<3, true, false>(a, M, nsteps, cchunks, splits, st);
-        else rc = launch_tc<3, false, false>(a, M, nsteps, cchunks, splits, st);
-    } else {
-        if (c1) rc = launch_tc<1, false, true>(a, M, nsteps, cchunks, splits, st);
-        else if (vec) rc = launch_tc<1, true, false>(a, M, nsteps, cchunks, splits, st);
-        else rc = launch_tc<1, false, false>(a, M, nsteps, cchunks, splits, st);
+    // weight operand through TMA when the caller supplies the pre-split packed copies
+    const CUtensorMap *mh = nullptr, *ml = nullptr;
+    const int kpad = c1 ? (int)K : a.T * ((a.Cc + 3) & ~3);
+    if (a.w_hi && a.w_lo && a.ws_ld >= kpad && a.ws_ld % 4 == 0 && aligned16(a.w_hi) && aligned16(a.w_lo)) {
+        mh = weight_tmap(a.w_hi, a.N, a.ws_ld);
+        ml = weight_tmap(a.w_lo, a.N, a.ws_ld);
+        if (!mh || !ml) mh = ml = nullptr;
     }
-    return rc;
+    if (mh) {
+        return mode == 3 ? launch_tc_shape<3, true>(a, M, nsteps, cchunks, splits, st, c1, vec, mh, ml)
+                         : launch_tc_shape<1, true>(a, M, nsteps, cchunks, splits, st, c1, vec, mh, ml);
+    }
+    return mode == 3 ? launch_tc_shape<3, false>(a, M, nsteps, cchunks, splits, st, c1, vec, nullptr, nullptr)
+                     : launch_tc_shape<1, false>(a, M, nsteps, cchunks, splits, st, c1, vec, nullptr, nullptr);
 }
 
 // ============================================================================ weight gradient
@@ -735,7 +844,7 @@ wgrad_tc_kernel(const m2d_wgrad_args a, const int Ktot, const int Ncols) {
                 store(it + 1, ra[1], rb[1]);
             }
         }
-    } else {
+    } else if (warp == 8) {
         if (lane == 0) {
             // both operands MN-major: a_major (bit 15) = b_major (bit 16) = 1
             const uint32_t idesc = tf32_idesc(TC_BM, bn) | (1u << 15) | (1u << 16);
@@ -779,9 +888,11 @@ wgrad_tc_kernel(const m2d_wgrad_args a, const int Ktot, const int Ncols) {
     }
     __syncthreads();
     const int Z = (int)gridDim.z;
-    if (warp == 8) {
-        tc_fence_after();
-        tmem_dealloc(tmem, (uint32_t)tm_cols);
+    if (warp >= 8) {
+        if (warp == 8) {
+            tc_fence_after();
+            tmem_dealloc(tmem, (uint32_t)tm_cols);
+        }
         if (Z > 1) {
             cluster_sync_all();
             cluster_sync_all();

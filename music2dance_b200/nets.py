@@ -75,45 +75,51 @@ class ConvLayer:
         self.need_dgrad = need_dgrad
         dev = w.device
         n = Cout * Cin * k
+        z = lambda m: torch.zeros(m, dtype=torch.float32, device=dev)
         self.wp = None if (Cin == 1 or k == 1) else torch.empty(n, dtype=torch.float32, device=dev)
         self.wd = torch.empty(n, dtype=torch.float32, device=dev) if (need_dgrad and Cin > 1) else None
-        self.res = []                                       # (r0, rho, c0, Trho, offset) per stride residue
-        off = 0
+        # 3xTF32 operand split of the packed weights (rows padded to 4 floats, pad stays zero) for the TMA path
+        self.ldf = (k * ((Cin + 3) // 4 * 4)) if Cin > 1 else (k + 3) // 4 * 4
+        self.wph, self.wpl = z(Cout * self.ldf), z(Cout * self.ldf)
+        self.res = []                                       # (rho, Trho, offset, padded offset, padded ld) per stride residue
+        off = poff = 0
         for rho in range(stride):
             Trho = max(0, -(-(k - rho) // stride))
-            self.res.append((rho, Trho, off))
+            ld = Trho * ((Cout + 3) // 4 * 4)
+            self.res.append((rho, Trho, off, poff, ld))
             off += Cin * Cout * Trho
+            poff += Cin * ld
+        self.ldb = (Cout + 3) // 4 * 4                      # Linear / full-length form: [k*Cin rows][Cout]
+        if self.wd is not None:
+            m = (k * Cin * self.ldb) if (self.full or k == 1) else poff
+            self.wdh, self.wdl = z(m), z(m)
+        else:
+            self.wdh = self.wdl = None
 
     def wf(self):
         return self.w if self.wp is None else self.wp
 
     def pack_entries(self):
         """(w, dst, Cout, Cin, k, stride, kind) rows of the batched re-layout table (ops.pack_batch)."""
-        e = []
-        if self.wp is not None:
-            e.append((self.w, self.wp, self.Cout, self.Cin, self.k, 1, ops.PACK_FWD))
+        e = [(self.w, self.wp, self.wph, self.wpl, self.Cout, self.Cin, self.k, 1, ops.PACK_FWD)]
         if self.wd is not None:
-            if self.k == 1:
-                e.append((self.w, self.wd, self.Cout, self.Cin, 1, 1, ops.PACK_BWD))
-            elif self.full:
-                e.append((self.w, self.wd, self.Cout, self.Cin, self.k, 1, ops.PACK_FULL_BWD))
+            if self.full or self.k == 1:
+                e.append((self.w, self.wd, self.wdh, self.wdl, self.Cout, self.Cin, self.k, 1, ops.PACK_FULL_BWD))
             else:
-                e.append((self.w, self.wd, self.Cout, self.Cin, self.k, self.s, ops.PACK_BWD))
+                e.append((self.w, self.wd, self.wdh, self.wdl, self.Cout, self.Cin, self.k, self.s, ops.PACK_BWD))
         return e
 
     def pack(self):
-        if self.wp is not None:
-            ops.pack_conv_fwd(self.w, self.wp, self.Cout, self.Cin, self.k)
-        if self.wd is not None:
-            if self.full or self.k == 1:
-                ops.pack_conv_bwd(self.wf(), self.wd, self.Cout, self.Cin * self.k, 1, 1)
-            else:
-                ops.pack_conv_bwd(self.w, self.wd, self.Cout, self.Cin, self.k, self.s)
+        tab = getattr(self, "_tab", None)
+        if tab is None:
+            tab = self._tab = ops.pack_table(self.pack_entries(), self.w.device)
+        ops.pack_batch(*tab)
 
     # y[b,l,:] = act(conv(x)[b,l,:] + bias)
     def fwd(self, x, y, act=0, bias=True, ws=None, win=None, **epi):
         ops.rowconv(x, self.wf(), y, T=self.k, Cc=self.Cin, N=self.Cout, sr=self.s, roff0=-self.p,
-                    droff=1, bias=self.b if bias else None, act=act, ws=ws, win=win, **epi)
+                    droff=1, bias=self.b if bias else None, act=act, ws=ws, win=win,
+                    w_split=(self.wph.data_ptr(), self.wpl.data_ptr(), self.ldf), **epi)
 
     # dx = conv_transpose(dy) with fused epilogue (mask by act'(prev), residual add, ...)
     def dgrad(self, dy, dx, ws=None, mask=None, mask_mode=0, add=None, add_before_mask=False, y2=None):
@@ -125,12 +131,13 @@ class ConvLayer:
             f = (lambda m: None if m is None else (m.flatten_cols().flat_rows() if fl else m.flat_rows()))
             yd = f(dx)
             ops.rowconv(xd, self.wd, yd, T=1, Cc=self.Cout, N=K, ws=ws, mask=f(mask), mask_mode=mask_mode,
-                        add=f(add), add_before_mask=add_before_mask, y2=f(y2))
+                        add=f(add), add_before_mask=add_before_mask, y2=f(y2),
+                        w_split=(self.wdh.data_ptr(), self.wdl.data_ptr(), self.ldb))
             return
         s = self.s
         for r0 in range(s):
             rho, c0 = (r0 + self.p) % s, (r0 + self.p) // s
-            _, Trho, off = self.res[rho]
+            _, Trho, off, poff, pld = self.res[rho]
             nrows = -(-(dx.rows - r0) // s)
             if nrows <= 0:
                 continue
@@ -145,7 +152,8 @@ class ConvLayer:
             wd = self.wd[off:]
             ops.rowconv(dy, wd, sub(dx), T=Trho, Cc=self.Cout, N=self.Cin, sr=1, roff0=c0, droff=-1,
                         ws=ws, mask=sub(mask), mask_mode=mask_mode, add=sub(add),
-                        add_before_mask=add_before_mask, y2=sub(y2))
+                        add_before_mask=add_before_mask, y2=sub(y2),
+                        w_split=(self.wdh.data_ptr() + 4 * poff, self.wdl.data_ptr() + 4 * poff, pld))
 
     def wgrad(self, dy, x, ws, scale=1.0, beta=0.0, win=None, bias=True, acc=None, bbeta=None):
         """gw = beta*gw + scale*dW;  gb = bbeta*gb + scale*db (bbeta defaults to beta)."""
