@@ -628,7 +628,7 @@ extern "C" int m2d_pack_conv_bwd(const float* w, float* wd, int Cout, int Cin, i
 
 extern "C" int m2d_pack_batch(const m2d_pack_desc* table, int n, void* stream) {
     M2D_REQUIRE(table && n > 0, "pack_batch: bad args");
-    dim3 grid(64, (unsigned)n);
+    dim3 grid(148, (unsigned)n);
     pack_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table);
     return check_launch("pack_batch");
 }

@@ -21,6 +21,7 @@
 // the fused bias / activation / mask / residual epilogue of m2d_rowconv, or split-K
 // partials into the workspace.
 #include <cuda.h>
+#include <cstdlib>
 #include <map>
 #include <tuple>
 #include "common.cuh"
@@ -30,8 +31,10 @@ namespace m2d {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;
 constexpr int TC_BNMAX = 128;
-constexpr int TC_PRODUCERS = 256;
-constexpr int TC_THREADS = TC_PRODUCERS + 64;   // + warp 8 (MMA issuer) + warp 9 (TMA issuer)
+constexpr int TC_PRODUCERS = 512;       // 16 producer / epilogue warps
+constexpr int TC_PW = TC_PRODUCERS / 32;   // index of the MMA-issuer warp; the TMA issuer is TC_PW + 1
+constexpr int TC_RPT = 128 * 8 / TC_PRODUCERS;   // 16-byte chunks of a 128-row x 128-byte tile per producer thread
+constexpr int TC_THREADS = TC_PRODUCERS + 64;   // + MMA-issuer warp + TMA-issuer warp
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;        // 16 KiB
 constexpr int TC_B_BYTES = TC_BNMAX * TC_BK * 4;     // 16 KiB
 
@@ -117,10 +120,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ bool aligned16d(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+// round to TF32 (10 explicit mantissa bits), nearest with ties away from zero — the result of
+// cvt.rna.tf32.f32, computed on the integer pipe (the conversion pipe is a quarter-rate unit)
 __device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 // K-major operand tile, SWIZZLE_128B: row r (128 bytes = 32 floats) lives at
@@ -148,12 +151,12 @@ __device__ __forceinline__ uint32_t tf32_idesc(int M, int N) {
 constexpr int TC_CLD = TC_BNMAX + 4;      // C staging tile row stride (floats): 16-byte aligned rows, conflict-free float4 access
 
 // TMEM accumulator (128 lanes x bn columns) -> shared C tile.  Warp w reads lanes 32*(w%4)..+31
-// (the tcgen05.ld lane-quarter rule); warps 0-3 take the even 16-column chunks, warps 4-7 the odd ones.
+// (the tcgen05.ld lane-quarter rule); the 16-column chunks are dealt round-robin to the warps of a quarter.
 __device__ __forceinline__ void tmem_to_smem(uint32_t tmem, float* Cs, int warp, int lane, int bn) {
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, part = warp >> 2;
     const int row = 32 * q + lane;
     const int chunks = bn / 16;
-    for (int ch = half; ch < chunks; ch += 2) {
+    for (int ch = part; ch < chunks; ch += TC_PW / 4) {
         float v[16];
         tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(16 * ch), v);
         float4* dst = reinterpret_cast<float4*>(Cs + row * TC_CLD + 16 * ch);
@@ -276,24 +279,29 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
         mbar_init(bar_acc, 1);
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(smem_u32(&tmem_slot), (uint32_t)tm_cols);
+    if (warp == TC_PW) tmem_alloc(smem_u32(&tmem_slot), (uint32_t)tm_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    // programmatic dependent launch: everything above overlapped the tail of the previous kernel on the
+    // stream; its results (activations, re-packed weights) are visible after this point
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    if (warp < 8) {
+    if (warp < TC_PW) {
         // ------------------------------------------------------------------ producers
         const int j = tid & 7;                 // 16-byte chunk of the 128-byte K row
-        const int rsub = tid >> 3;             // 0..31
-        constexpr int NB = BTMA ? 1 : 4;
-        float4 ra[2][4], rb[2][NB];
+        const int rsub = tid >> 3;             // 0..63
+        constexpr int RS = TC_PRODUCERS / 8;    // row stride between the chunks of one thread
+        constexpr int NB = BTMA ? 1 : TC_RPT;
+        constexpr int D = BTMA ? 4 : 2;         // k-blocks of A (and B) held in registers ahead of the stores
+        float4 ra[D][TC_RPT], rb[D][NB];
         // the four A rows of this thread stay in registers (no table lookups in the K loop)
-        const float* arow[4];
-        int ar0[4];
+        const float* arow[TC_RPT];
+        int ar0[TC_RPT];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const TcRow r = rows[rsub + 32 * q];
+        for (int q = 0; q < TC_RPT; ++q) {
+            const TcRow r = rows[rsub + RS * q];
             ar0[q] = r.base >= 0 ? r.r0 : (1 << 29);          // beyond every x_rows: row reads as zero
             arow[q] = a.x + (r.base >= 0 ? r.base : 0) + (long long)r.r0 * a.x_ld;
         }
@@ -307,10 +315,10 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
                 c = (s - t * cchunks) * TC_BK + 4 * j;
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < TC_RPT; ++q) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (C1) {
-                    const TcRow r = rows[rsub + 32 * q];
+                    const TcRow r = rows[rsub + RS * q];
                     if (r.base >= 0) {
                         float e[4];
 #pragma unroll
@@ -342,8 +350,8 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
             }
             if (!BTMA) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int nl = rsub + 32 * q;
+                for (int q = 0; q < TC_RPT; ++q) {
+                    const int nl = rsub + RS * q;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (nl < bn && n0 + nl < a.N) {
                         const float* wrow = a.w + (long long)(n0 + nl) * a.w_ld;
@@ -386,26 +394,29 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
             uint8_t* sA = smem + (size_t)st * STAGE_BYTES;
             uint8_t* sB = sA + (NS == 3 ? 2 : 1) * TC_A_BYTES;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) split_store(sA, sA + TC_A_BYTES, rsub + 32 * q, pa[q]);
+            for (int q = 0; q < TC_RPT; ++q) split_store(sA, sA + TC_A_BYTES, rsub + RS * q, pa[q]);
             if (!BTMA) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (rsub + 32 * q < bn) split_store(sB, sB + TC_B_BYTES, rsub + 32 * q, pb[q]);
+                for (int q = 0; q < TC_RPT; ++q)
+                    if (rsub + RS * q < bn) split_store(sB, sB + TC_B_BYTES, rsub + RS * q, pb[q]);
             }
             fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
             mbar_arrive(bar_full + 8 * st);
         };
 
-        if (nk > 0) load(s_begin, ra[0], rb[0]);
-        for (int it = 0; it < nk; it += 2) {
-            if (it + 1 < nk) load(s_begin + it + 1, ra[1], rb[BTMA ? 0 : 1]);
-            store(it, ra[0], rb[0]);
-            if (it + 1 < nk) {
-                if (it + 2 < nk) load(s_begin + it + 2, ra[0], rb[0]);
-                store(it + 1, ra[1], rb[BTMA ? 0 : 1]);
+#pragma unroll
+        for (int p = 0; p < D - 1; ++p)
+            if (p < nk) load(s_begin + p, ra[p], rb[p]);
+        for (int it = 0; it < nk; it += D) {
+#pragma unroll
+            for (int u = 0; u < D; ++u) {
+                if (it + u < nk) {
+                    if (it + u + D - 1 < nk) load(s_begin + it + u + D - 1, ra[(u + D - 1) % D], rb[(u + D - 1) % D]);
+                    store(it + u, ra[u], rb[u]);
+                }
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == TC_PW) {
         // ------------------------------------------------------------------ MMA issuer (one elected lane)
         if (lane == 0) {
             const uint32_t idesc = tf32_idesc(TC_BM, bn);
@@ -460,7 +471,7 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
 
     // ---------------------------------------------------------------------- epilogue
     float* Cs = reinterpret_cast<float*>(smem);      // [128][TC_CLD], reuses the (drained) stages
-    if (warp < 8) {
+    if (warp < TC_PW) {
         if (nk > 0) {
             mbar_wait(bar_acc, 0);
             tc_fence_after();
@@ -472,8 +483,8 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
     }
     __syncthreads();
     const int Z = (int)gridDim.z;                    // == cluster size along z
-    if (warp >= 8) {
-        if (warp == 8) {
+    if (warp >= TC_PW) {
+        if (warp == TC_PW) {
             tc_fence_after();
             tmem_dealloc(tmem, (uint32_t)tm_cols);
         }
@@ -559,6 +570,17 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
     if (Z > 1) cluster_sync_all();                   // keep this CTA's tile alive until every peer has read it
 }
 
+// Programmatic dependent launch of the tensor-core kernels (prologue overlaps the previous kernel's
+// tail; the kernels call griddepcontrol.wait before touching dependent data).  M2D_PDL=0 disables it.
+static bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("M2D_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 // Launch with the split-K CTAs of a tile grouped into a (1,1,Z) thread-block cluster.
 template <typename K, typename... Args>
 static int launch_clustered(const char* what, K kern, dim3 grid, int smem, int Z, cudaStream_t st, Args... args) {
@@ -567,13 +589,22 @@ static int launch_clustered(const char* what, K kern, dim3 grid, int smem, int Z
     cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = (size_t)smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = (unsigned)Z;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (Z > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 1;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = (unsigned)Z;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = Z > 1 ? 1 : 0;
+    cfg.numAttrs = na;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
     if (e != cudaSuccess) {
         set_error("%s: launch (grid %u,%u,%u cluster z=%d): %s", what, grid.x, grid.y, grid.z, Z, cudaGetErrorString(e));
@@ -682,6 +713,10 @@ int rowconv_tc_dispatch(const m2d_rowconv_args& a, int M, int mode, cudaStream_t
     const bool c1 = a.Cc == 1;
     const long long K = (long long)a.T * a.Cc;
     if (a.N < 8 || (long long)M * a.N * K < (1ll << 18)) return 1;
+    // a handful of rows against a long contraction (audio_d.l6, stick_d.fconv and their backward-data
+    // passes at small batch) is weight-streaming work: one 128-row tile cannot spread over more than a
+    // cluster of CTAs, the FP32 kernel splits K over the whole chip
+    if (M <= 64 && K >= 4096 && a.ws) return 1;
     const bool vec = !c1 && a.Cc % 4 == 0 && a.x_ld % 4 == 0 && a.x_bs % 4 == 0 && a.w_ld % 4 == 0 &&
                      aligned16(a.x) && aligned16(a.w);
     const int cchunks = c1 ? 1 : (int)cdiv(a.Cc, TC_BK);
@@ -769,27 +804,31 @@ wgrad_tc_kernel(const m2d_wgrad_args a, const int Ktot, const int Ncols) {
         mbar_init(bar_acc, 1);
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(smem_u32(&tmem_slot), (uint32_t)tm_cols);
+    if (warp == TC_PW) tmem_alloc(smem_u32(&tmem_slot), (uint32_t)tm_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    // programmatic dependent launch: everything above overlapped the tail of the previous kernel on the
+    // stream; its results (activations, re-packed weights) are visible after this point
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    if (warp < 8) {
+    if (warp < TC_PW) {
         const int j = tid & 7;                 // 16-byte chunk within a 32-wide block
-        const int kl = tid >> 3;               // K row of the block handled by this thread (0..31)
+        const int kl = (tid >> 3) & 31;        // K row of the block handled by this thread (0..31)
+        const int qb = (tid >> 8) * TC_RPT;    // first of the TC_RPT 32-wide M / N blocks of this thread
         // the four (tap, channel) column chunks of the B operand are fixed over the K loop
-        int bt[4], bc[4];
-        bool bok[4];
+        int bt[TC_RPT], bc[TC_RPT];
+        bool bok[TC_RPT];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            int n = n0 + 32 * q + 4 * j;
+        for (int q = 0; q < TC_RPT; ++q) {
+            int n = n0 + 32 * (qb + q) + 4 * j;
             bok[q] = n < Ncols;
             int nn = bok[q] ? n : 0;
             bt[q] = nn / a.Cc;
             bc[q] = nn - bt[q] * a.Cc;
         }
-        float4 ra[2][4], rb[2][4];
+        float4 ra[2][TC_RPT], rb[2][TC_RPT];
         auto load = [&](int s, float4* pa, float4* pb) {
             const int k = s * TC_BK + kl;
             const bool kok = k < Ktot;
@@ -798,15 +837,15 @@ wgrad_tc_kernel(const m2d_wgrad_args a, const int Ktot, const int Ncols) {
             const int l = kc - b * a.dy_rows;
             const float* dyr = a.dy + (long long)b * a.dy_bs + (long long)l * a.dy_ld;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int co = m0 + 32 * q + 4 * j;
+            for (int q = 0; q < TC_RPT; ++q) {
+                const int co = m0 + 32 * (qb + q) + 4 * j;
                 pa[q] = (kok && co < a.Cout) ? __ldg(reinterpret_cast<const float4*>(dyr + co))
                                              : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             const float* xb = a.x + (long long)b * a.x_bs;
             const int rbase = l * a.sr + a.roff0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < TC_RPT; ++q) {
                 const int r = rbase + bt[q] * a.droff;
                 const bool ok = kok && bok[q] && r >= 0 && r < a.x_rows;
                 pb[q] = ok ? __ldg(reinterpret_cast<const float4*>(xb + (long long)r * a.x_ld + bc[q]))
@@ -828,10 +867,10 @@ wgrad_tc_kernel(const m2d_wgrad_args a, const int Ktot, const int Ncols) {
             uint8_t* sA = smem + (size_t)st * STAGE_BYTES;
             uint8_t* sB = sA + (NS == 3 ? 2 : 1) * TC_A_BYTES;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) split_store(sA, sA + TC_A_BYTES, mn_off(kl, 8 * q + j), pa[q]);
+            for (int q = 0; q < TC_RPT; ++q) split_store(sA, sA + TC_A_BYTES, mn_off(kl, 8 * (qb + q) + j), pa[q]);
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (32 * q < bn) split_store(sB, sB + TC_B_BYTES, mn_off(kl, 8 * q + j), pb[q]);
+            for (int q = 0; q < TC_RPT; ++q)
+                if (32 * (qb + q) < bn) split_store(sB, sB + TC_B_BYTES, mn_off(kl, 8 * (qb + q) + j), pb[q]);
             fence_proxy_async_smem();
             mbar_arrive(bar_full + 8 * st);
         };
@@ -844,7 +883,7 @@ wgrad_tc_kernel(const m2d_wgrad_args a, const int Ktot, const int Ncols) {
                 store(it + 1, ra[1], rb[1]);
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == TC_PW) {
         if (lane == 0) {
             // both operands MN-major: a_major (bit 15) = b_major (bit 16) = 1
             const uint32_t idesc = tf32_idesc(TC_BM, bn) | (1u << 15) | (1u << 16);
@@ -876,7 +915,7 @@ wgrad_tc_kernel(const m2d_wgrad_args a, const int Ktot, const int Ncols) {
     }
 
     float* Cs = reinterpret_cast<float*>(smem);
-    if (warp < 8) {
+    if (warp < TC_PW) {
         if (nk > 0) {
             mbar_wait(bar_acc, 0);
             tc_fence_after();
@@ -888,8 +927,8 @@ wgrad_tc_kernel(const m2d_wgrad_args a, const int Ktot, const int Ncols) {
     }
     __syncthreads();
     const int Z = (int)gridDim.z;
-    if (warp >= 8) {
-        if (warp == 8) {
+    if (warp >= TC_PW) {
+        if (warp == TC_PW) {
             tc_fence_after();
             tmem_dealloc(tmem, (uint32_t)tm_cols);
         }
