@@ -244,29 +244,44 @@ __device__ __forceinline__ void gru_mbar_wait(uint32_t bar, uint32_t parity) {
 
 constexpr int GRU2_BGMAX = 8;
 
-template <int KS, bool SAVE>
+__device__ __forceinline__ void gru_st_async4(uint32_t raddr, float4 v, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+                 "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)),
+                 "r"(__float_as_uint(v.w)), "r"(rbar)
+                 : "memory");
+}
+
+// Layout shared by the forward and backward recurrences.  A vector of length V (V = H forward,
+// 3H backward) lives in shared memory as V floats padded to 32*KC; thread (unit ul = tid/8,
+// k-part kp = tid%8) owns the 16-byte chunks c = 8*i + kp, i < KC, i.e. elements 4c..4c+3: the eight
+// k-parts of a unit read 128 contiguous bytes per i (conflict-free, no padding), and the matching
+// weight elements w[4*i + e] <-> k = 4*(8*i + kp) + e stay in registers for the whole sequence.
+// Hidden units are dealt to the cluster's CTAs in blocks of nu (a multiple of 4): warp w of CTA
+// `rank` owns units rank*nu + 4w .. +3, so the four results of a warp form one aligned 16-byte
+// st.async per destination CTA.
+
+template <int KC, bool SAVE>
 __global__ void __launch_bounds__(256)
 gru_fwd2_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
                 float* __restrict__ h_out, int ldh, float* __restrict__ save, int B, int T, int H, int nu,
                 int BG) {
-    constexpr int KSP = ((KS + 3) / 4) * 4 + 4;          // padded k-part stride: conflict-free float4 reads
+    constexpr int VP = 32 * KC;
     cg::cluster_group cluster = cg::this_cluster();
     const int NC = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
     const int b0 = (blockIdx.x / NC) * BG;
     const int nb = min(BG, B - b0);
     const int u0 = rank * nu;
-    const int nown = max(0, min(nu, H - u0));
-    __shared__ __align__(16) float hs[2][GRU2_BGMAX][8 * KSP];
+    __shared__ __align__(16) float hs[2][GRU2_BGMAX][VP];
     __shared__ __align__(8) uint64_t bars[2];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int kp = tid & 7, ul = tid >> 3;
-    const bool active = ul < nown;
     const int uu = u0 + ul;
+    const bool active = ul < nu && uu < H;
 
-    for (int i = tid; i < 2 * GRU2_BGMAX * 8 * KSP; i += 256) (&hs[0][0][0])[i] = 0.f;
+    for (int i = tid; i < 2 * GRU2_BGMAX * VP; i += 256) (&hs[0][0][0])[i] = 0.f;
     const uint32_t bar0 = gru_smem_u32(&bars[0]);
-    const uint32_t tx_bytes = 4u * (uint32_t)H * (uint32_t)nb;
+    const uint32_t tx_bytes = 4u * (uint32_t)((H + 3) & ~3) * (uint32_t)nb;      // whole 4-unit groups are sent
     if (tid == 0) {
         gru_mbar_init(bar0, 1);
         gru_mbar_init(bar0 + 8, 1);
@@ -274,16 +289,19 @@ gru_fwd2_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, co
         if (T > 1) gru_mbar_expect(bar0 + 8, tx_bytes);      // filled by the sends of step 0
         if (T > 2) gru_mbar_expect(bar0, tx_bytes);          // filled by the sends of step 1
     }
-    // recurrent weights -> registers
-    float w[3][KS];
+    float w[3][4 * KC];
 #pragma unroll
     for (int g = 0; g < 3; ++g)
 #pragma unroll
-        for (int i = 0; i < KS; ++i) {
-            const int k = kp * KS + i;
-            w[g][i] = (active && k < H) ? __ldg(w_hh + ((long long)g * H + uu) * H + k) : 0.f;
-        }
+        for (int i = 0; i < KC; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int k = 4 * (8 * i + kp) + e;
+                w[g][4 * i + e] = (active && k < H) ? __ldg(w_hh + ((long long)g * H + uu) * H + k) : 0.f;
+            }
     const bool fin = active && kp < nb;                  // this lane finishes batch entry kp of unit uu
+    // lane b (< nb) of a warp whose first unit exists sends the warp's four h values of batch entry b
+    const bool sender = lane < nb && (u0 + 4 * (tid >> 5)) < H && 4 * (tid >> 5) < nu;
     float bhr = 0.f, bhz = 0.f, bhn = 0.f;
     long long row0 = 0;
     float gir = 0.f, giz = 0.f, gin = 0.f, hprev = 0.f;
@@ -294,7 +312,6 @@ gru_fwd2_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, co
         gir = g0[uu]; giz = g0[H + uu]; gin = g0[2 * H + uu];
     }
     const uint32_t hs_addr = gru_smem_u32(&hs[0][0][0]);
-    const uint32_t dst_off = (uint32_t)(((uu / KS) * KSP + (uu % KS)) * 4);   // position of unit uu inside a row of hs
     __syncthreads();
     cluster.sync();                                      // every CTA's buffers / barriers are ready
 
@@ -311,48 +328,34 @@ gru_fwd2_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, co
             nr = g1[uu]; nz = g1[H + uu]; nn = g1[2 * H + uu];
         }
         float ar = 0.f, az = 0.f, an = 0.f;
-        {   // every lane takes part (full-mask shuffles); lanes without a unit hold zero weights
-            for (int b = 0; b < nb; ++b) {
-                const float4* hv = reinterpret_cast<const float4*>(&hs[cur][b][kp * KSP]);
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f;
+        for (int b = 0; b < nb; ++b) {                   // every lane takes part (full-mask shuffles)
+            const float4* hv = reinterpret_cast<const float4*>(&hs[cur][b][0]) + kp;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f;
 #pragma unroll
-                for (int i4 = 0; i4 < (KS + 3) / 4; ++i4) {
-                    const float4 h4 = hv[i4];
-                    const float hh[4] = {h4.x, h4.y, h4.z, h4.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int i = 4 * i4 + e;
-                        if (i < KS) {
-                            if (e & 1) {
-                                q0 = fmaf(w[0][i], hh[e], q0); q1 = fmaf(w[1][i], hh[e], q1); q2 = fmaf(w[2][i], hh[e], q2);
-                            } else {
-                                s0 = fmaf(w[0][i], hh[e], s0); s1 = fmaf(w[1][i], hh[e], s1); s2 = fmaf(w[2][i], hh[e], s2);
-                            }
-                        }
-                    }
-                }
-                s0 += q0; s1 += q1; s2 += q2;
-#pragma unroll
-                for (int o = 4; o > 0; o >>= 1) {
-                    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                }
-                if (kp == b) { ar = s0; az = s1; an = s2; }
+            for (int i = 0; i < KC; ++i) {
+                const float4 h4 = hv[8 * i];
+                s0 = fmaf(w[0][4 * i], h4.x, s0); s1 = fmaf(w[1][4 * i], h4.x, s1); s2 = fmaf(w[2][4 * i], h4.x, s2);
+                q0 = fmaf(w[0][4 * i + 1], h4.y, q0); q1 = fmaf(w[1][4 * i + 1], h4.y, q1); q2 = fmaf(w[2][4 * i + 1], h4.y, q2);
+                s0 = fmaf(w[0][4 * i + 2], h4.z, s0); s1 = fmaf(w[1][4 * i + 2], h4.z, s1); s2 = fmaf(w[2][4 * i + 2], h4.z, s2);
+                q0 = fmaf(w[0][4 * i + 3], h4.w, q0); q1 = fmaf(w[1][4 * i + 3], h4.w, q1); q2 = fmaf(w[2][4 * i + 3], h4.w, q2);
             }
+            s0 += q0; s1 += q1; s2 += q2;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            if (kp == b) { ar = s0; az = s1; an = s2; }
         }
+        float h = 0.f;
         if (fin) {
             const float r = sigmoidf_(gir + (ar + bhr));
             const float z = sigmoidf_(giz + (az + bhz));
             const float ghn = an + bhn;
             const float n = tanhf(gin + r * ghn);
-            const float h = (1.f - z) * n + z * hprev;
+            h = (1.f - z) * n + z * hprev;
             hprev = h;
-            if (t + 1 < T) {
-                const uint32_t off = (uint32_t)((((cur ^ 1) * GRU2_BGMAX + kp) * 8 * KSP) * 4) + dst_off;
-                for (int rk = 0; rk < NC; ++rk)
-                    gru_st_async(gru_mapa(hs_addr + off, (uint32_t)rk), h, gru_mapa(bar0 + 8 * (cur ^ 1), (uint32_t)rk));
-            }
             const long long row = row0 + t;
             h_out[row * ldh + uu] = h;
             if (SAVE) {
@@ -361,8 +364,147 @@ gru_fwd2_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, co
             }
             gir = nr; giz = nz; gin = nn;
         }
+        // gather the warp's four units of batch entry (lane & 7) into one 16-byte message
+        float4 h4;
+        h4.x = __shfl_sync(0xffffffffu, h, (lane & 7));
+        h4.y = __shfl_sync(0xffffffffu, h, (lane & 7) + 8);
+        h4.z = __shfl_sync(0xffffffffu, h, (lane & 7) + 16);
+        h4.w = __shfl_sync(0xffffffffu, h, (lane & 7) + 24);
+        if (sender && t + 1 < T) {
+            const uint32_t off = (uint32_t)((((cur ^ 1) * GRU2_BGMAX + lane) * VP + u0 + 4 * (tid >> 5)) * 4);
+            for (int rk = 0; rk < NC; ++rk)
+                gru_st_async4(gru_mapa(hs_addr + off, (uint32_t)rk), h4, gru_mapa(bar0 + 8 * (cur ^ 1), (uint32_t)rk));
+        }
     }
     cluster.sync();      // no CTA leaves while a peer could still address its shared memory
+}
+
+// ---------------------------------------------------------------------------- backward, v2
+// Same organisation for BPTT.  Per step (t descending) lane (unit, batch) turns dh = dh_out[t] + dh_rec
+// into the three gate gradients, stores dgi / dgh, and the warp pushes them (three 16-byte messages:
+// the r, z and n thirds of the 3H-vector) to every CTA; after the mbarrier wait each thread
+// accumulates its slice of  dh_rec[u] = sum_j W_hh[j][u] * dgh[j]  (W_hh^T slice in registers).
+template <int KC>
+__global__ void __launch_bounds__(256)
+gru_bwd2_kernel(const float* __restrict__ dh_out, int ldd, const float* __restrict__ h_out, int ldh,
+                const float* __restrict__ save, const float* __restrict__ w_hh, float* __restrict__ dgi,
+                float* __restrict__ dgh, int B, int T, int H, int nu, int BG) {
+    constexpr int VP = 32 * KC;                          // padded length of ONE third (r | z | n) of the vector
+    cg::cluster_group cluster = cg::this_cluster();
+    const int NC = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int b0 = (blockIdx.x / NC) * BG;
+    const int nb = min(BG, B - b0);
+    const int u0 = rank * nu;
+    extern __shared__ __align__(16) float ds_dyn[];      // [2][BG][3][VP]
+    __shared__ __align__(8) uint64_t bars[2];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int kp = tid & 7, ul = tid >> 3;
+    const int uu = u0 + ul;
+    const bool active = ul < nu && uu < H;
+    const int H3 = 3 * H;
+
+    for (int i = tid; i < 2 * BG * 3 * VP; i += 256) ds_dyn[i] = 0.f;
+    const uint32_t bar0 = gru_smem_u32(&bars[0]);
+    const uint32_t tx_bytes = 3u * 4u * (uint32_t)((H + 3) & ~3) * (uint32_t)nb;
+    if (tid == 0) {
+        gru_mbar_init(bar0, 1);
+        gru_mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (T > 1) gru_mbar_expect(bar0, tx_bytes);          // sends of the first processed step (index 0)
+        if (T > 2) gru_mbar_expect(bar0 + 8, tx_bytes);
+    }
+    // W_hh^T slice: wt[g][4i+e] = w_hh[g*H + j][uu],  j = 4*(8i+kp)+e
+    float wt[3][4 * KC];
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int i = 0; i < KC; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = 4 * (8 * i + kp) + e;
+                wt[g][4 * i + e] = (active && j < H) ? __ldg(w_hh + ((long long)g * H + j) * H + uu) : 0.f;
+            }
+    const bool fin = active && kp < nb;
+    const bool sender = lane < nb && (u0 + 4 * (tid >> 5)) < H && 4 * (tid >> 5) < nu;
+    const long long row0 = (long long)(b0 + (fin ? kp : 0)) * T;
+    float dh_rec = 0.f;
+    float p_dh = 0.f, p_r = 0.f, p_z = 0.f, p_n = 0.f, p_g = 0.f, p_hp = 0.f;
+    auto fetch = [&](int t) {
+        const long long row = row0 + t;
+        p_dh = dh_out[row * ldd + uu];
+        const float* sv = save + row * 4 * H;
+        p_r = sv[uu]; p_z = sv[H + uu]; p_n = sv[2 * H + uu]; p_g = sv[3 * H + uu];
+        p_hp = t > 0 ? h_out[(row - 1) * ldh + uu] : 0.f;
+    };
+    if (fin) fetch(T - 1);
+    const uint32_t ds_addr = gru_smem_u32(ds_dyn);
+    __syncthreads();
+    cluster.sync();
+
+    for (int s = 0; s < T; ++s) {                        // s-th processed step, t = T-1-s
+        const int t = T - 1 - s;
+        const int cur = s & 1;                           // buffer / barrier written by this step's sends
+        float drp = 0.f, dzp = 0.f, dghn = 0.f, dh_direct = 0.f;
+        if (fin) {
+            const float dh = p_dh + dh_rec;
+            const float r = p_r, z = p_z, n = p_n, ghn = p_g, hp = p_hp;
+            if (t > 0) fetch(t - 1);
+            const float dn = dh * (1.f - z);
+            const float dz = dh * (hp - n);
+            const float dnp = dn * (1.f - n * n);
+            dzp = dz * z * (1.f - z);
+            drp = dnp * ghn * r * (1.f - r);
+            dghn = dnp * r;
+            const long long row = row0 + t;
+            float* gi_ = dgi + row * H3;
+            float* gh_ = dgh + row * H3;
+            gi_[uu] = drp; gi_[H + uu] = dzp; gi_[2 * H + uu] = dnp;
+            gh_[uu] = drp; gh_[H + uu] = dzp; gh_[2 * H + uu] = dghn;
+            dh_direct = dh * z;
+        }
+        if (t == 0) break;                               // nothing flows further back
+        float4 m0, m1, m2;
+        const int src = lane & 7;
+        m0.x = __shfl_sync(0xffffffffu, drp, src);      m0.y = __shfl_sync(0xffffffffu, drp, src + 8);
+        m0.z = __shfl_sync(0xffffffffu, drp, src + 16); m0.w = __shfl_sync(0xffffffffu, drp, src + 24);
+        m1.x = __shfl_sync(0xffffffffu, dzp, src);      m1.y = __shfl_sync(0xffffffffu, dzp, src + 8);
+        m1.z = __shfl_sync(0xffffffffu, dzp, src + 16); m1.w = __shfl_sync(0xffffffffu, dzp, src + 24);
+        m2.x = __shfl_sync(0xffffffffu, dghn, src);      m2.y = __shfl_sync(0xffffffffu, dghn, src + 8);
+        m2.z = __shfl_sync(0xffffffffu, dghn, src + 16); m2.w = __shfl_sync(0xffffffffu, dghn, src + 24);
+        if (sender) {
+            const uint32_t off = (uint32_t)((((cur * BG + lane) * 3) * VP + u0 + 4 * (tid >> 5)) * 4);
+            for (int rk = 0; rk < NC; ++rk) {
+                const uint32_t ra = gru_mapa(ds_addr + off, (uint32_t)rk), rb = gru_mapa(bar0 + 8 * cur, (uint32_t)rk);
+                gru_st_async4(ra, m0, rb);
+                gru_st_async4(ra + 4 * VP, m1, rb);
+                gru_st_async4(ra + 8 * VP, m2, rb);
+            }
+        }
+        gru_mbar_wait(bar0 + 8 * cur, (uint32_t)(s >> 1) & 1u);
+        if (tid == 0 && s + 2 <= T - 2) gru_mbar_expect(bar0 + 8 * cur, tx_bytes);
+        float acc = 0.f;
+        for (int b = 0; b < nb; ++b) {
+            const float4* dv = reinterpret_cast<const float4*>(ds_dyn + ((cur * BG + b) * 3) * VP) + kp;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < KC; ++i) {
+                const float4 d0 = dv[8 * i], d1 = dv[8 * i + VP / 4], d2 = dv[8 * i + 2 * (VP / 4)];
+                a0 = fmaf(wt[0][4 * i], d0.x, a0); a0 = fmaf(wt[0][4 * i + 1], d0.y, a0);
+                a0 = fmaf(wt[0][4 * i + 2], d0.z, a0); a0 = fmaf(wt[0][4 * i + 3], d0.w, a0);
+                a1 = fmaf(wt[1][4 * i], d1.x, a1); a1 = fmaf(wt[1][4 * i + 1], d1.y, a1);
+                a1 = fmaf(wt[1][4 * i + 2], d1.z, a1); a1 = fmaf(wt[1][4 * i + 3], d1.w, a1);
+                a2 = fmaf(wt[2][4 * i], d2.x, a2); a2 = fmaf(wt[2][4 * i + 1], d2.y, a2);
+                a2 = fmaf(wt[2][4 * i + 2], d2.z, a2); a2 = fmaf(wt[2][4 * i + 3], d2.w, a2);
+            }
+            float sum = a0 + a1 + a2;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (kp == b) acc = sum;
+        }
+        dh_rec = dh_direct + acc;
+    }
+    cluster.sync();
 }
 
 template <typename K, typename... Args>
@@ -396,15 +538,36 @@ static int launch_cluster(K kernel, int nblocks, int NC, size_t smem, cudaStream
 
 using namespace m2d;
 
-template <int KS>
+struct Gru2Plan { int NC, nu, BG, KC; };
+static Gru2Plan gru2_plan(int B, int H) {
+    Gru2Plan p;
+    p.NC = H <= 32 ? 1 : (H <= 64 ? 2 : (H <= 128 ? 4 : 8));
+    p.nu = (((H + p.NC - 1) / p.NC) + 3) & ~3;       // units per CTA, multiple of 4 (<= 32)
+    p.BG = B <= 18 ? 1 : (B + 17) / 18;
+    if (p.BG > GRU2_BGMAX) p.BG = GRU2_BGMAX;
+    p.KC = (H + 31) / 32;
+    return p;
+}
+
+template <int KC>
 static int launch_gru2(const float* gi, const float* w_hh, const float* b_hh, float* h_out, int ldh, float* save,
-                       int B, int T, int H, int NC, int nu, int BG, cudaStream_t st) {
-    int groups = (B + BG - 1) / BG;
+                       int B, int T, int H, const Gru2Plan& p, cudaStream_t st) {
+    int groups = (B + p.BG - 1) / p.BG;
     if (save)
-        return launch_cluster(gru_fwd2_kernel<KS, true>, groups * NC, NC, 0, st, gi, w_hh, b_hh, h_out, ldh, save,
-                              B, T, H, nu, BG);
-    return launch_cluster(gru_fwd2_kernel<KS, false>, groups * NC, NC, 0, st, gi, w_hh, b_hh, h_out, ldh, save, B,
-                          T, H, nu, BG);
+        return launch_cluster(gru_fwd2_kernel<KC, true>, groups * p.NC, p.NC, 0, st, gi, w_hh, b_hh, h_out, ldh, save,
+                              B, T, H, p.nu, p.BG);
+    return launch_cluster(gru_fwd2_kernel<KC, false>, groups * p.NC, p.NC, 0, st, gi, w_hh, b_hh, h_out, ldh, save,
+                          B, T, H, p.nu, p.BG);
+}
+
+template <int KC>
+static int launch_gru2_bwd(const float* dh_out, int ldd, const float* h_out, int ldh, const float* save,
+                           const float* w_hh, float* dgi, float* dgh, int B, int T, int H, const Gru2Plan& p,
+                           cudaStream_t st) {
+    int groups = (B + p.BG - 1) / p.BG;
+    size_t smem = (size_t)2 * p.BG * 3 * 32 * KC * sizeof(float);
+    return launch_cluster(gru_bwd2_kernel<KC>, groups * p.NC, p.NC, smem, st, dh_out, ldd, h_out, ldh, save, w_hh,
+                          dgi, dgh, B, T, H, p.nu, p.BG);
 }
 
 namespace m2d { int g_gru_impl = 2; }
@@ -414,19 +577,18 @@ extern "C" int m2d_gru_forward(const float* gi, const float* w_hh, const float* 
                                int ldh, float* save, int B, int T, int H, void* stream) {
     M2D_REQUIRE(gi && w_hh && b_hh && h_out && B > 0 && T > 0 && H > 0 && ldh >= H, "gru_forward: bad args");
     if (m2d::g_gru_impl == 2 && H <= 256) {
-        const int NC = H <= 32 ? 1 : (H <= 64 ? 2 : (H <= 128 ? 4 : 8));
-        const int nu = (H + NC - 1) / NC;
-        int BG = B <= 18 ? 1 : (B + 17) / 18;
-        if (BG > GRU2_BGMAX) BG = GRU2_BGMAX;
-        const int ks = (H + 7) / 8;
+        const Gru2Plan p = gru2_plan(B, H);
         cudaStream_t st = (cudaStream_t)stream;
-        if (ks <= 2) return launch_gru2<2>(gi, w_hh, b_hh, h_out, ldh, save, B, T, H, NC, nu, BG, st);
-        if (ks <= 4) return launch_gru2<4>(gi, w_hh, b_hh, h_out, ldh, save, B, T, H, NC, nu, BG, st);
-        if (ks <= 8) return launch_gru2<8>(gi, w_hh, b_hh, h_out, ldh, save, B, T, H, NC, nu, BG, st);
-        if (ks <= 16) return launch_gru2<16>(gi, w_hh, b_hh, h_out, ldh, save, B, T, H, NC, nu, BG, st);
-        if (ks <= 20) return launch_gru2<20>(gi, w_hh, b_hh, h_out, ldh, save, B, T, H, NC, nu, BG, st);
-        if (ks <= 24) return launch_gru2<24>(gi, w_hh, b_hh, h_out, ldh, save, B, T, H, NC, nu, BG, st);
-        return launch_gru2<32>(gi, w_hh, b_hh, h_out, ldh, save, B, T, H, NC, nu, BG, st);
+        switch (p.KC) {
+            case 1: return launch_gru2<1>(gi, w_hh, b_hh, h_out, ldh, save, B, T, H, p, st);
+            case 2: return launch_gru2<2>(gi, w_hh, b_hh, h_out, ldh, save, B, T, H, p, st);
+            case 3: return launch_gru2<3>(gi, w_hh, b_hh, h_out, ldh, save, B, T, H, p, st);
+            case 4: return launch_gru2<4>(gi, w_hh, b_hh, h_out, ldh, save, B, T, H, p, st);
+            case 5: return launch_gru2<5>(gi, w_hh, b_hh, h_out, ldh, save, B, T, H, p, st);
+            case 6: return launch_gru2<6>(gi, w_hh, b_hh, h_out, ldh, save, B, T, H, p, st);
+            case 7: return launch_gru2<7>(gi, w_hh, b_hh, h_out, ldh, save, B, T, H, p, st);
+            default: return launch_gru2<8>(gi, w_hh, b_hh, h_out, ldh, save, B, T, H, p, st);
+        }
     }
     GruPlan p = make_plan(H);
     size_t smem = (size_t)(3 * p.nu * p.HP + 2 * p.BG * p.HP) * sizeof(float);
@@ -444,6 +606,20 @@ extern "C" int m2d_gru_backward(const float* dh_out, int ldd, const float* h_out
                                 int T, int H, void* stream) {
     M2D_REQUIRE(dh_out && h_out && save && w_hh && dgi && dgh && B > 0 && T > 0 && H > 0,
                 "gru_backward: bad args");
+    if (m2d::g_gru_impl == 2 && H <= 256) {
+        const Gru2Plan p = gru2_plan(B, H);
+        cudaStream_t st = (cudaStream_t)stream;
+        switch (p.KC) {
+            case 1: return launch_gru2_bwd<1>(dh_out, ldd, h_out, ldh, save, w_hh, dgi, dgh, B, T, H, p, st);
+            case 2: return launch_gru2_bwd<2>(dh_out, ldd, h_out, ldh, save, w_hh, dgi, dgh, B, T, H, p, st);
+            case 3: return launch_gru2_bwd<3>(dh_out, ldd, h_out, ldh, save, w_hh, dgi, dgh, B, T, H, p, st);
+            case 4: return launch_gru2_bwd<4>(dh_out, ldd, h_out, ldh, save, w_hh, dgi, dgh, B, T, H, p, st);
+            case 5: return launch_gru2_bwd<5>(dh_out, ldd, h_out, ldh, save, w_hh, dgi, dgh, B, T, H, p, st);
+            case 6: return launch_gru2_bwd<6>(dh_out, ldd, h_out, ldh, save, w_hh, dgi, dgh, B, T, H, p, st);
+            case 7: return launch_gru2_bwd<7>(dh_out, ldd, h_out, ldh, save, w_hh, dgi, dgh, B, T, H, p, st);
+            default: return launch_gru2_bwd<8>(dh_out, ldd, h_out, ldh, save, w_hh, dgi, dgh, B, T, H, p, st);
+        }
+    }
     GruPlan p = make_plan(H);
     size_t smem = (size_t)(p.nu * p.HP3 + 2 * p.BG * p.HP3) * sizeof(float);
     M2D_REQUIRE(smem <= 220 * 1024, "gru_backward: hidden size %d needs %zu B of shared memory", H, smem);
