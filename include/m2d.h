@@ -115,6 +115,8 @@ typedef struct {
     int Cout, T, Cc;
     int sr, roff0, droff;
     float* dw;
+    int packed;                          /* 0: dw in the PyTorch layout (Cout, Cc, T);  1: dw[co, t*Cc + c] (coalesced
+                                            stores; m2d_pack_batch kind M2D_UNPACK_GRAD turns it into the PyTorch layout) */
     float scale, beta;
     float* ws; long long ws_floats;
 } m2d_wgrad_args;
@@ -133,7 +135,8 @@ int m2d_pack_conv_bwd(const float* w, float* wd, int Cout, int Cin, int k, int s
  * DEVICE memory (pointers are stable, so it is built once).  kind FWD / BWD as above; FULL_BWD is
  * the backward layout of a convolution whose kernel spans its whole input (fconv, l6, encoder heads),
  * used as a Linear over (tap, channel):  dst[(t*Cin + ci), co] = w[co, ci, t]. */
-enum { M2D_PACK_FWD = 0, M2D_PACK_BWD = 1, M2D_PACK_FULL_BWD = 2 };
+enum { M2D_PACK_FWD = 0, M2D_PACK_BWD = 1, M2D_PACK_FULL_BWD = 2,
+       M2D_UNPACK_GRAD = 3 /* dst[co, ci, t] = w[co, t*Cin + ci]: packed weight gradient -> parameter layout */ };
 typedef struct {
     const float* w; float* dst;           /* dst may be NULL (no exact copy wanted) */
     float* dst_hi; float* dst_lo;         /* optional 3xTF32 split copies in the m2d_rowconv_args.w_hi layout: the

@@ -45,6 +45,7 @@ class WgradArgs(C.Structure):
         ("Cout", C.c_int), ("T", C.c_int), ("Cc", C.c_int),
         ("sr", C.c_int), ("roff0", C.c_int), ("droff", C.c_int),
         ("dw", f32p),
+        ("packed", C.c_int),
         ("scale", C.c_float), ("beta", C.c_float),
         ("ws", f32p), ("ws_floats", i64),
     ]

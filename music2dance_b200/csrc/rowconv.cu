@@ -360,7 +360,7 @@ __global__ void wgrad_reduce_kernel(const m2d_wgrad_args a, const int Ncols, con
         int rem = (int)(idx - (long long)co * Ncols);
         int c = rem / a.T;
         int t = rem - c * a.T;
-        long long src = (long long)co * Ncols + (long long)t * a.Cc + c;
+        long long src = a.packed ? idx : (long long)co * Ncols + (long long)t * a.Cc + c;
         float v = 0.f;
         for (int z = 0; z < splits; ++z) v += a.ws[(long long)z * total + src];
         v *= a.scale;
@@ -425,6 +425,14 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const m2d_pack_desc* __
          idx += (long long)gridDim.x * blockDim.x) {
         float v;
         long long pidx;                               // index in the padded split copies
+        if (d.kind == M2D_UNPACK_GRAD) {              // dst[co, ci, t] = w[co, t*Cin + ci]  (idx walks dst)
+            int t = (int)(idx % k);
+            long long r = idx / k;
+            int ci = (int)(r % Cin);
+            int co = (int)(r / Cin);
+            d.dst[idx] = w[((long long)co * k + t) * Cin + ci];
+            continue;
+        }
         if (d.kind == M2D_PACK_FWD) {                 // dst[co, t*Cin + ci]
             int ci = (int)(idx % Cin);
             long long r = idx / Cin;

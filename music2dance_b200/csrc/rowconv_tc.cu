@@ -967,6 +967,16 @@ wgrad_tc_kernel(const m2d_wgrad_args a, const int Ktot, const int Ncols) {
             const float4 q = *reinterpret_cast<const float4*>(Cs + rl * TC_CLD + c4);
             v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
         }
+        if (a.packed) {                                  // dw[co, t*Cc + c]: one aligned 16-byte store
+            float4* d = reinterpret_cast<float4*>(a.dw + (long long)co * Ncols + n);
+            float4 o = make_float4(v[0] * a.scale, v[1] * a.scale, v[2] * a.scale, v[3] * a.scale);
+            if (a.beta != 0.f) {
+                const float4 p = *d;
+                o.x += a.beta * p.x; o.y += a.beta * p.y; o.z += a.beta * p.z; o.w += a.beta * p.w;
+            }
+            *d = o;
+            continue;
+        }
         float* d = a.dw + ((long long)co * a.Cc + c) * a.T + t;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -1007,7 +1017,8 @@ static int launch_wgrad_tc(const m2d_wgrad_args& a, int Ktot, int Ncols, int wan
 // (split-K partials are reduced across the cluster inside the kernel).
 int wgrad_tc_dispatch(const m2d_wgrad_args& a, int Ktot, int Ncols, int mode, cudaStream_t st) {
     const bool ok = a.win_T == 0 && a.Cc % 4 == 0 && a.Cout % 4 == 0 && a.x_ld % 4 == 0 && a.x_bs % 4 == 0 &&
-                    a.dy_ld % 4 == 0 && a.dy_bs % 4 == 0 && aligned16(a.x) && aligned16(a.dy);
+                    a.dy_ld % 4 == 0 && a.dy_bs % 4 == 0 && aligned16(a.x) && aligned16(a.dy) &&
+                    (!a.packed || aligned16(a.dw));
     if (!ok || (long long)a.Cout * Ncols * Ktot < (1ll << 18)) return 1;
     const int nsteps = (int)cdiv(Ktot, TC_BK);
     const long long tiles = cdiv(a.Cout, TC_BM) * cdiv(Ncols, TC_BNMAX);

@@ -101,6 +101,7 @@ class Engine:
         return self.slot, self.slot_gen[self.slot]
 
     def grads_in_param_order(self, scale=None):
+        self.net.unpack_grads()          # tap-major weight gradients -> parameter layout
         out = []
         for n in self.fp.names:
             g = self.fp.G.get(n)

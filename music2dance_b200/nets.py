@@ -89,6 +89,9 @@ class ConvLayer:
             self.res.append((rho, Trho, off, poff, ld))
             off += Cin * Cout * Trho
             poff += Cin * ld
+        # weight gradients of real convolutions are produced tap-major [co, t*Cin + ci] (coalesced stores) and
+        # turned into the parameter layout by one batched kernel per network (unpack_entries)
+        self.gwp = z(n) if (gw is not None and k > 1 and Cin > 1) else None
         self.ldb = (Cout + 3) // 4 * 4                      # Linear / full-length form: [k*Cin rows][Cout]
         if self.wd is not None:
             m = (k * Cin * self.ldb) if (self.full or k == 1) else poff
@@ -108,6 +111,19 @@ class ConvLayer:
             else:
                 e.append((self.w, self.wd, self.wdh, self.wdl, self.Cout, self.Cin, self.k, self.s, ops.PACK_BWD))
         return e
+
+    def unpack_entries(self):
+        if self.gwp is None:
+            return []
+        return [(self.gwp, self.gw, None, None, self.Cout, self.Cin, self.k, 1, ops.UNPACK_GRAD)]
+
+    def unpack_grad(self):
+        """Single-layer form of the batched gradient unpack (tests)."""
+        if self.gwp is not None:
+            tab = getattr(self, "_utab", None)
+            if tab is None:
+                tab = self._utab = ops.pack_table(self.unpack_entries(), self.w.device)
+            ops.pack_batch(*tab)
 
     def pack(self):
         tab = getattr(self, "_tab", None)
@@ -157,8 +173,9 @@ class ConvLayer:
 
     def wgrad(self, dy, x, ws, scale=1.0, beta=0.0, win=None, bias=True, acc=None, bbeta=None):
         """gw = beta*gw + scale*dW;  gb = bbeta*gb + scale*db (bbeta defaults to beta)."""
-        ops.wgrad(dy, x, self.gw, Cout=self.Cout, T=self.k, Cc=self.Cin, sr=self.s, roff0=-self.p, droff=1,
-                  scale=scale, beta=beta, ws=ws, win=win)
+        ops.wgrad(dy, x, self.gw if self.gwp is None else self.gwp, Cout=self.Cout, T=self.k, Cc=self.Cin,
+                  sr=self.s, roff0=-self.p, droff=1, scale=scale, beta=beta, ws=ws, win=win,
+                  packed=self.gwp is not None)
         if bias and self.gb is not None:
             ops.colsum(dy.flat_rows(), self.gb, acc, scale=scale, beta=beta if bbeta is None else bbeta)
 
@@ -226,6 +243,18 @@ class ConvBNAct:
         cv.wgrad(dc, self.x, wk.scratch, win=win, acc=wk.acc_slot(cv.Cout))
         if e_x is not None:
             cv.dgrad(dc, e_x, ws=wk.scratch, **dg)
+
+
+def _unpack_net_grads(net):
+    """Tap-major weight gradients -> parameter layout, ONE launch per network (call once all weight
+    gradients of a backward phase have been accumulated, before Adam / all-reduce / autograd hand-off)."""
+    tab = getattr(net, "_unpack_tab", None)
+    if tab is None:
+        entries = [e for c in net.convs() for e in c.unpack_entries()]
+        tab = ops.pack_table(entries, net.dev) if entries else (None, 0)
+        net._unpack_tab = tab
+    if tab[1]:
+        ops.pack_batch(tab[0], tab[1])
 
 
 def _pack_net(net):
@@ -513,6 +542,9 @@ class GeneratorNet:
     def pack(self):
         _pack_net(self)
 
+    def unpack_grads(self):
+        _unpack_net_grads(self)
+
     def window(self, T):
         cfg = self.cfg
         pad = cfg["pad_samples"]
@@ -640,6 +672,9 @@ class CriticNet:
 
     def pack(self):
         _pack_net(self)
+
+    def unpack_grads(self):
+        _unpack_net_grads(self)
 
     # ---------------------------------------------------------------- pose branch
     def pose_fwd(self, X, n, tag):

@@ -123,7 +123,7 @@ def rowconv(x, w, y, *, T, Cc, N, sr=1, roff0=0, droff=1, w_ld=None, bias=None, 
     call("m2d_rowconv", C.byref(a), _stream())
 
 
-def wgrad(dy, x, dw, *, Cout, T, Cc, sr=1, roff0=0, droff=1, scale=1.0, beta=0.0, ws=None, win=None):
+def wgrad(dy, x, dw, *, Cout, T, Cc, sr=1, roff0=0, droff=1, scale=1.0, beta=0.0, ws=None, win=None, packed=False):
     a = WgradArgs()
     a.dy, a.dy_bs, a.dy_ld, a.dy_rows = dy.ptr, dy.bs, dy.ld, dy.rows
     a.nb = dy.nb
@@ -136,6 +136,7 @@ def wgrad(dy, x, dw, *, Cout, T, Cc, sr=1, roff0=0, droff=1, scale=1.0, beta=0.0
     a.Cout, a.T, a.Cc = Cout, T, Cc
     a.sr, a.roff0, a.droff = sr, roff0, droff
     a.dw = _p(dw)
+    a.packed = int(packed)
     a.scale, a.beta = scale, beta
     a.ws, a.ws_floats = ws.data_ptr(), ws.numel()
     LAUNCHES[0] += 1
@@ -152,7 +153,7 @@ def pack_conv_bwd(w, wd, Cout, Cin, k, stride):
     call("m2d_pack_conv_bwd", _p(w), _p(wd), Cout, Cin, k, stride, _stream())
 
 
-PACK_FWD, PACK_BWD, PACK_FULL_BWD = 0, 1, 2
+PACK_FWD, PACK_BWD, PACK_FULL_BWD, UNPACK_GRAD = 0, 1, 2, 3
 
 
 def pack_table(entries, device):

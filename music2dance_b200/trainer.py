@@ -101,6 +101,7 @@ class Phase3Trainer:
         gradient_penalty_pass(D, fw, B, "c:gp", gamma, 0.0, self.gp_buf, self.k0, self.k1)
         wasserstein_backward(D, fw, B, 2 * B, (-1.0, 1.0), B, "c:w", beta=1.0)
         ops.wgan_scalars(sums, self.gp_buf, B, 1, 1, gamma, 0.0, 0, self.log_c[i])
+        D.unpack_grads()
         if update:
             self._adam(self.de, self.mD, self.vD, self.stepD, self.cfg["lr_critic"])
 
@@ -129,6 +130,7 @@ class Phase3Trainer:
         ops.pose_losses(real, self.fake_g, dfake, B, T, O, beta, eta, True, sums[2:4])
         ops.wgan_scalars(sums, None, B, B * T * O, B * (T - 1) * O, beta, eta, 1, self.log_g)
         G.backward(dfake.flat_rows())
+        G.unpack_grads()
         if update:
             self._adam(self.ge, self.mG, self.vG, self.stepG, self.cfg["lr_gen"])
 

@@ -101,10 +101,12 @@ def test_conv_fwd_dgrad_wgrad(lib, case):
     d = cl(dy * (y_ref > 0).float())
     D = Mat.of(d, B, Lout, Cout)
     lay.wgrad(D, X, scratch, acc=acc[:Cout])
+    lay.unpack_grad()
     close(lay.gw, wr.grad, what="wgrad")
     close(lay.gb, br.grad, what="bgrad")
     # accumulate form: beta=1, scale=0.5
     lay.wgrad(D, X, scratch, scale=0.5, beta=1.0, acc=acc[:Cout])
+    lay.unpack_grad()
     close(lay.gw, 1.5 * wr.grad, what="wgrad-acc")
     if Cin > 1:
         DX = Mat.of(torch.empty(B, L, Cin, device=DEV), B, L, Cin)
@@ -175,6 +177,7 @@ def test_full_length_conv(lib, case):
     lay.dgrad(D, DX, ws=scratch, mask=Mat.of(cl(msk), B, L, Cin), mask_mode=1)
     close(ncl(DX, B, L, Cin), xr.grad * (msk > 0), what="dgrad")
     lay.wgrad(D, X, scratch, acc=acc[:Cout])
+    lay.unpack_grad()
     close(lay.gw, wr.grad, what="wgrad")
 
 
@@ -233,6 +236,7 @@ def test_windowed_first_conv(lib):
     scratch = torch.empty(1 << 22, device=DEV)
     acc = torch.zeros(64, dtype=torch.float64, device=DEV)
     lay.wgrad(Mat.of(cl(dy), B * T, Lout, 32), audio.to(DEV), scratch, win=win, acc=acc[:32])
+    lay.unpack_grad()
     close(lay.gw, wr.grad, what="windowed wgrad")
 
 
