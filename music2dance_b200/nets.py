@@ -7,6 +7,8 @@ losses.py:5-60, phase3/train.py:186-237.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -24,6 +26,7 @@ class Workspace:
         self.device = device
         self.bufs = {}
         self.scratch = torch.empty(scratch_floats, dtype=torch.float32, device=device)
+        self.scratch_a = torch.empty(scratch_floats, dtype=torch.float32, device=device)   # side-stream work
         self.acc = torch.zeros(acc_doubles, dtype=torch.float64, device=device)
         self.acc_used = 0
 
@@ -56,11 +59,31 @@ class Workspace:
         return s
 
     def bytes(self):
-        return sum(t.numel() * t.element_size() for t in self.bufs.values()) + self.scratch.numel() * 4
+        return sum(t.numel() * t.element_size() for t in self.bufs.values()) + self.scratch.numel() * 8
 
 
 def conv_out_len(L, k, s, p):
     return (L + 2 * p - k) // s + 1
+
+
+class _Fork:
+    """`with net.fork():` runs the enclosed launches on the side stream, ordered after everything already
+    enqueued on the current stream; `net.join()` makes the current stream wait for them."""
+
+    def __init__(self, side):
+        self.side, self.ctx = side, None
+
+    def __enter__(self):
+        if self.side is not None:
+            self.side.wait_stream(torch.cuda.current_stream())
+            self.ctx = torch.cuda.stream(self.side)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
 
 
 class ConvLayer:
@@ -663,6 +686,17 @@ class CriticNet:
         self.fc1 = _conv_from(P, G, "fc1", self.F, 128, 1, 1, 0, 1)
         self.fc2 = _conv_from(P, G, "fc2", 128, 1, 1, 1, 0, 1)
         self.wk = Workspace(self.dev)
+        # the audio branch is independent of the pose branch between the inputs and the fusion MLP:
+        # it runs on a side stream (fork / join below; CUDA-graph capture turns that into parallel branches)
+        self.par = os.environ.get("M2D_OVERLAP", "1") != "0" and not self.ablated
+        self.s_aud = torch.cuda.Stream(device=self.dev) if self.par else None
+
+    def fork(self):
+        return _Fork(self.s_aud if self.par else None)
+
+    def join(self):
+        if self.par:
+            torch.cuda.current_stream().wait_stream(self.s_aud)
 
     def convs(self):
         c = [self.s_conv1] + [x for blk in self.s_blocks for x in blk] + [self.s_fconv]
@@ -779,10 +813,10 @@ class CriticNet:
         sv = {"X": x, "q": []}
         for l in self.a_layers:
             q = wk.mat(f"{tag}:q{l.name}", n, l.Lout, l.Cout)
-            l.fwd(x, q, act=ACT_RELU, ws=wk.scratch)
+            l.fwd(x, q, act=ACT_RELU, ws=wk.scratch_a)
             sv["q"].append(q)
             x = q
-        self.a_l6.fwd(x, code_out.as_rows(n, 1), act=self.act, ws=wk.scratch)
+        self.a_l6.fwd(x, code_out.as_rows(n, 1), act=self.act, ws=wk.scratch_a)
         sv["code"] = code_out
         return sv
 
@@ -794,11 +828,11 @@ class CriticNet:
         dl = {"l6": d_code}
         q = sv["q"]
         d = wk.mat(f"{tag}:dq5", n, q[4].rows, q[4].cols)
-        self.a_l6.dgrad(d_code.as_rows(n, 1), d, ws=wk.scratch, mask=q[4], mask_mode=ACT_RELU)
+        self.a_l6.dgrad(d_code.as_rows(n, 1), d, ws=wk.scratch_a, mask=q[4], mask_mode=ACT_RELU)
         dl[4] = d
         for i in range(4, 0, -1):
             dn = wk.mat(f"{tag}:dq{i}", n, q[i - 1].rows, q[i - 1].cols)
-            self.a_layers[i].dgrad(dl[i], dn, ws=wk.scratch, mask=q[i - 1], mask_mode=ACT_RELU)
+            self.a_layers[i].dgrad(dl[i], dn, ws=wk.scratch_a, mask=q[i - 1], mask_mode=ACT_RELU)
             dl[i - 1] = dn
         sv["delta"] = dl
         if dX is not None:
@@ -814,10 +848,10 @@ class CriticNet:
         kw = dict(scale=scale, beta=beta, bias=bias, bbeta=bbeta)
         x = X
         for i, l in enumerate(self.a_layers):
-            l.wgrad(dl[i], x, wk.scratch, acc=wk.acc_slot(l.Cout), **kw)
+            l.wgrad(dl[i], x, wk.scratch_a, acc=wk.acc_slot(l.Cout), **kw)
             x = q[i]
         n = x.nb
-        self.a_l6.wgrad(dl["l6"].as_rows(n, 1), x, wk.scratch, acc=wk.acc_slot(self.a_l6.Cout), **kw)
+        self.a_l6.wgrad(dl["l6"].as_rows(n, 1), x, wk.scratch_a, acc=wk.acc_slot(self.a_l6.Cout), **kw)
 
     def audio_tangent(self, sv, V, n, tag, t_code):
         wk = self.wk
@@ -827,11 +861,11 @@ class CriticNet:
         tq = []
         for i, l in enumerate(self.a_layers):
             t = wk.mat(f"{tag}:t{l.name}", n, l.Lout, l.Cout)
-            l.fwd(x, t, bias=False, ws=wk.scratch, mask=sv["q"][i], mask_mode=ACT_RELU)
+            l.fwd(x, t, bias=False, ws=wk.scratch_a, mask=sv["q"][i], mask_mode=ACT_RELU)
             tq.append(t)
             x = t
         m = dict(mask=sv["code"].as_rows(n, 1), mask_mode=self.act) if self.act != ACT_ID else {}
-        self.a_l6.fwd(x, t_code.as_rows(n, 1), bias=False, ws=wk.scratch, **m)
+        self.a_l6.fwd(x, t_code.as_rows(n, 1), bias=False, ws=wk.scratch_a, **m)
         return {"X": x0, "q": tq}
 
     # ---------------------------------------------------------------- fusion MLP

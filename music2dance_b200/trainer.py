@@ -17,6 +17,8 @@ a batch and the scalar log runs in libm2d_b200 kernels on channels-last activati
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import dp, ops
@@ -55,7 +57,7 @@ class Phase3Trainer:
         self.in_noise_g = torch.zeros(B, T, Nz, **f)
         self.log_c = torch.zeros(nc, 8, **f)
         self.log_g = torch.zeros(8, **f)
-        self.fake_c = torch.zeros(B * T, O, **f)       # generated poses of the last critic iteration
+        self.fake_c = torch.zeros(nc, B * T, O, **f)   # generated poses of every critic iteration
         self.fake_g = torch.zeros(B * T, O, **f)       # ... of the generator update
         nD, nG = self.de.fp.n_live_padded, self.ge.fp.n_live_padded
         self.mD, self.vD = torch.zeros(nD, **f), torch.zeros(nD, **f)
@@ -66,6 +68,11 @@ class Phase3Trainer:
         self.k0, self.k1 = torch.zeros(B, **f), torch.zeros(B, **f)
         self.use_graphs = use_graphs
         self.graphs = None
+        # The generator's weights do not change during the n_critic critic iterations, so its forwards
+        # (one per iteration + the one of the generator update, in the reference's order: BatchNorm
+        # running statistics advance sequentially) run on a side stream and overlap the critic work.
+        self.overlap = os.environ.get("M2D_OVERLAP", "1") != "0"
+        self.s_gen = torch.cuda.Stream(device=dev)
 
     # ------------------------------------------------------------------ pieces
     def _all_reduce(self, flat):
@@ -78,20 +85,31 @@ class Phase3Trainer:
         ops.adam(eng.fp.flat, eng.fp.grad, m, v, n, step, float(lr), gscale=1.0 / self.world)
         eng.net.pack()
 
-    def critic_iteration(self, i, update=True):
+    def _gen_forward(self, i):
+        """Generator forward of critic iteration i (train-mode BatchNorm, no graph kept)."""
+        self.G.forward(self.in_audio[i], self.in_noise[i], self.B, self.T, train=True,
+                       out=Mat.of(self.fake_c[i], 1, self.B * self.T, self.O))
+
+    def _gen_forward_update(self):
+        """Generator forward of the generator update (its activations feed G.backward)."""
+        self.G.forward(self.in_audio[self.nc - 1], self.in_noise_g, self.B, self.T, train=True,
+                       out=Mat.of(self.fake_g, 1, self.B * self.T, self.O))
+
+    def critic_iteration(self, i, update=True, gen_inline=True):
         """train.py:187-216 on staged batch i."""
         B, T, O, D, G = self.B, self.T, self.O, self.D, self.G
         real, audio = self.in_real[i], self.in_audio[i]
-        fake = Mat.of(self.fake_c, 1, B * T, O)
-        G.forward(audio, self.in_noise[i], B, T, train=True, out=fake)
+        if gen_inline:
+            self._gen_forward(i)
+        fake_c = self.fake_c[i]
         wk = D.wk
         wk.acc_reset()
         n3 = 3 * B
         X3 = wk.mat("c:X3", n3, T, O)
         per = T * O
-        ops.interp(real, self.fake_c, self.in_alpha[i], X3, B, per)
+        ops.interp(real, fake_c, self.in_alpha[i], X3, B, per)
         ops.axpby(real, None, rows(X3, B, 2 * B), B * per, 1.0, 0.0)
-        ops.axpby(self.fake_c, None, rows(X3, 2 * B, n3), B * per, 1.0, 0.0)
+        ops.axpby(fake_c, None, rows(X3, 2 * B, n3), B * per, 1.0, 0.0)
         fw = critic_forward(D, X3, None if D.ablated else audio, n3, B, "c", groups=3)
         sums = wk.acc_slot(4)
         d = fw["d"]
@@ -105,13 +123,13 @@ class Phase3Trainer:
         if update:
             self._adam(self.de, self.mD, self.vD, self.stepD, self.cfg["lr_critic"])
 
-    def generator_update(self, update=True):
+    def generator_update(self, update=True, gen_inline=True):
         """train.py:222-237 on the last staged batch."""
         B, T, O, D, G = self.B, self.T, self.O, self.D, self.G
         i = self.nc - 1
         real, audio = self.in_real[i], self.in_audio[i]
-        fake = Mat.of(self.fake_g, 1, B * T, O)
-        G.forward(audio, self.in_noise_g, B, T, train=True, out=fake)
+        if gen_inline:
+            self._gen_forward_update()
         wk = D.wk
         wk.acc_reset()
         n2 = 2 * B
@@ -186,9 +204,28 @@ class Phase3Trainer:
         self.graphs = graphs
 
     def _run_eager(self):
+        if not self.overlap or self.world > 1:
+            for i in range(self.nc):
+                self.critic_iteration(i)
+            self.generator_update()
+            return
+        main = torch.cuda.current_stream()
+        self.s_gen.wait_stream(main)                  # staged inputs, updated generator weights
+        evs = []
+        with torch.cuda.stream(self.s_gen):
+            for i in range(self.nc):
+                self._gen_forward(i)
+                ev = torch.cuda.Event()
+                ev.record(self.s_gen)
+                evs.append(ev)
+            self._gen_forward_update()
+            ev_g = torch.cuda.Event()
+            ev_g.record(self.s_gen)
         for i in range(self.nc):
-            self.critic_iteration(i)
-        self.generator_update()
+            main.wait_event(evs[i])
+            self.critic_iteration(i, gen_inline=False)
+        main.wait_event(ev_g)
+        self.generator_update(gen_inline=False)
 
     def load_batches(self, real, audio, noise, alpha, noise_g, non_blocking=True):
         """Stage one train step's inputs (host or device tensors):

@@ -39,13 +39,15 @@ def critic_forward(D, X, audio, nS, nA, tag, groups=1):
     row groups of nA samples each: Q13 de-duplication), fusion MLP on nS rows."""
     wk = D.wk
     sa = wk.mat(f"{tag}:sa", 1, nS, D.F)
-    svp = D.pose_fwd(X, nS, tag)
-    ops.copy2d(svp["code"], sa.cols_slice(0, D.code))
     sva = None
     if not D.ablated:
-        sva = D.audio_fwd(audio, nA, tag)
-        for g in range(groups):
-            ops.copy2d(sva["code"], rows(sa, g * nA, (g + 1) * nA).cols_slice(D.code, D.F))
+        with D.fork():                                   # audio branch: side stream
+            sva = D.audio_fwd(audio, nA, tag)
+            for g in range(groups):
+                ops.copy2d(sva["code"], rows(sa, g * nA, (g + 1) * nA).cols_slice(D.code, D.F))
+    svp = D.pose_fwd(X, nS, tag)
+    ops.copy2d(svp["code"], sa.cols_slice(0, D.code))
+    D.join()
     u, d = D.fusion_fwd(sa, nS, tag)
     return dict(svp=svp, sva=sva, sa=sa, u=u, d=d)
 
@@ -64,44 +66,51 @@ def gradient_penalty_pass(D, fw, B, tag, scale, beta, gp_out, k0, k1, weight_gra
     ones = wk.vec("ones", B)
     ops.fill(ones, B, 1.0)
     dh, dsa = D.fusion_bwd(Mat(ones, 1, B, 1), u, B, tag)
+    g1 = ss1 = None
+    if not D.ablated:
+        A = D.cfg["audio_length"]
+        ss1 = wk.acc_slot(B)
+        g1 = wk.vec(f"{tag}:g1", B * A)
+        with D.fork():
+            d_a = wk.mat(f"{tag}:d_a", 1, B, code)
+            ops.copy2d(dsa.cols_slice(code, D.F), d_a)
+            D.audio_bwd(sva, d_a, B, tag, wgrads=False, dX=g1)
+            ops.rows_sumsq(g1, B, A, ss1)
     d_s = wk.mat(f"{tag}:d_s", 1, B, code)
     ops.copy2d(dsa.cols_slice(0, code), d_s)
     g0 = wk.mat(f"{tag}:g0", B, T, O)
     D.pose_bwd(svp, d_s, B, tag, wgrads=False, dX=g0)
     ss0 = wk.acc_slot(B)
     ops.rows_sumsq(g0, B, T * O, ss0)
-    g1 = ss1 = None
-    if not D.ablated:
-        A = D.cfg["audio_length"]
-        d_a = wk.mat(f"{tag}:d_a", 1, B, code)
-        ops.copy2d(dsa.cols_slice(code, D.F), d_a)
-        g1 = wk.vec(f"{tag}:g1", B * A)
-        D.audio_bwd(sva, d_a, B, tag, wgrads=False, dX=g1)
-        ss1 = wk.acc_slot(B)
-        ops.rows_sumsq(g1, B, A, ss1)
+    D.join()
     ops.gp_finalize(ss0, ss1, B, gp_out, k0, k1)
     out = dict(g0=g0, g1=g1)
     if not weight_grads:
         return out
     # tangent pass along v = kappa * g
-    ops.scale_rows(g0, k0, g0, B, T * O)
     t_sa = wk.mat(f"{tag}:t_sa", 1, B, D.F)
+    tva = None
+    if not D.ablated:
+        with D.fork():
+            ops.scale_rows(g1, k1, g1, B, A)
+            t_a = wk.mat(f"{tag}:t_a", 1, B, code)
+            tva = D.audio_tangent(sva, g1, B, tag, t_a)
+            ops.copy2d(t_a, t_sa.cols_slice(code, D.F))
+    ops.scale_rows(g0, k0, g0, B, T * O)
     t_s = wk.mat(f"{tag}:t_s", 1, B, code)
     tvp = D.pose_tangent(svp, g0, B, tag, t_s)
     ops.copy2d(t_s, t_sa.cols_slice(0, code))
-    if not D.ablated:
-        ops.scale_rows(g1, k1, g1, B, A)
-        t_a = wk.mat(f"{tag}:t_a", 1, B, code)
-        tva = D.audio_tangent(sva, g1, B, tag, t_a)
-        ops.copy2d(t_a, t_sa.cols_slice(code, D.F))
+    D.join()
     t_h = wk.mat(f"{tag}:t_h", 1, B, 128)
     D.fc1.fwd(t_sa, t_h, bias=False, ws=wk.scratch, mask=u, mask_mode=ACT_RELU)
     # weight gradients: wgrad(first-backward delta, tangent activation)
+    if not D.ablated:
+        with D.fork():
+            D.audio_wgrads(sva["delta"], tva["X"], tva["q"], scale, beta, bias=False)
     ops.colsum(t_h, D.fc2.gw, wk.acc_slot(128), scale=scale, beta=beta)
     D.fc1.wgrad(dh, t_sa, wk.scratch, scale=scale, beta=beta, bias=False)
     D.pose_wgrads(svp["delta"], g0, tvp, scale, beta, bias=False)
-    if not D.ablated:
-        D.audio_wgrads(sva["delta"], tva["X"], tva["q"], scale, beta, bias=False)
+    D.join()
     return out
 
 
@@ -123,6 +132,12 @@ def wasserstein_backward(D, fw, r0, nR, signs, B, tag, beta, dX_rows=None, dX=No
     dh, dsa = D.fusion_bwd(ddm, u, n, tag)
     if param_grads:
         D.fc1.wgrad(dh, sa, wk.scratch, beta=beta, bbeta=0.0, acc=wk.acc_slot(128))
+    if not D.ablated and param_grads:
+        with D.fork():
+            d_a = wk.mat(f"{tag}:d_a", 1, B, code)
+            for g in range(len(signs)):
+                ops.copy2d(rows(dsa, g * B, (g + 1) * B).cols_slice(code, D.F), d_a, accumulate=(g > 0))
+            D.audio_bwd(fw["sva"], d_a, B, tag, scale=1.0, beta=beta, wgrads=True, bbeta=0.0)
     d_s = wk.mat(f"{tag}:d_s", 1, n, code)
     ops.copy2d(dsa.cols_slice(0, code), d_s)
     svp = slice_pose_saves(fw["svp"], r0, r0 + n)
@@ -133,8 +148,4 @@ def wasserstein_backward(D, fw, r0, nR, signs, B, tag, beta, dX_rows=None, dX=No
         g = dX_rows
         D.pose_bwd(slice_pose_saves(svp, g * B, (g + 1) * B), rows(d_s, g * B, (g + 1) * B), B, tag,
                    wgrads=False, dX=dX)
-    if not D.ablated and param_grads:
-        d_a = wk.mat(f"{tag}:d_a", 1, B, code)
-        for g in range(len(signs)):
-            ops.copy2d(rows(dsa, g * B, (g + 1) * B).cols_slice(code, D.F), d_a, accumulate=(g > 0))
-        D.audio_bwd(fw["sva"], d_a, B, tag, scale=1.0, beta=beta, wgrads=True, bbeta=0.0)
+    D.join()
