@@ -371,6 +371,8 @@ def run_b200(args):
         kt.install()
         saved_flag = tr.use_graphs
         tr.use_graphs = False
+        saved_ov = (tr.overlap, tr.D.par)
+        tr.overlap, tr.D.par = False, False             # one stream: every launch is timed alone
         tr.load_batches(*devs[0])
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(dev)
@@ -385,6 +387,7 @@ def run_b200(args):
         torch.cuda.synchronize(dev)
         eager_ms = e0.elapsed_time(e1)
         tr.use_graphs = saved_flag
+        tr.overlap, tr.D.par = saved_ov
         kt.remove()
         fams = kt.summary()
         top = max(fams, key=lambda f: fams[f]["ms"])
@@ -403,6 +406,8 @@ def run_b200(args):
         roof.update({"kernel": top, "launches_per_step": d["launches"],
                      "avg_launch_us": 1e3 * d["ms"] / d["launches"],
                      "share_of_eager_step": d["ms"] / eager_ms,
+                     "measured_in": "one instrumented eager train step, single stream (multi-stream overlap off), "
+                                    "CUDA events around every launch of the family",
                      "peak_source": pk["source"] + ("; TF32 dense peak taken as half the measured sustained bf16 rate "
                                                     "(no TF32 figure in the file); gemm mode " + args.gemm +
                                                     (" issues 3 tensor-core products per algorithmic product"

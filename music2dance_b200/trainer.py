@@ -172,28 +172,46 @@ class Phase3Trainer:
                 self._run_eager()
             graphs.append(("all", g))
         else:
-            # NCCL all-reduce stays outside the graphs: [grads] -> all-reduce -> [adam + repack]
-            for i in range(self.nc):
+            # NCCL all-reduce stays outside the graphs: [grads] -> all-reduce -> [adam + repack].
+            # Generator forwards are software-pipelined: graph i runs the forward the NEXT iteration needs
+            # (or the generator update's) on the side stream next to critic iteration i.
+            def cap(fn):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
+                    fn()
+                return g
+
+            def critic_and_next_forward(i):
+                if not self.overlap:
                     self.critic_iteration(i, update=False)
-                graphs.append(("c", g))
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    ops.adam(self.de.fp.flat, self.de.fp.grad, self.mD, self.vD, self.de.fp.n_live_padded,
-                             self.stepD, float(self.cfg["lr_critic"]), gscale=1.0 / self.world)
-                    self.de.net.pack()
-                graphs.append(("cu", g))
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self.generator_update(update=False)
-            graphs.append(("g", g))
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+                    return
+                main = torch.cuda.current_stream()
+                self.s_gen.wait_stream(main)
+                with torch.cuda.stream(self.s_gen):
+                    if i + 1 < self.nc:
+                        self._gen_forward(i + 1)
+                    else:
+                        self._gen_forward_update()
+                self.critic_iteration(i, update=False, gen_inline=False)
+                main.wait_stream(self.s_gen)
+
+            def adam_d():
+                ops.adam(self.de.fp.flat, self.de.fp.grad, self.mD, self.vD, self.de.fp.n_live_padded,
+                         self.stepD, float(self.cfg["lr_critic"]), gscale=1.0 / self.world)
+                self.de.net.pack()
+
+            def adam_g():
                 ops.adam(self.ge.fp.flat, self.ge.fp.grad, self.mG, self.vG, self.ge.fp.n_live_padded,
                          self.stepG, float(self.cfg["lr_gen"]), gscale=1.0 / self.world)
                 self.ge.net.pack()
-            graphs.append(("gu", g))
+
+            if self.overlap:
+                graphs.append(("p", cap(lambda: self._gen_forward(0))))
+            for i in range(self.nc):
+                graphs.append(("c", cap(lambda i=i: critic_and_next_forward(i))))
+                graphs.append(("cu", cap(adam_d)))
+            graphs.append(("g", cap(lambda: self.generator_update(update=False, gen_inline=not self.overlap))))
+            graphs.append(("gu", cap(adam_g)))
         torch.cuda.synchronize(self.dev)
         with torch.no_grad():
             for t, s in zip(self._state(), saved):
