@@ -25,10 +25,20 @@ class Workspace:
     def __init__(self, device, scratch_floats=1 << 25, acc_doubles=1 << 16):
         self.device = device
         self.bufs = {}
-        self.scratch = torch.empty(scratch_floats, dtype=torch.float32, device=device)
-        self.scratch_a = torch.empty(scratch_floats, dtype=torch.float32, device=device)   # side-stream work
+        self.scratch_floats = scratch_floats
+        self._scratch = {}                     # split-K scratch of the FP32 kernels, one per CUDA stream
         self.acc = torch.zeros(acc_doubles, dtype=torch.float64, device=device)
         self.acc_used = 0
+
+    @property
+    def scratch(self):
+        """Scratch of the stream the caller is launching on (concurrent branches never share one)."""
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        t = self._scratch.get(key)
+        if t is None:
+            t = torch.empty(self.scratch_floats, dtype=torch.float32, device=self.device)
+            self._scratch[key] = t
+        return t
 
     def mat(self, name, nb, rows, cols, ld=None):
         ld = cols if ld is None else ld
@@ -59,7 +69,7 @@ class Workspace:
         return s
 
     def bytes(self):
-        return sum(t.numel() * t.element_size() for t in self.bufs.values()) + self.scratch.numel() * 8
+        return sum(t.numel() * t.element_size() for t in self.bufs.values()) + 4 * self.scratch_floats * len(self._scratch)
 
 
 def conv_out_len(L, k, s, p):
@@ -688,15 +698,31 @@ class CriticNet:
         self.wk = Workspace(self.dev)
         # the audio branch is independent of the pose branch between the inputs and the fusion MLP:
         # it runs on a side stream (fork / join below; CUDA-graph capture turns that into parallel branches)
-        self.par = os.environ.get("M2D_OVERLAP", "1") != "0" and not self.ablated
-        self.s_aud = torch.cuda.Stream(device=self.dev) if self.par else None
+        self.par = os.environ.get("M2D_OVERLAP", "1") != "0"
+        mk = lambda: torch.cuda.Stream(device=self.dev)
+        # s_aud: audio branch next to the pose branch; s_w / s_wa: the Wasserstein backward (pose / audio)
+        # next to the gradient-penalty passes
+        self.s_aud, self.s_w, self.s_wa = (mk(), mk(), mk()) if self.par else (None, None, None)
+
+    def _side(self):
+        cur = torch.cuda.current_stream(self.dev)
+        return self.s_wa if (self.s_w is not None and cur.cuda_stream == self.s_w.cuda_stream) else self.s_aud
 
     def fork(self):
-        return _Fork(self.s_aud if self.par else None)
+        """Audio-branch work of the chain running on the current stream -> its side stream."""
+        return _Fork(self._side() if (self.par and not self.ablated) else None)
 
     def join(self):
+        if self.par and not self.ablated:
+            torch.cuda.current_stream(self.dev).wait_stream(self._side())
+
+    def fork_w(self):
+        """Second chain (Wasserstein backward) next to the chain on the current stream."""
+        return _Fork(self.s_w if self.par else None)
+
+    def join_w(self):
         if self.par:
-            torch.cuda.current_stream().wait_stream(self.s_aud)
+            torch.cuda.current_stream(self.dev).wait_stream(self.s_w)
 
     def convs(self):
         c = [self.s_conv1] + [x for blk in self.s_blocks for x in blk] + [self.s_fconv]
@@ -813,10 +839,10 @@ class CriticNet:
         sv = {"X": x, "q": []}
         for l in self.a_layers:
             q = wk.mat(f"{tag}:q{l.name}", n, l.Lout, l.Cout)
-            l.fwd(x, q, act=ACT_RELU, ws=wk.scratch_a)
+            l.fwd(x, q, act=ACT_RELU, ws=wk.scratch)
             sv["q"].append(q)
             x = q
-        self.a_l6.fwd(x, code_out.as_rows(n, 1), act=self.act, ws=wk.scratch_a)
+        self.a_l6.fwd(x, code_out.as_rows(n, 1), act=self.act, ws=wk.scratch)
         sv["code"] = code_out
         return sv
 
@@ -828,11 +854,11 @@ class CriticNet:
         dl = {"l6": d_code}
         q = sv["q"]
         d = wk.mat(f"{tag}:dq5", n, q[4].rows, q[4].cols)
-        self.a_l6.dgrad(d_code.as_rows(n, 1), d, ws=wk.scratch_a, mask=q[4], mask_mode=ACT_RELU)
+        self.a_l6.dgrad(d_code.as_rows(n, 1), d, ws=wk.scratch, mask=q[4], mask_mode=ACT_RELU)
         dl[4] = d
         for i in range(4, 0, -1):
             dn = wk.mat(f"{tag}:dq{i}", n, q[i - 1].rows, q[i - 1].cols)
-            self.a_layers[i].dgrad(dl[i], dn, ws=wk.scratch_a, mask=q[i - 1], mask_mode=ACT_RELU)
+            self.a_layers[i].dgrad(dl[i], dn, ws=wk.scratch, mask=q[i - 1], mask_mode=ACT_RELU)
             dl[i - 1] = dn
         sv["delta"] = dl
         if dX is not None:
@@ -848,10 +874,10 @@ class CriticNet:
         kw = dict(scale=scale, beta=beta, bias=bias, bbeta=bbeta)
         x = X
         for i, l in enumerate(self.a_layers):
-            l.wgrad(dl[i], x, wk.scratch_a, acc=wk.acc_slot(l.Cout), **kw)
+            l.wgrad(dl[i], x, wk.scratch, acc=wk.acc_slot(l.Cout), **kw)
             x = q[i]
         n = x.nb
-        self.a_l6.wgrad(dl["l6"].as_rows(n, 1), x, wk.scratch_a, acc=wk.acc_slot(self.a_l6.Cout), **kw)
+        self.a_l6.wgrad(dl["l6"].as_rows(n, 1), x, wk.scratch, acc=wk.acc_slot(self.a_l6.Cout), **kw)
 
     def audio_tangent(self, sv, V, n, tag, t_code):
         wk = self.wk
@@ -861,11 +887,11 @@ class CriticNet:
         tq = []
         for i, l in enumerate(self.a_layers):
             t = wk.mat(f"{tag}:t{l.name}", n, l.Lout, l.Cout)
-            l.fwd(x, t, bias=False, ws=wk.scratch_a, mask=sv["q"][i], mask_mode=ACT_RELU)
+            l.fwd(x, t, bias=False, ws=wk.scratch, mask=sv["q"][i], mask_mode=ACT_RELU)
             tq.append(t)
             x = t
         m = dict(mask=sv["code"].as_rows(n, 1), mask_mode=self.act) if self.act != ACT_ID else {}
-        self.a_l6.fwd(x, t_code.as_rows(n, 1), bias=False, ws=wk.scratch_a, **m)
+        self.a_l6.fwd(x, t_code.as_rows(n, 1), bias=False, ws=wk.scratch, **m)
         return {"X": x0, "q": tq}
 
     # ---------------------------------------------------------------- fusion MLP

@@ -116,8 +116,12 @@ class Phase3Trainer:
         ops.sum_(rows(d, B, 2 * B), B, sums[0:1])
         ops.sum_(rows(d, 2 * B, n3), B, sums[1:2])
         gamma = float(self.cfg["gamma"])
-        gradient_penalty_pass(D, fw, B, "c:gp", gamma, 0.0, self.gp_buf, self.k0, self.k1)
-        wasserstein_backward(D, fw, B, 2 * B, (-1.0, 1.0), B, "c:w", beta=1.0)
+        # two independent backward chains over the same forward state: the Wasserstein terms (second
+        # stream pair; they OVERWRITE the gradient buffers) and the gradient penalty (backward-data,
+        # tangent pass; its weight gradients ACCUMULATE once the first chain is done)
+        with D.fork_w():
+            wasserstein_backward(D, fw, B, 2 * B, (-1.0, 1.0), B, "c:w", beta=0.0)
+        gradient_penalty_pass(D, fw, B, "c:gp", gamma, 1.0, self.gp_buf, self.k0, self.k1, before_wgrads=D.join_w)
         ops.wgan_scalars(sums, self.gp_buf, B, 1, 1, gamma, 0.0, 0, self.log_c[i])
         D.unpack_grads()
         if update:

@@ -52,7 +52,7 @@ def critic_forward(D, X, audio, nS, nA, tag, groups=1):
     return dict(svp=svp, sva=sva, sa=sa, u=u, d=d)
 
 
-def gradient_penalty_pass(D, fw, B, tag, scale, beta, gp_out, k0, k1, weight_grads=True):
+def gradient_penalty_pass(D, fw, B, tag, scale, beta, gp_out, k0, k1, weight_grads=True, before_wgrads=None):
     """GP on the first B rows of forward state `fw`.  Writes gp to gp_out[0] and, if
     weight_grads, accumulates  scale * dGP/dW  into the critic's gradient buffers
     (gw = beta*gw + ...; biases receive nothing, Q5)."""
@@ -104,6 +104,8 @@ def gradient_penalty_pass(D, fw, B, tag, scale, beta, gp_out, k0, k1, weight_gra
     t_h = wk.mat(f"{tag}:t_h", 1, B, 128)
     D.fc1.fwd(t_sa, t_h, bias=False, ws=wk.scratch, mask=u, mask_mode=ACT_RELU)
     # weight gradients: wgrad(first-backward delta, tangent activation)
+    if before_wgrads is not None:
+        before_wgrads()                  # e.g. wait for a concurrent chain that writes the same gradient buffers first
     if not D.ablated:
         with D.fork():
             D.audio_wgrads(sva["delta"], tva["X"], tva["q"], scale, beta, bias=False)
