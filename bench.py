@@ -403,6 +403,17 @@ def run_b200(args):
             ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
             peak = pk["hbm_gbs"]
             roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None}
+        # DRAM bytes per launch of the same kernel family from the committed ncu capture (tools/gpu_traffic.sh);
+        # null when the capture does not cover the dominant family
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_tc_traffic.json")) as f:
+                tj = json.load(f)
+            if args.batch == 7 and args.enc == "default" and top in tj:
+                roof["traffic"] = tj[top]["traffic_bytes_per_launch"]
+                roof["traffic_source"] = ("profiles/r01_tc_traffic.json: mean dram__bytes_read+write per launch over the "
+                                          f"{tj[top]['launches']} {top} tensor-core launches of one train step")
+        except (OSError, ValueError, KeyError):
+            pass
         roof.update({"kernel": top, "launches_per_step": d["launches"],
                      "avg_launch_us": 1e3 * d["ms"] / d["launches"],
                      "share_of_eager_step": d["ms"] / eager_ms,
@@ -412,7 +423,8 @@ def run_b200(args):
                                                     "(no TF32 figure in the file); gemm mode " + args.gemm +
                                                     (" issues 3 tensor-core products per algorithmic product"
                                                      if args.gemm == "tf32x3" else "") if tensor_bound else ""),
-                     "algorithmic_gflop_per_launch": d["flops"] / d["launches"] / 1e9})
+                     "algorithmic_gflop_per_launch": d["flops"] / d["launches"] / 1e9,
+                     "algorithmic_bytes_per_launch": d["bytes"] / d["launches"]})
         for f in fams.values():
             f["tflops"] = f["flops"] / max(f["ms"], 1e-9) / 1e9
             f["gbs"] = f["bytes"] / max(f["ms"], 1e-9) / 1e6
