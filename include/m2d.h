@@ -136,7 +136,10 @@ int m2d_pack_conv_bwd(const float* w, float* wd, int Cout, int Cin, int k, int s
  * the backward layout of a convolution whose kernel spans its whole input (fconv, l6, encoder heads),
  * used as a Linear over (tap, channel):  dst[(t*Cin + ci), co] = w[co, ci, t]. */
 enum { M2D_PACK_FWD = 0, M2D_PACK_BWD = 1, M2D_PACK_FULL_BWD = 2,
-       M2D_UNPACK_GRAD = 3 /* dst[co, ci, t] = w[co, t*Cin + ci]: packed weight gradient -> parameter layout */ };
+       M2D_UNPACK_GRAD = 3 /* dst[co, ci, t] = w[co, t*Cin + ci]: packed weight gradient -> parameter layout */,
+       M2D_PACK_BWD_MERGED = 4 /* all stride residues in one matrix [(r0, ci)][q'*Cout + co] (unified taps,
+                                  `reserved` = conv padding): backward-data as one stride-1 row convolution
+                                  whose N = stride*Cin columns are the fine rows of a coarse output row */ };
 typedef struct {
     const float* w; float* dst;           /* dst may be NULL (no exact copy wanted) */
     float* dst_hi; float* dst_lo;         /* optional 3xTF32 split copies in the m2d_rowconv_args.w_hi layout: the

@@ -433,6 +433,39 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const m2d_pack_desc* __
             d.dst[idx] = w[((long long)co * k + t) * Cin + ci];
             continue;
         }
+        if (d.kind == M2D_PACK_BWD_MERGED) {
+            // backward-data of a stride-s convolution as ONE stride-1 row convolution that produces the s fine
+            // rows of a coarse row at once: output column (r0, ci), unified tap q' with input row m + cmax - q'
+            //   dst[(r0*Cin + ci), q'*Cout + co] = w[co, ci, s*q + rho],  rho = (r0+pad) % s, c0 = (r0+pad) / s,
+            //   q' = q + cmax - c0;  taps a residue does not have stay zero (buffers are allocated zeroed)
+            const int pad = d.reserved;
+            const int j = (int)(idx % k);
+            long long r = idx / k;
+            const int ci = (int)(r % Cin);
+            const int co = (int)(r / Cin);
+            const int rho = j % stride, q = j / stride;
+            int r0 = (rho - pad) % stride;
+            if (r0 < 0) r0 += stride;
+            const int c0 = (r0 + pad) / stride, cmax = (stride - 1 + pad) / stride;
+            int Tm = 0;
+            for (int rr = 0; rr < stride; ++rr) {
+                const int rh = (rr + pad) % stride, cc = (rr + pad) / stride;
+                const int Tr = (k - rh + stride - 1) / stride + cmax - cc;
+                Tm = Tr > Tm ? Tr : Tm;
+            }
+            const int qp = q + cmax - c0;
+            const int cop = (Cout + 3) & ~3;
+            const long long row = (long long)r0 * Cin + ci;
+            const float v = w[idx];
+            if (d.dst) d.dst[row * Tm * Cout + (long long)qp * Cout + co] = v;
+            if (d.dst_hi) {
+                const float h = rna_tf32(v);
+                const long long pidx = row * Tm * cop + (long long)qp * cop + co;
+                d.dst_hi[pidx] = h;
+                d.dst_lo[pidx] = rna_tf32(v - h);
+            }
+            continue;
+        }
         if (d.kind == M2D_PACK_FWD) {                 // dst[co, t*Cin + ci]
             int ci = (int)(idx % Cin);
             long long r = idx / Cin;

@@ -712,7 +712,7 @@ static int launch_tc_shape(const m2d_rowconv_args& a, int M, int nsteps, int cch
 int rowconv_tc_dispatch(const m2d_rowconv_args& a, int M, int mode, cudaStream_t st) {
     const bool c1 = a.Cc == 1;
     const long long K = (long long)a.T * a.Cc;
-    if (a.N < 8 || (long long)M * a.N * K < (1ll << 18)) return 1;
+    if (a.N < 4 || (long long)M * a.N * K < (1ll << 18)) return 1;
     // a handful of rows against a long contraction (audio_d.l6, stick_d.fconv and their backward-data
     // passes at small batch) is weight-streaming work: one 128-row tile cannot spread over more than a
     // cluster of CTAs, the FP32 kernel splits K over the whole chip

@@ -110,7 +110,9 @@ class ConvLayer:
         n = Cout * Cin * k
         z = lambda m: torch.zeros(m, dtype=torch.float32, device=dev)
         self.wp = None if (Cin == 1 or k == 1) else torch.empty(n, dtype=torch.float32, device=dev)
-        self.wd = torch.empty(n, dtype=torch.float32, device=dev) if (need_dgrad and Cin > 1) else None
+        # merged backward-data (all stride residues in one launch): needs Lin % stride == 0
+        self.merged = bool(need_dgrad and stride > 1 and not self.full and Lin % stride == 0)
+        self.wd = torch.empty(n, dtype=torch.float32, device=dev) if (need_dgrad and Cin > 1 and not self.merged) else None
         # 3xTF32 operand split of the packed weights (rows padded to 4 floats, pad stays zero) for the TMA path
         self.ldf = (k * ((Cin + 3) // 4 * 4)) if Cin > 1 else (k + 3) // 4 * 4
         self.wph, self.wpl = z(Cout * self.ldf), z(Cout * self.ldf)
@@ -125,6 +127,13 @@ class ConvLayer:
         # weight gradients of real convolutions are produced tap-major [co, t*Cin + ci] (coalesced stores) and
         # turned into the parameter layout by one batched kernel per network (unpack_entries)
         self.gwp = z(n) if (gw is not None and k > 1 and Cin > 1) else None
+        if self.merged:
+            self.cmax = (stride - 1 + pad) // stride
+            self.Tm = max(-(-(k - (r + pad) % stride) // stride) + self.cmax - (r + pad) // stride for r in range(stride))
+            cop = (Cout + 3) // 4 * 4
+            self.wdm = z(stride * Cin * self.Tm * Cout)
+            self.wdmh, self.wdml = z(stride * Cin * self.Tm * cop), z(stride * Cin * self.Tm * cop)
+            self.ldm = self.Tm * cop
         self.ldb = (Cout + 3) // 4 * 4                      # Linear / full-length form: [k*Cin rows][Cout]
         if self.wd is not None:
             m = (k * Cin * self.ldb) if (self.full or k == 1) else poff
@@ -138,6 +147,9 @@ class ConvLayer:
     def pack_entries(self):
         """(w, dst, Cout, Cin, k, stride, kind) rows of the batched re-layout table (ops.pack_batch)."""
         e = [(self.w, self.wp, self.wph, self.wpl, self.Cout, self.Cin, self.k, 1, ops.PACK_FWD)]
+        if self.merged:
+            e.append((self.w, self.wdm, self.wdmh, self.wdml, self.Cout, self.Cin, self.k, self.s,
+                      ops.PACK_BWD_MERGED, self.p))
         if self.wd is not None:
             if self.full or self.k == 1:
                 e.append((self.w, self.wd, self.wdh, self.wdl, self.Cout, self.Cin, self.k, 1, ops.PACK_FULL_BWD))
@@ -172,8 +184,8 @@ class ConvLayer:
 
     # dx = conv_transpose(dy) with fused epilogue (mask by act'(prev), residual add, ...)
     def dgrad(self, dy, dx, ws=None, mask=None, mask_mode=0, add=None, add_before_mask=False, y2=None):
-        assert self.wd is not None
         if self.full or self.k == 1:
+            assert self.wd is not None
             K = self.k * self.Cin
             xd = dy.flat_rows()
             fl = self.k > 1          # full-length conv: (n, L, C) -> (n, L*C); Linear: rows as they are
@@ -184,6 +196,21 @@ class ConvLayer:
                         w_split=(self.wdh.data_ptr(), self.wdl.data_ptr(), self.ldb))
             return
         s = self.s
+        dense = all(m is None or (m.ld == m.cols and m.bs == m.rows * m.ld) for m in (dx, mask, add, y2))
+        if self.merged and dense and dx.rows == self.Lin:
+            # one stride-1 row convolution: coarse row m holds the s fine rows 4m..4m+s-1 as s*Cin columns
+            def mv(m):
+                if m is None:
+                    return None
+                v = Mat(m.t, m.nb, m.rows // s, s * m.cols, s * m.ld, m.bs)
+                v.ptr = m.ptr
+                return v
+            ops.rowconv(dy, self.wdm, mv(dx), T=self.Tm, Cc=self.Cout, N=s * self.Cin, sr=1, roff0=self.cmax,
+                        droff=-1, ws=ws, mask=mv(mask), mask_mode=mask_mode, add=mv(add),
+                        add_before_mask=add_before_mask, y2=mv(y2),
+                        w_split=(self.wdmh.data_ptr(), self.wdml.data_ptr(), self.ldm))
+            return
+        assert self.wd is not None, "strided backward-data into a non-dense buffer is not supported for this layer"
         for r0 in range(s):
             rho, c0 = (r0 + self.p) % s, (r0 + self.p) // s
             _, Trho, off, poff, pld = self.res[rho]
@@ -863,8 +890,11 @@ class CriticNet:
         sv["delta"] = dl
         if dX is not None:
             l1 = self.a_layers[0]
-            ops.conv_dgrad_c1(dl[0], l1.w, dX, nb=n, Lout=l1.Lout, Cout=l1.Cout, k=l1.k, stride=l1.s,
-                              pad=l1.p, Lin=l1.Lin)
+            if l1.merged:                                # tensor-core path: N = stride columns per coarse sample
+                l1.dgrad(dl[0], Mat(dX, n, l1.Lin, 1), ws=wk.scratch)
+            else:
+                ops.conv_dgrad_c1(dl[0], l1.w, dX, nb=n, Lout=l1.Lout, Cout=l1.Cout, k=l1.k, stride=l1.s,
+                                  pad=l1.p, Lin=l1.Lin)
         if wgrads:
             self.audio_wgrads(dl, sv["X"], sv["q"], scale, beta, bias=True, bbeta=bbeta)
         return dl

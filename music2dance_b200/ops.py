@@ -153,7 +153,7 @@ def pack_conv_bwd(w, wd, Cout, Cin, k, stride):
     call("m2d_pack_conv_bwd", _p(w), _p(wd), Cout, Cin, k, stride, _stream())
 
 
-PACK_FWD, PACK_BWD, PACK_FULL_BWD, UNPACK_GRAD = 0, 1, 2, 3
+PACK_FWD, PACK_BWD, PACK_FULL_BWD, UNPACK_GRAD, PACK_BWD_MERGED = 0, 1, 2, 3, 4
 
 
 def pack_table(entries, device):
@@ -163,8 +163,9 @@ def pack_table(entries, device):
                    ("k", "<i4"), ("stride", "<i4"), ("kind", "<i4"), ("reserved", "<i4")])
     arr = np.zeros(len(entries), dtype=dt)
     ptr = lambda t: 0 if t is None else t.data_ptr()
-    for i, (w, dst, dh, dl, Cout, Cin, k, stride, kind) in enumerate(entries):
-        arr[i] = (w.data_ptr(), ptr(dst), ptr(dh), ptr(dl), Cout, Cin, k, stride, kind, 0)
+    for i, e in enumerate(entries):
+        w, dst, dh, dl, Cout, Cin, k, stride, kind = e[:9]
+        arr[i] = (w.data_ptr(), ptr(dst), ptr(dh), ptr(dl), Cout, Cin, k, stride, kind, e[9] if len(e) > 9 else 0)
     t = torch.from_numpy(arr.view(np.uint8).copy()).to(device)
     return t, len(entries)
 

@@ -118,6 +118,31 @@ def test_conv_fwd_dgrad_wgrad(lib, case):
         close(dx.cpu(), xr.grad[:, 0], what="dgrad_c1")
 
 
+@pytest.mark.parametrize("case", [(1, 32, 25, 4, 11, 7680, 2), (1, 16, 9, 2, 4, 512, 3), (32, 64, 25, 4, 11, 1200, 2)])
+def test_merged_strided_dgrad(lib, case):
+    """Backward-data of a strided conv as ONE stride-1 row convolution over all stride residues
+    (incl. the single-input-channel audio_d.l1 form that yields the GP gradient w.r.t. the audio)."""
+    from music2dance_b200.nets import ConvLayer
+    from music2dance_b200.ops import Mat
+    Cin, Cout, k, s, p, L, B = case
+    g = torch.Generator().manual_seed(11)
+    w = torch.randn(Cout, Cin, k, generator=g) / (Cin * k) ** 0.5
+    b = torch.zeros(Cout)
+    wd_, bd_ = w.to(DEV), b.to(DEV)
+    lay = ConvLayer("t", wd_, bd_, torch.zeros_like(wd_), torch.zeros_like(bd_), Cin, Cout, k, s, p, L, need_dgrad=True)
+    assert lay.merged
+    lay.pack()
+    x = torch.randn(B, Cin, L, generator=g).requires_grad_(True)
+    y = F.conv1d(x, w, None, stride=s, padding=p)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    msk = torch.randn(B, Cin, L, generator=g)
+    D = Mat.of(cl(dy), B, y.shape[-1], Cout)
+    DX = Mat.of(torch.empty(B, L, Cin, device=DEV), B, L, Cin)
+    lay.dgrad(D, DX, ws=torch.empty(1 << 22, device=DEV), mask=Mat.of(cl(msk), B, L, Cin), mask_mode=1)
+    close(ncl(DX, B, L, Cin), x.grad * (msk > 0), what="merged dgrad")
+
+
 def test_conv_epilogue_mask_add_y2(lib):
     from music2dance_b200.ops import Mat
     Cin, Cout, k, s, p, L, B = 128, 128, 7, 1, 3, 120, 2
