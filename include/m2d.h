@@ -227,6 +227,11 @@ int m2d_pose_losses(const float* real, const float* fake, float* dfake, int B, i
                     float beta, float eta, int accumulate, double* acc, void* stream);
 /* relu / leaky / tanh derivative applied in place from stored activations */
 int m2d_act_bwd(float* d, const float* y, long long n, int mask_mode, void* stream);
+/* out = alpha * a * b * c elementwise on strided row matrices [M][C]: the second-order term of the
+ * gradient penalty through a tanh code activation (autograd double backward of default.py:333,303
+ * inside losses.py:40-44) */
+int m2d_mul3(const float* a, int lda, const float* b, int ldb, const float* c, int ldc, float* out, int ldo,
+             long long M, int C, float alpha, void* stream);
 /* MaxPool1d(2,2) and Upsample(x2, linear, align_corners=False) on channels-last rows
  * (default.py:236-237) */
 int m2d_maxpool2(const float* x, int ldx, float* y, int ldy, int nb, int Lin, int C, void* stream);

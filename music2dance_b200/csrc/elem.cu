@@ -284,6 +284,19 @@ __global__ void act_bwd_kernel(float* d, const float* __restrict__ y, long long 
         d[i] *= act_deriv(y[i], mode);
 }
 
+// out[r, c] = alpha * a[r, c] * b[r, c] * c3[r, c] on strided row matrices (second-order tanh term of the
+// gradient penalty: -2 * code * tangent * dD/dcode)
+__global__ void mul3_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
+                            const float* __restrict__ c3, int ldc, float* out, int ldo, int C,
+                            long long total, float alpha) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long r = i / C;
+        int c = (int)(i - r * C);
+        out[r * ldo + c] = alpha * a[r * lda + c] * b[r * ldb + c] * c3[r * ldc + c];
+    }
+}
+
 // ---------------------------------------------------------------- pool / upsample
 __global__ void maxpool2_kernel(const float* __restrict__ x, int ldx, float* y, int ldy, int Lin,
                                 int Lout, int C, long long total) {
@@ -580,6 +593,14 @@ extern "C" int m2d_act_bwd(float* d, const float* y, long long n, int mask_mode,
     M2D_REQUIRE(d && y && n > 0, "act_bwd: bad args");
     act_bwd_kernel<<<grid1d(n), 256, 0, (cudaStream_t)stream>>>(d, y, n, mask_mode);
     return check_launch("act_bwd");
+}
+
+extern "C" int m2d_mul3(const float* a, int lda, const float* b, int ldb, const float* c, int ldc, float* out,
+                        int ldo, long long M, int C, float alpha, void* stream) {
+    M2D_REQUIRE(a && b && c && out && M > 0 && C > 0, "mul3: bad args");
+    long long total = M * C;
+    mul3_kernel<<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, c, ldc, out, ldo, C, total, alpha);
+    return check_launch("mul3");
 }
 
 extern "C" int m2d_maxpool2(const float* x, int ldx, float* y, int ldy, int nb, int Lin, int C,

@@ -41,9 +41,12 @@ class _GradPenaltyFn(torch.autograd.Function):
             k0, k1 = wk.vec("gp:k0", B), wk.vec("gp:k1", B)
             gradient_penalty_pass(D, fw, B, "gp", 1.0, 0.0, gp, k0, k1, weight_grads=True)
             ctx.grads = [None if g is None else g for g in eng.grads_in_param_order()]
-            # GP gives no gradient to biases (Q5): the bias slots were not written by this pass
+            # GP gives no gradient to biases (Q5): the bias slots were not written by this pass —
+            # except below a tanh code activation, whose curvature term reaches the branch biases
             names = eng.fp.names
-            ctx.grads = [g if (g is not None and not n.endswith(".bias")) else None
+            tanh = critic.activ == "tanh" if hasattr(critic, "activ") else False
+            live_bias = lambda n: tanh and not n.startswith("fc")
+            ctx.grads = [g if (g is not None and (not n.endswith(".bias") or live_bias(n))) else None
                          for n, g in zip(names, ctx.grads)]
             return gp.view(())
 

@@ -784,12 +784,13 @@ class CriticNet:
         sv["y"], sv["code"] = x, code_out
         return sv
 
-    def pose_bwd(self, sv, d_code, n, tag, scale=1.0, beta=0.0, wgrads=True, dX=None, bbeta=None):
+    def pose_bwd(self, sv, d_code, n, tag, scale=1.0, beta=0.0, wgrads=True, dX=None, bbeta=None, pre_act=False):
         """d_code Mat [1,n,code] = gradient w.r.t. the pose code (post-activ; modified in
-        place when activ != id).  Produces pre-activation deltas (kept in `sv` for the GP
-        weight gradients), optional weight grads (scale/beta) and optional dX."""
+        place when activ != id; pre_act: already w.r.t. the pre-activation).  Produces
+        pre-activation deltas (kept in `sv` for the GP weight gradients), optional weight
+        grads (scale/beta) and optional dX."""
         wk, T, Ch = self.wk, self.T, self.Ch
-        if self.act != ACT_ID:
+        if self.act != ACT_ID and not pre_act:
             ops.act_bwd(d_code, sv["code"], n * self.code, self.act)
         dl = {"fconv": d_code}
         e = wk.mat(f"{tag}:e_top", n, T, Ch)
@@ -873,10 +874,11 @@ class CriticNet:
         sv["code"] = code_out
         return sv
 
-    def audio_bwd(self, sv, d_code, n, tag, scale=1.0, beta=0.0, wgrads=True, dX=None, bbeta=None):
-        """Backward through the audio branch from d_code [1,n,code].  dX: tensor [n,A] or None."""
+    def audio_bwd(self, sv, d_code, n, tag, scale=1.0, beta=0.0, wgrads=True, dX=None, bbeta=None, pre_act=False):
+        """Backward through the audio branch from d_code [1,n,code] (pre_act: gradient w.r.t. the
+        pre-activation of the code).  dX: tensor [n,A] or None."""
         wk = self.wk
-        if self.act != ACT_ID:
+        if self.act != ACT_ID and not pre_act:
             ops.act_bwd(d_code, sv["code"], n * self.code, self.act)
         dl = {"l6": d_code}
         q = sv["q"]

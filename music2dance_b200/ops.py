@@ -271,6 +271,12 @@ def act_bwd(d, y, n, mode):
     call("m2d_act_bwd", _p(d), _p(y), n, mode, _stream())
 
 
+def mul3(a, b, c, out, alpha=1.0):
+    """out = alpha * a * b * c on same-shaped Mats (strided rows)."""
+    LAUNCHES[0] += 1
+    call("m2d_mul3", a.ptr, a.ld, b.ptr, b.ld, c.ptr, c.ld, out.ptr, out.ld, a.M, a.cols, alpha, _stream())
+
+
 def maxpool2(x, y, nb, Lin, Cn):
     LAUNCHES[0] += 1
     call("m2d_maxpool2", x.ptr, x.ld, y.ptr, y.ld, nb, Lin, Cn, _stream())

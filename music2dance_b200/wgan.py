@@ -7,12 +7,17 @@ The gradient penalty is evaluated without autograd:
   4. weight gradients  dW_k = wgrad(delta_k, t_{k-1})  — for a piecewise-linear critic
      d/dtheta <v, grad_x D> = d/dtheta JVP_v(D), whose back-propagated deltas equal the
      first-backward deltas, so no second backward sweep over the data path is needed and
-     the identically-zero passes of autograd's double backward never run.
+     the identically-zero passes of autograd's double backward never run,
+  5. activ='tanh' (tanh.yaml): the code activations c = tanh(z) are the only curved part of
+     the critic, so the double backward has exactly one more term, the curvature of tanh:
+     <v, J_z^T (s * d(1 - c^2))> = <e_z, dz/dtheta>  with  e_z = -2 c * t_c * s,
+     s = dD/dc, t_c = tangent of c.  That is one ordinary backward of each branch from e_z
+     (weights AND biases: with tanh the penalty does reach the biases below the codes).
 """
 from __future__ import annotations
 
 from . import ops
-from .nets import ACT_ID, ACT_RELU
+from .nets import ACT_ID, ACT_RELU, ACT_TANH
 from .ops import Mat
 
 
@@ -57,9 +62,8 @@ def gradient_penalty_pass(D, fw, B, tag, scale, beta, gp_out, k0, k1, weight_gra
     weight_grads, accumulates  scale * dGP/dW  into the critic's gradient buffers
     (gw = beta*gw + ...; biases receive nothing, Q5)."""
     wk, T, O, code = D.wk, D.T, D.O, D.code
-    if D.act not in (ACT_ID, ACT_RELU) and weight_grads:
-        raise NotImplementedError("gradient-penalty weight gradients with activ='tanh' need the second-order "
-                                  "tanh term; only 'id' and 'relu' are implemented")
+    if D.act not in (ACT_ID, ACT_RELU, ACT_TANH) and weight_grads:
+        raise NotImplementedError("gradient-penalty weight gradients: activ must be 'id', 'relu' or 'tanh'")
     svp = slice_pose_saves(fw["svp"], 0, B)
     sva = fw["sva"]
     u = rows(fw["u"], 0, B)
@@ -113,6 +117,19 @@ def gradient_penalty_pass(D, fw, B, tag, scale, beta, gp_out, k0, k1, weight_gra
     D.fc1.wgrad(dh, t_sa, wk.scratch, scale=scale, beta=beta, bias=False)
     D.pose_wgrads(svp["delta"], g0, tvp, scale, beta, bias=False)
     D.join()
+    if D.act == ACT_TANH:
+        # curvature of the code activations: ordinary backward of both branches from
+        # e_z = -2 c * t_c * s (dsa still holds s = dD/dc: the first backward worked on copies)
+        if not D.ablated:
+            with D.fork():
+                e_a = wk.mat(f"{tag}:e2_a", 1, B, code)
+                ops.mul3(dsa.cols_slice(code, D.F), t_a, sva["code"], e_a, alpha=-2.0)
+                D.audio_bwd(dict(sva), e_a, B, f"{tag}2", scale=scale, beta=1.0, wgrads=True, bbeta=beta,
+                            pre_act=True)
+        e_s = wk.mat(f"{tag}:e2_s", 1, B, code)
+        ops.mul3(dsa.cols_slice(0, code), t_s, svp["code"], e_s, alpha=-2.0)
+        D.pose_bwd(dict(svp), e_s, B, f"{tag}2", scale=scale, beta=1.0, wgrads=True, bbeta=beta, pre_act=True)
+        D.join()
     return out
 
 

@@ -40,7 +40,7 @@ def oracle_params(module):
 
 
 @pytest.mark.parametrize("state", ["init", "perturbed"])
-@pytest.mark.parametrize("variant", ["default", "wavegan", "unet", "ablated"])
+@pytest.mark.parametrize("variant", ["default", "wavegan", "unet", "ablated", "tanh"])
 def test_dropin_step_vs_reference_fixtures(variant, state):
     """phase3/train.py:187-237 written with the drop-in API, compared with what the
     reference modules produced for the same seeds (fixtures)."""
@@ -184,7 +184,8 @@ def test_generator_long_sequence():
     assert float((out.cpu() - ref).abs().max() / ref.abs().max()) < TOL_FP32
 
 
-@pytest.mark.parametrize("variant,B,nc", [("default", 2, 2), ("default", 7, 3), ("wavegan", 3, 2), ("ablated", 4, 2)])
+@pytest.mark.parametrize("variant,B,nc", [("default", 2, 2), ("default", 7, 3), ("wavegan", 3, 2), ("ablated", 4, 2),
+                                          ("tanh", 2, 2)])
 @pytest.mark.parametrize("graphs", [False, True])
 def test_fused_trainer_vs_oracle(variant, B, nc, graphs):
     """Phase3Trainer (fused step, Adam included, optionally CUDA-graph replayed) against the
