@@ -53,6 +53,8 @@ int m2d_check_device(int dev);
  * Shapes the tensor-core kernels do not cover (N < 8, tiny problems, weight gradients with
  * Cout or Cc not a multiple of 4) run on the FP32 kernels in every mode. */
 enum { M2D_GEMM_FP32 = 0, M2D_GEMM_TF32 = 1, M2D_GEMM_TF32X3 = 3 };
+/* number of m2d_rowconv calls served by the TMA halo-tile kernel so far (diagnostics / tests) */
+long long m2d_halo_launch_count(void);
 int m2d_set_gemm_mode(int mode);
 int m2d_get_gemm_mode(void);
 
@@ -82,10 +84,14 @@ typedef struct {
     int nb;
     int win_T, win_stride, win_pad, win_seq_len;
     const float* w; int w_ld;
-    const float* w_hi; const float* w_lo; int ws_ld;   /* optional pre-split copies of w for the tensor-core path:
-                                            w_hi = tf32_rn(w), w_lo = tf32_rn(w - w_hi); element (n, t, c) at
-                                            n*ws_ld + t*roundup4(Cc) + c (Cc == 1: n*ws_ld + t), pad zero; loaded by TMA
-                                            (every tap 16-byte aligned).  NULL: operands are split on the fly */
+    const float* w_tiled;                /* optional pre-split, pre-tiled copy of w for the tensor-core kernels (written
+                                            by m2d_pack_batch): the weight operand as the tensor core reads it from shared
+                                            memory, one contiguous block per (N tile, tap, 32-channel block) so that a stage
+                                            is ONE bulk copy.  Block ((nt*T + t)*ceil(Cc/32) + c) holds R = (N <= 64 ? 64 : 128)
+                                            rows x 32 floats of w_hi = tf32_rn(w) followed by the same of w_lo =
+                                            tf32_rn(w - w_hi), rows 128 bytes apart, 16-byte chunks XOR-swizzled with
+                                            (row & 7) (SWIZZLE_128B K-major); entries beyond N / Cc are zero.  Cc == 1: the
+                                            taps play the role of channels (T = 1).  NULL: operands are split on the fly */
     int N, T, Cc;
     int sr, roff0, droff;
     float* y; long long y_bs; int y_ld; int y_rows;
@@ -142,9 +148,11 @@ enum { M2D_PACK_FWD = 0, M2D_PACK_BWD = 1, M2D_PACK_FULL_BWD = 2,
                                   whose N = stride*Cin columns are the fine rows of a coarse output row */ };
 typedef struct {
     const float* w; float* dst;           /* dst may be NULL (no exact copy wanted) */
-    float* dst_hi; float* dst_lo;         /* optional 3xTF32 split copies in the m2d_rowconv_args.w_hi layout: the
-                                             contraction channel count of every tap padded to a multiple of 4 floats
-                                             (pad never written: allocate zeroed); BWD blocks follow each other */
+    float* dst_tiled;                     /* optional 3xTF32 split copy in the m2d_rowconv_args.w_tiled layout of the
+                                             GEMM the kind defines (FWD: N = Cout, T = k, Cc = Cin, or T = 1, Cc = k when
+                                             Cin == 1; FULL_BWD: N = k*Cin, T = 1, Cc = Cout; BWD: per residue N = Cin,
+                                             T = T_rho, Cc = Cout, blocks back to back; BWD_MERGED: N = stride*Cin, T = Tm,
+                                             Cc = Cout).  Padding is never written: allocate zeroed */
     int Cout, Cin, k, stride, kind, reserved;
 } m2d_pack_desc;
 int m2d_pack_batch(const m2d_pack_desc* table, int n, void* stream);

@@ -23,7 +23,7 @@ class RowConvArgs(C.Structure):
         ("nb", C.c_int),
         ("win_T", C.c_int), ("win_stride", C.c_int), ("win_pad", C.c_int), ("win_seq_len", C.c_int),
         ("w", f32p), ("w_ld", C.c_int),
-        ("w_hi", f32p), ("w_lo", f32p), ("ws_ld", C.c_int),
+        ("w_tiled", f32p),
         ("N", C.c_int), ("T", C.c_int), ("Cc", C.c_int),
         ("sr", C.c_int), ("roff0", C.c_int), ("droff", C.c_int),
         ("y", f32p), ("y_bs", i64), ("y_ld", C.c_int), ("y_rows", C.c_int),
@@ -59,6 +59,7 @@ SIGNATURES = {
     "m2d_check_device": [_I],
     "m2d_set_gemm_mode": [_I],
     "m2d_get_gemm_mode": [],
+    "m2d_halo_launch_count": [],
     "m2d_rowconv": [C.POINTER(RowConvArgs), _P],
     "m2d_wgrad": [C.POINTER(WgradArgs), _P],
     "m2d_wgrad_min_ws": [_I, _I, _I],
@@ -95,8 +96,8 @@ SIGNATURES = {
     "m2d_slice_audio": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "m2d_adam": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _P],
 }
-_RESTYPE = {"m2d_wgrad_min_ws": i64}
-_NOCHECK = {"m2d_wgrad_min_ws", "m2d_version", "m2d_get_gemm_mode"}     # return a value, not a status
+_RESTYPE = {"m2d_wgrad_min_ws": i64, "m2d_halo_launch_count": i64}
+_NOCHECK = {"m2d_wgrad_min_ws", "m2d_version", "m2d_get_gemm_mode", "m2d_halo_launch_count"}     # return a value, not a status
 
 _lib = None
 

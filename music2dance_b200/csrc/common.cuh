@@ -32,6 +32,20 @@ inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 
 constexpr int kNumSMs = 148;   // B200
 
+// m2d_rowconv_args.w_tiled layout (include/m2d.h): rows per block and float index of the hi value of
+// element (n, tap t, channel ci) of an [N][T x Cc] weight operand; the lo value lives R*32 floats further.
+__host__ __device__ inline int tiled_rows(int N) { return N <= 64 ? 64 : 128; }
+__host__ __device__ inline long long tiled_block_floats(int R) { return 2LL * R * 32; }
+__host__ __device__ inline long long tiled_blocks(int N, int T, int Cc) {
+    const int R = tiled_rows(N);
+    return (long long)((N + R - 1) / R) * T * ((Cc + 31) / 32);
+}
+__host__ __device__ inline long long tiled_index(int n, int t, int ci, int T, int Cc, int R) {
+    const int nt = n / R, nl = n - nt * R, c = ci >> 5, kk = ci & 31;
+    const long long blk = ((long long)nt * T + t) * ((Cc + 31) / 32) + c;
+    return blk * tiled_block_floats(R) + nl * 32 + ((((kk >> 2) ^ (nl & 7)) << 2) | (kk & 3));
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == M2D_ACT_RELU) return v > 0.f ? v : 0.f;
     if (act == M2D_ACT_LEAKY) return v > 0.f ? v : 0.2f * v;

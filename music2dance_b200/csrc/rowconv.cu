@@ -410,7 +410,8 @@ __global__ void pack_bwd_kernel(const float* __restrict__ w, float* __restrict__
 
 // all weight re-layouts of one network in ONE launch: blockIdx.y selects the table entry.  Besides
 // the exact fp32 copy (dst), each entry may request the 3xTF32 operand split of the same matrix
-// (dst_hi / dst_lo, rows padded to a multiple of 4 floats for TMA) consumed by the tensor-core kernels.
+// (dst_tiled: pre-tiled in the tensor core's shared-memory image, see m2d_rowconv_args.w_tiled) consumed by
+// the tensor-core kernels.
 __device__ __forceinline__ float rna_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -424,7 +425,8 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const m2d_pack_desc* __
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         float v;
-        long long pidx;                               // index in the padded split copies
+        int R_ = 128;                                 // rows per block of the tiled copy
+        long long pidx;                               // index of the hi value in the tiled split copy
         if (d.kind == M2D_UNPACK_GRAD) {              // dst[co, ci, t] = w[co, t*Cin + ci]  (idx walks dst)
             int t = (int)(idx % k);
             long long r = idx / k;
@@ -454,15 +456,15 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const m2d_pack_desc* __
                 Tm = Tr > Tm ? Tr : Tm;
             }
             const int qp = q + cmax - c0;
-            const int cop = (Cout + 3) & ~3;
             const long long row = (long long)r0 * Cin + ci;
             const float v = w[idx];
             if (d.dst) d.dst[row * Tm * Cout + (long long)qp * Cout + co] = v;
-            if (d.dst_hi) {
+            if (d.dst_tiled) {
                 const float h = rna_tf32(v);
-                const long long pidx = row * Tm * cop + (long long)qp * cop + co;
-                d.dst_hi[pidx] = h;
-                d.dst_lo[pidx] = rna_tf32(v - h);
+                const int R = tiled_rows(stride * Cin);
+                const long long pidx = tiled_index((int)row, qp, co, Tm, Cout, R);
+                d.dst_tiled[pidx] = h;
+                d.dst_tiled[pidx + R * 32] = rna_tf32(v - h);
             }
             continue;
         }
@@ -472,29 +474,29 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const m2d_pack_desc* __
             int t = (int)(r % k);
             int co = (int)(r / k);
             v = w[((long long)co * Cin + ci) * k + t];
-            // every tap starts on a 16-byte boundary (TMA source alignment); Cin == 1: plain [co][tap] rows
-            const int cp = Cin == 1 ? 1 : ((Cin + 3) & ~3);
-            const int ld = Cin == 1 ? ((k + 3) & ~3) : k * cp;
-            pidx = (long long)co * ld + t * cp + ci;
+            // Cin == 1: the taps are the contraction channels of a single-tap operand
+            pidx = Cin == 1 ? tiled_index(co, 0, t, 1, k, tiled_rows(Cout))
+                            : tiled_index(co, t, ci, k, Cin, tiled_rows(Cout));
+            R_ = tiled_rows(Cout);
         } else if (d.kind == M2D_PACK_FULL_BWD) {     // dst[(t*Cin + ci), co]
             int co = (int)(idx % Cout);
             long long r = idx / Cout;
             int ci = (int)(r % Cin);
             int t = (int)(r / Cin);
             v = w[((long long)co * Cin + ci) * k + t];
-            const int ld = (Cout + 3) & ~3;
-            pidx = r * ld + co;
+            R_ = tiled_rows(k * Cin);
+            pidx = tiled_index((int)r, 0, co, 1, Cout, R_);
         } else {                                      // per stride residue rho: dst_rho[ci, q*Cout + co]
             long long off = 0, poff = 0;
-            int rho = 0, Trho = 0, ld = 0;
+            int rho = 0, Trho = 0;
+            R_ = tiled_rows(Cin);
             for (rho = 0; rho < stride; ++rho) {
                 Trho = (k - rho + stride - 1) / stride;
                 if (Trho < 0) Trho = 0;
-                ld = Trho * ((Cout + 3) & ~3);
                 long long sz = (long long)Cin * Cout * Trho;
                 if (idx < off + sz) break;
                 off += sz;
-                poff += (long long)Cin * ld;
+                poff += tiled_blocks(Cin, Trho, Cout) * tiled_block_floats(R_);
             }
             long long loc = idx - off;
             int co = (int)(loc % Cout);
@@ -502,13 +504,13 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const m2d_pack_desc* __
             int q = (int)(r % Trho);
             int ci = (int)(r / Trho);
             v = w[((long long)co * Cin + ci) * k + stride * q + rho];
-            pidx = poff + (long long)ci * ld + q * ((Cout + 3) & ~3) + co;
+            pidx = poff + tiled_index(ci, q, co, Trho, Cout, R_);
         }
         if (d.dst) d.dst[idx] = v;
-        if (d.dst_hi) {
+        if (d.dst_tiled) {
             const float h = rna_tf32(v);
-            d.dst_hi[pidx] = h;
-            d.dst_lo[pidx] = rna_tf32(v - h);
+            d.dst_tiled[pidx] = h;
+            d.dst_tiled[pidx + R_ * 32] = rna_tf32(v - h);
         }
     }
 }

@@ -26,177 +26,9 @@
 #include <tuple>
 #include "common.cuh"
 
+#include "tc_ptx.cuh"
+
 namespace m2d {
-
-constexpr int TC_BM = 128;
-constexpr int TC_BK = 32;
-constexpr int TC_BNMAX = 128;
-constexpr int TC_PRODUCERS = 512;       // 16 producer / epilogue warps
-constexpr int TC_PW = TC_PRODUCERS / 32;   // index of the MMA-issuer warp; the TMA issuer is TC_PW + 1
-constexpr int TC_RPT = 128 * 8 / TC_PRODUCERS;   // 16-byte chunks of a 128-row x 128-byte tile per producer thread
-constexpr int TC_THREADS = TC_PRODUCERS + 64;   // + MMA-issuer warp + TMA-issuer warp
-constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;        // 16 KiB
-constexpr int TC_B_BYTES = TC_BNMAX * TC_BK * 4;     // 16 KiB
-
-__host__ __device__ constexpr int tc_stage_bytes(int ns) { return (ns == 3 ? 2 : 1) * (TC_A_BYTES + TC_B_BYTES); }
-__host__ __device__ constexpr int tc_stages(int ns) { return ns == 3 ? 3 : 4; }
-// stages + epilogue staging tile never coexist: the C tile (128 x 129 floats) reuses the stages
-__host__ __device__ constexpr int tc_smem_bytes(int ns) { return tc_stages(ns) * tc_stage_bytes(ns) + 1024; }
-
-// ---------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// Spin on the barrier; a pipeline bug must surface as a launch failure, never as a hung GPU:
-// after 2^22 failed polls (each poll suspends up to the hardware time limit: seconds) the kernel traps.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try(bar, parity)) {
-        if (++spins > (1u << 22)) __trap();
-    }
-}
-__device__ __forceinline__ void fence_barrier_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_smem() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by ONE thread
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ bool aligned16d(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-// round to TF32 (10 explicit mantissa bits), nearest with ties away from zero — the result of
-// cvt.rna.tf32.f32, computed on the integer pipe (the conversion pipe is a quarter-rate unit)
-__device__ __forceinline__ float to_tf32(float x) {
-    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
-}
-
-// K-major operand tile, SWIZZLE_128B: row r (128 bytes = 32 floats) lives at
-// (r/8)*1024 + (r%8)*128, its 16-byte chunk j at chunk position j ^ (r%8).
-__device__ __forceinline__ uint32_t sw128_off(int r, int j) {
-    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
-}
-// shared-memory matrix descriptor (tcgen05): start >> 4 | LBO(16 B, unused for swizzled K-major) |
-// SBO = 1024 B between 8-row groups | version 1 | layout SWIZZLE_128B (2)
-__device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-// instruction descriptor: D = F32 (1 @ bit 4), A = B = TF32 (2 @ bits 7, 10), both K-major,
-// N >> 3 @ bit 17, M >> 4 @ bit 24
-__device__ __forceinline__ uint32_t tf32_idesc(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-constexpr int TC_CLD = TC_BNMAX + 4;      // C staging tile row stride (floats): 16-byte aligned rows, conflict-free float4 access
-
-// TMEM accumulator (128 lanes x bn columns) -> shared C tile.  Warp w reads lanes 32*(w%4)..+31
-// (the tcgen05.ld lane-quarter rule); the 16-column chunks are dealt round-robin to the warps of a quarter.
-__device__ __forceinline__ void tmem_to_smem(uint32_t tmem, float* Cs, int warp, int lane, int bn) {
-    const int q = warp & 3, part = warp >> 2;
-    const int row = 32 * q + lane;
-    const int chunks = bn / 16;
-    for (int ch = part; ch < chunks; ch += TC_PW / 4) {
-        float v[16];
-        tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(16 * ch), v);
-        float4* dst = reinterpret_cast<float4*>(Cs + row * TC_CLD + 16 * ch);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) dst[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
-    }
-}
-// named barrier over the 256 producer / epilogue threads (warp 8 does not take part)
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-// Split-K over a thread-block cluster: the gridDim.z CTAs of one (m,n) tile form a cluster (1,1,Z).
-// Each keeps its partial C tile in shared memory; after a cluster barrier CTA `rank` sums rows
-// [rank*128/Z, (rank+1)*128/Z) over all Z tiles through distributed shared memory (fixed order:
-// deterministic), applies the epilogue and stores.  No global workspace, no second launch.
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_rank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ float4 dsmem_ld4(uint32_t local_addr, uint32_t rank) {
-    uint32_t ra;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
-    float4 v;
-    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
-    return v;
-}
-// sum of the 4-float chunk at (row, c4) of the C tiles of all Z CTAs of the cluster
-__device__ __forceinline__ void cluster_reduce4(const float* Cs, int rl, int c4, int Z, float* v) {
-    const uint32_t addr = smem_u32(Cs + rl * TC_CLD + c4);
-    v[0] = v[1] = v[2] = v[3] = 0.f;
-    for (int z = 0; z < Z; ++z) {
-        const float4 t = dsmem_ld4(addr, (uint32_t)z);
-        v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
-    }
-}
 
 struct TcRow {          // per output row of the CTA tile
     long long base;     // element offset of the row's batch (or sequence) in x; -1: row beyond M
@@ -205,25 +37,13 @@ struct TcRow {          // per output row of the CTA tile
     int b, i;           // batch / row indices for the epilogue
 };
 
-// TMA: one box of [128 weight rows][32 floats] lands in shared memory already in the SWIZZLE_128B
-// K-major layout the tensor core reads; completion is signalled on the stage's mbarrier.
-__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
-        : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-
-// BTMA: the weight operand comes from the pre-split packed copies (w_hi = rna_tf32(w), w_lo =
-// rna_tf32(w - w_hi), written by the re-layout kernel after each optimizer step) through TMA
-// (warp 9); the producer warps then only stage the activation operand.
+// BTMA: the weight operand comes from the pre-split, pre-tiled copy (a.w_tiled: w_hi = rna_tf32(w), w_lo =
+// rna_tf32(w - w_hi) in the tensor core's shared-memory image, written by the re-layout kernel after each
+// optimizer step): one contiguous bulk copy per stage (warp TC_PW + 1); the producer warps then only stage
+// the activation operand.
 template <int NS, bool VEC, bool C1, bool BTMA>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const int cchunks,
-                  const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
+rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const int cchunks) {
     constexpr int STAGES = tc_stages(NS);
     constexpr int STAGE_BYTES = tc_stage_bytes(NS);
     extern __shared__ uint8_t smem_raw[];
@@ -417,22 +237,25 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
             }
         }
     } else if (warp == TC_PW) {
-        // ------------------------------------------------------------------ MMA issuer (one elected lane)
-        if (lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
+        {
             const uint32_t idesc = tf32_idesc(TC_BM, bn);
             for (int it = 0; it < nk; ++it) {
                 const int st = it % STAGES;
                 const uint32_t ph = (uint32_t)((it / STAGES) & 1);
                 mbar_wait(bar_full + 8 * st, ph);
                 tc_fence_after();
+                if (elect_one()) {
                 const uint32_t sA = smem_base + (uint32_t)st * STAGE_BYTES;
                 const uint32_t sB = sA + (NS == 3 ? 2 : 1) * TC_A_BYTES;
+                // the lo plane follows the hi plane: 128 rows apart when staged by threads, R rows in a tiled block
+                const uint32_t b_plane = BTMA ? (uint32_t)tiled_rows(a.N) * 128u : (uint32_t)TC_B_BYTES;
 #pragma unroll
                 for (int k = 0; k < TC_BK / 8; ++k) {
                     const uint64_t ah = sw128_desc(sA + 32 * k), bh = sw128_desc(sB + 32 * k);
                     if (NS == 3) {
                         const uint64_t al = sw128_desc(sA + TC_A_BYTES + 32 * k);
-                        const uint64_t bl = sw128_desc(sB + TC_B_BYTES + 32 * k);
+                        const uint64_t bl = sw128_desc(sB + b_plane + 32 * k);
                         umma_tf32(tmem, al, bh, idesc, (it | k) != 0);
                         umma_tf32(tmem, ah, bl, idesc, 1);
                         umma_tf32(tmem, ah, bh, idesc, 1);
@@ -441,29 +264,30 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
                     }
                 }
                 umma_commit(bar_empty + 8 * st);     // stage reusable once these MMAs have read it
+                }
+                __syncwarp();
             }
-            umma_commit(bar_acc);                    // accumulator complete
+            if (elect_one()) umma_commit(bar_acc);   // accumulator complete
         }
         __syncwarp();
     } else {
-        // ------------------------------------------------------------------ weight-tile TMA issuer
-        if (BTMA && lane == 0) {
+        // ------------------------------------------------------------------ weight blocks: one bulk copy per stage
+        if (BTMA) {
+            const int R = tiled_rows(a.N);
+            const uint32_t bytes = (NS == 3 ? 2u : 1u) * (uint32_t)R * 128u;       // hi [+ lo] plane of the block
+            // block ((nt*T + t)*cchunks + c); Cc == 1: single tap whose channels are the taps (T = 1, c = K step)
+            const long long nt_base = (long long)blockIdx.y * (C1 ? 1 : a.T) * (C1 ? nsteps : cchunks);
             for (int it = 0; it < nk; ++it) {
                 const int st = it % STAGES;
                 const uint32_t ph = (uint32_t)((it / STAGES) & 1);
-                const int s = s_begin + it;
-                int kcol;
-                if (C1) {
-                    kcol = s * TC_BK;
-                } else {
-                    const int t = s / cchunks;
-                    kcol = t * ((a.Cc + 3) & ~3) + (s - t * cchunks) * TC_BK;   // taps padded to 4 floats in the split copies
-                }
+                const float* src = a.w_tiled + (nt_base + s_begin + it) * tiled_block_floats(R);
                 mbar_wait(bar_empty + 8 * st, ph ^ 1);
                 const uint32_t sB = smem_base + (uint32_t)st * STAGE_BYTES + (NS == 3 ? 2 : 1) * TC_A_BYTES;
-                mbar_arrive_expect_tx(bar_full + 8 * st, (NS == 3 ? 2u : 1u) * TC_B_BYTES);
-                tma_load_2d(sB, &map_hi, kcol, n0, bar_full + 8 * st);
-                if (NS == 3) tma_load_2d(sB + TC_B_BYTES, &map_lo, kcol, n0, bar_full + 8 * st);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(bar_full + 8 * st, bytes);
+                    bulk_load(sB, src, bytes, bar_full + 8 * st);
+                }
+                __syncwarp();
             }
         }
         __syncwarp();
@@ -583,10 +407,11 @@ static bool pdl_enabled() {
 
 // Launch with the split-K CTAs of a tile grouped into a (1,1,Z) thread-block cluster.
 template <typename K, typename... Args>
-static int launch_clustered(const char* what, K kern, dim3 grid, int smem, int Z, cudaStream_t st, Args... args) {
+static int launch_clustered(const char* what, K kern, dim3 grid, int smem, int Z, cudaStream_t st, int threads,
+                            Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(TC_THREADS);
+    cfg.blockDim = dim3((unsigned)threads);
     cfg.dynamicSmemBytes = (size_t)smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
@@ -615,13 +440,13 @@ static int launch_clustered(const char* what, K kern, dim3 grid, int smem, int Z
 
 // largest power-of-two split <= want that the device can co-schedule as one cluster of this kernel
 template <typename K>
-static int max_cluster_z(K kern, int smem, int want, bool allow16) {
+static int max_cluster_z(K kern, int smem, int want, bool allow16, int threads = TC_THREADS) {
     int z = 1;
     while (z * 2 <= want && z * 2 <= (allow16 ? 16 : 8)) z *= 2;
     for (; z > 1; z /= 2) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(1, 1, (unsigned)z);
-        cfg.blockDim = dim3(TC_THREADS);
+        cfg.blockDim = dim3((unsigned)threads);
         cfg.dynamicSmemBytes = (size_t)smem;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -637,7 +462,7 @@ static int max_cluster_z(K kern, int smem, int want, bool allow16) {
     return z;
 }
 
-// ---- TMA descriptors for the packed, pre-split weight matrices [N rows][ld floats] -------------
+// ---- TMA descriptor encoder (activation halo tiles, rowconv_halo.cuh) -------------
 typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -655,29 +480,8 @@ static tmap_encode_fn tmap_encoder() {
     }
     return fn;
 }
-// box = 32 floats (one 128-byte swizzle row) x 128 weight rows; rows / columns beyond the matrix read as zero
-static const CUtensorMap* weight_tmap(const float* w, int N, int ld) {
-    static std::map<std::tuple<const void*, int, int>, CUtensorMap> cache;
-    auto key = std::make_tuple((const void*)w, N, ld);
-    auto it = cache.find(key);
-    if (it != cache.end()) return &it->second;
-    tmap_encode_fn enc = tmap_encoder();
-    if (!enc) return nullptr;
-    CUtensorMap m;
-    cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)N};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {TC_BK, TC_BNMAX};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return nullptr;
-    return &cache.emplace(key, m).first->second;
-}
-
 template <int NS, bool VEC, bool C1, bool BTMA>
-static int launch_tc(const m2d_rowconv_args& a, int M, int nsteps, int cchunks, int want_splits, cudaStream_t st,
-                     const CUtensorMap* mh, const CUtensorMap* ml) {
+static int launch_tc(const m2d_rowconv_args& a, int M, int nsteps, int cchunks, int want_splits, cudaStream_t st) {
     auto kern = rowconv_tc_kernel<NS, VEC, C1, BTMA>;
     static bool configured = false;
     static int zmax = 1;
@@ -694,18 +498,20 @@ static int launch_tc(const m2d_rowconv_args& a, int M, int nsteps, int cchunks, 
     int Z = 1;
     while (Z * 2 <= want_splits && Z * 2 <= zmax) Z *= 2;
     dim3 grid((unsigned)cdiv(M, TC_BM), (unsigned)cdiv(a.N, TC_BNMAX), (unsigned)Z);
-    static const CUtensorMap dummy = {};
-    return launch_clustered("rowconv_tc", kern, grid, smem, Z, st, a, M, nsteps, cchunks, mh ? *mh : dummy,
-                            ml ? *ml : dummy);
+    return launch_clustered("rowconv_tc", kern, grid, smem, Z, st, TC_THREADS, a, M, nsteps, cchunks);
 }
 
 template <int NS, bool BTMA>
 static int launch_tc_shape(const m2d_rowconv_args& a, int M, int nsteps, int cchunks, int splits, cudaStream_t st,
-                           bool c1, bool vec, const CUtensorMap* mh, const CUtensorMap* ml) {
-    if (c1) return launch_tc<NS, false, true, BTMA>(a, M, nsteps, cchunks, splits, st, mh, ml);
-    if (vec) return launch_tc<NS, true, false, BTMA>(a, M, nsteps, cchunks, splits, st, mh, ml);
-    return launch_tc<NS, false, false, BTMA>(a, M, nsteps, cchunks, splits, st, mh, ml);
+                           bool c1, bool vec) {
+    if (c1) return launch_tc<NS, false, true, BTMA>(a, M, nsteps, cchunks, splits, st);
+    if (vec) return launch_tc<NS, true, false, BTMA>(a, M, nsteps, cchunks, splits, st);
+    return launch_tc<NS, false, false, BTMA>(a, M, nsteps, cchunks, splits, st);
 }
+
+#include "rowconv_halo.cuh"
+
+long long halo_launch_count() { return g_halo_launches; }
 
 // Called by m2d_rowconv when the tensor-core path is selected.  Returns 1 if the shape is
 // not worth a tensor-core launch (caller falls through to the SIMT kernel), <= 0 otherwise.
@@ -717,6 +523,11 @@ int rowconv_tc_dispatch(const m2d_rowconv_args& a, int M, int mode, cudaStream_t
     // passes at small batch) is weight-streaming work: one 128-row tile cannot spread over more than a
     // cluster of CTAs, the FP32 kernel splits K over the whole chip
     if (M <= 64 && K >= 4096 && a.ws) return 1;
+    // both operands through TMA, activation halo tile shared by the taps of a stride residue
+    if (!c1) {
+        const int rc = rowconv_halo_dispatch(a, M, mode, st);
+        if (rc <= 0) return rc;
+    }
     const bool vec = !c1 && a.Cc % 4 == 0 && a.x_ld % 4 == 0 && a.x_bs % 4 == 0 && a.w_ld % 4 == 0 &&
                      aligned16(a.x) && aligned16(a.w);
     const int cchunks = c1 ? 1 : (int)cdiv(a.Cc, TC_BK);
@@ -728,20 +539,13 @@ int rowconv_tc_dispatch(const m2d_rowconv_args& a, int M, int mode, cudaStream_t
         splits = (int)(want < nsteps / 4 ? want : nsteps / 4);
         if (splits < 1) splits = 1;
     }
-    // weight operand through TMA when the caller supplies the pre-split packed copies
-    const CUtensorMap *mh = nullptr, *ml = nullptr;
-    const int kpad = c1 ? (int)K : a.T * ((a.Cc + 3) & ~3);
-    if (a.w_hi && a.w_lo && a.ws_ld >= kpad && a.ws_ld % 4 == 0 && aligned16(a.w_hi) && aligned16(a.w_lo)) {
-        mh = weight_tmap(a.w_hi, a.N, a.ws_ld);
-        ml = weight_tmap(a.w_lo, a.N, a.ws_ld);
-        if (!mh || !ml) mh = ml = nullptr;
+    // weight operand by bulk copy when the caller supplies the pre-split, pre-tiled copy
+    if (a.w_tiled && aligned16(a.w_tiled)) {
+        return mode == 3 ? launch_tc_shape<3, true>(a, M, nsteps, cchunks, splits, st, c1, vec)
+                         : launch_tc_shape<1, true>(a, M, nsteps, cchunks, splits, st, c1, vec);
     }
-    if (mh) {
-        return mode == 3 ? launch_tc_shape<3, true>(a, M, nsteps, cchunks, splits, st, c1, vec, mh, ml)
-                         : launch_tc_shape<1, true>(a, M, nsteps, cchunks, splits, st, c1, vec, mh, ml);
-    }
-    return mode == 3 ? launch_tc_shape<3, false>(a, M, nsteps, cchunks, splits, st, c1, vec, nullptr, nullptr)
-                     : launch_tc_shape<1, false>(a, M, nsteps, cchunks, splits, st, c1, vec, nullptr, nullptr);
+    return mode == 3 ? launch_tc_shape<3, false>(a, M, nsteps, cchunks, splits, st, c1, vec)
+                     : launch_tc_shape<1, false>(a, M, nsteps, cchunks, splits, st, c1, vec);
 }
 
 // ============================================================================ weight gradient
@@ -884,7 +688,7 @@ wgrad_tc_kernel(const m2d_wgrad_args a, const int Ktot, const int Ncols) {
             }
         }
     } else if (warp == TC_PW) {
-        if (lane == 0) {
+        {
             // both operands MN-major: a_major (bit 15) = b_major (bit 16) = 1
             const uint32_t idesc = tf32_idesc(TC_BM, bn) | (1u << 15) | (1u << 16);
             for (int it = 0; it < nk; ++it) {
@@ -892,6 +696,7 @@ wgrad_tc_kernel(const m2d_wgrad_args a, const int Ktot, const int Ncols) {
                 const uint32_t ph = (uint32_t)((it / STAGES) & 1);
                 mbar_wait(bar_full + 8 * st, ph);
                 tc_fence_after();
+                if (elect_one()) {
                 const uint32_t sA = smem_base + (uint32_t)st * STAGE_BYTES;
                 const uint32_t sB = sA + (NS == 3 ? 2 : 1) * TC_A_BYTES;
 #pragma unroll
@@ -908,8 +713,10 @@ wgrad_tc_kernel(const m2d_wgrad_args a, const int Ktot, const int Ncols) {
                     }
                 }
                 umma_commit(bar_empty + 8 * st);
+                }
+                __syncwarp();
             }
-            umma_commit(bar_acc);
+            if (elect_one()) umma_commit(bar_acc);
         }
         __syncwarp();
     }
@@ -1010,7 +817,7 @@ static int launch_wgrad_tc(const m2d_wgrad_args& a, int Ktot, int Ncols, int wan
     int Z = 1;
     while (Z * 2 <= want_splits && Z * 2 <= zmax) Z *= 2;
     dim3 grid((unsigned)cdiv(a.Cout, TC_BM), (unsigned)cdiv(Ncols, TC_BNMAX), (unsigned)Z);
-    return launch_clustered("wgrad_tc", kern, grid, smem, Z, st, a, Ktot, Ncols);
+    return launch_clustered("wgrad_tc", kern, grid, smem, Z, st, TC_THREADS, a, Ktot, Ncols);
 }
 
 // Returns 1 when the shape does not qualify (caller uses the SIMT kernel); otherwise dw is final

@@ -113,54 +113,49 @@ class ConvLayer:
         # merged backward-data (all stride residues in one launch): needs Lin % stride == 0
         self.merged = bool(need_dgrad and stride > 1 and not self.full and Lin % stride == 0)
         self.wd = torch.empty(n, dtype=torch.float32, device=dev) if (need_dgrad and Cin > 1 and not self.merged) else None
-        # 3xTF32 operand split of the packed weights (rows padded to 4 floats, pad stays zero) for the TMA path
-        self.ldf = (k * ((Cin + 3) // 4 * 4)) if Cin > 1 else (k + 3) // 4 * 4
-        self.wph, self.wpl = z(Cout * self.ldf), z(Cout * self.ldf)
-        self.res = []                                       # (rho, Trho, offset, padded offset, padded ld) per stride residue
+        # 3xTF32 operand split of the packed weights, pre-tiled in the tensor core's shared-memory image
+        # (ops.tiled_floats; padding stays zero): one bulk copy per pipeline stage
+        tf = ops.tiled_floats
+        self.wpt = z(tf(Cout, k, Cin) if Cin > 1 else tf(Cout, 1, k))
+        self.res = []                                       # (rho, Trho, offset, tiled offset) per stride residue
         off = poff = 0
         for rho in range(stride):
             Trho = max(0, -(-(k - rho) // stride))
-            ld = Trho * ((Cout + 3) // 4 * 4)
-            self.res.append((rho, Trho, off, poff, ld))
+            self.res.append((rho, Trho, off, poff))
             off += Cin * Cout * Trho
-            poff += Cin * ld
+            poff += tf(Cin, Trho, Cout) if Trho > 0 else 0
         # weight gradients of real convolutions are produced tap-major [co, t*Cin + ci] (coalesced stores) and
         # turned into the parameter layout by one batched kernel per network (unpack_entries)
         self.gwp = z(n) if (gw is not None and k > 1 and Cin > 1) else None
         if self.merged:
             self.cmax = (stride - 1 + pad) // stride
             self.Tm = max(-(-(k - (r + pad) % stride) // stride) + self.cmax - (r + pad) // stride for r in range(stride))
-            cop = (Cout + 3) // 4 * 4
             self.wdm = z(stride * Cin * self.Tm * Cout)
-            self.wdmh, self.wdml = z(stride * Cin * self.Tm * cop), z(stride * Cin * self.Tm * cop)
-            self.ldm = self.Tm * cop
-        self.ldb = (Cout + 3) // 4 * 4                      # Linear / full-length form: [k*Cin rows][Cout]
-        if self.wd is not None:
-            m = (k * Cin * self.ldb) if (self.full or k == 1) else poff
-            self.wdh, self.wdl = z(m), z(m)
+            self.wdmt = z(tf(stride * Cin, self.Tm, Cout))
+        if self.wd is not None:                             # Linear / full-length form: [k*Cin rows][Cout]
+            self.wdt = z(tf(k * Cin, 1, Cout) if (self.full or k == 1) else poff)
         else:
-            self.wdh = self.wdl = None
+            self.wdt = None
 
     def wf(self):
         return self.w if self.wp is None else self.wp
 
     def pack_entries(self):
         """(w, dst, Cout, Cin, k, stride, kind) rows of the batched re-layout table (ops.pack_batch)."""
-        e = [(self.w, self.wp, self.wph, self.wpl, self.Cout, self.Cin, self.k, 1, ops.PACK_FWD)]
+        e = [(self.w, self.wp, self.wpt, self.Cout, self.Cin, self.k, 1, ops.PACK_FWD)]
         if self.merged:
-            e.append((self.w, self.wdm, self.wdmh, self.wdml, self.Cout, self.Cin, self.k, self.s,
-                      ops.PACK_BWD_MERGED, self.p))
+            e.append((self.w, self.wdm, self.wdmt, self.Cout, self.Cin, self.k, self.s, ops.PACK_BWD_MERGED, self.p))
         if self.wd is not None:
             if self.full or self.k == 1:
-                e.append((self.w, self.wd, self.wdh, self.wdl, self.Cout, self.Cin, self.k, 1, ops.PACK_FULL_BWD))
+                e.append((self.w, self.wd, self.wdt, self.Cout, self.Cin, self.k, 1, ops.PACK_FULL_BWD))
             else:
-                e.append((self.w, self.wd, self.wdh, self.wdl, self.Cout, self.Cin, self.k, self.s, ops.PACK_BWD))
+                e.append((self.w, self.wd, self.wdt, self.Cout, self.Cin, self.k, self.s, ops.PACK_BWD))
         return e
 
     def unpack_entries(self):
         if self.gwp is None:
             return []
-        return [(self.gwp, self.gw, None, None, self.Cout, self.Cin, self.k, 1, ops.UNPACK_GRAD)]
+        return [(self.gwp, self.gw, None, self.Cout, self.Cin, self.k, 1, ops.UNPACK_GRAD)]
 
     def unpack_grad(self):
         """Single-layer form of the batched gradient unpack (tests)."""
@@ -180,7 +175,7 @@ class ConvLayer:
     def fwd(self, x, y, act=0, bias=True, ws=None, win=None, **epi):
         ops.rowconv(x, self.wf(), y, T=self.k, Cc=self.Cin, N=self.Cout, sr=self.s, roff0=-self.p,
                     droff=1, bias=self.b if bias else None, act=act, ws=ws, win=win,
-                    w_split=(self.wph.data_ptr(), self.wpl.data_ptr(), self.ldf), **epi)
+                    w_tiled=self.wpt.data_ptr(), **epi)
 
     # dx = conv_transpose(dy) with fused epilogue (mask by act'(prev), residual add, ...)
     def dgrad(self, dy, dx, ws=None, mask=None, mask_mode=0, add=None, add_before_mask=False, y2=None):
@@ -193,7 +188,7 @@ class ConvLayer:
             yd = f(dx)
             ops.rowconv(xd, self.wd, yd, T=1, Cc=self.Cout, N=K, ws=ws, mask=f(mask), mask_mode=mask_mode,
                         add=f(add), add_before_mask=add_before_mask, y2=f(y2),
-                        w_split=(self.wdh.data_ptr(), self.wdl.data_ptr(), self.ldb))
+                        w_tiled=self.wdt.data_ptr())
             return
         s = self.s
         dense = all(m is None or (m.ld == m.cols and m.bs == m.rows * m.ld) for m in (dx, mask, add, y2))
@@ -208,12 +203,12 @@ class ConvLayer:
             ops.rowconv(dy, self.wdm, mv(dx), T=self.Tm, Cc=self.Cout, N=s * self.Cin, sr=1, roff0=self.cmax,
                         droff=-1, ws=ws, mask=mv(mask), mask_mode=mask_mode, add=mv(add),
                         add_before_mask=add_before_mask, y2=mv(y2),
-                        w_split=(self.wdmh.data_ptr(), self.wdml.data_ptr(), self.ldm))
+                        w_tiled=self.wdmt.data_ptr())
             return
         assert self.wd is not None, "strided backward-data into a non-dense buffer is not supported for this layer"
         for r0 in range(s):
             rho, c0 = (r0 + self.p) % s, (r0 + self.p) // s
-            _, Trho, off, poff, pld = self.res[rho]
+            _, Trho, off, poff = self.res[rho]
             nrows = -(-(dx.rows - r0) // s)
             if nrows <= 0:
                 continue
@@ -229,7 +224,7 @@ class ConvLayer:
             ops.rowconv(dy, wd, sub(dx), T=Trho, Cc=self.Cout, N=self.Cin, sr=1, roff0=c0, droff=-1,
                         ws=ws, mask=sub(mask), mask_mode=mask_mode, add=sub(add),
                         add_before_mask=add_before_mask, y2=sub(y2),
-                        w_split=(self.wdh.data_ptr() + 4 * poff, self.wdl.data_ptr() + 4 * poff, pld))
+                        w_tiled=self.wdt.data_ptr() + 4 * poff)
 
     def wgrad(self, dy, x, ws, scale=1.0, beta=0.0, win=None, bias=True, acc=None, bbeta=None):
         """gw = beta*gw + scale*dW;  gb = bbeta*gb + scale*db (bbeta defaults to beta)."""

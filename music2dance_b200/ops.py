@@ -91,7 +91,7 @@ def new_mat(nb, rows, cols, device, ld=None):
 # ---------------------------------------------------------------------------
 
 def rowconv(x, w, y, *, T, Cc, N, sr=1, roff0=0, droff=1, w_ld=None, bias=None, act=0,
-            mask=None, mask_mode=0, add=None, add_before_mask=False, y2=None, ws=None, win=None, w_split=None):
+            mask=None, mask_mode=0, add=None, add_before_mask=False, y2=None, ws=None, win=None, w_tiled=None):
     """y = epi(rowconv(x, w)); see m2d_rowconv in include/m2d.h.  `win` = (T_frames,
     stride, pad, seq_len) switches on fused audio windowing (x = raw audio)."""
     a = RowConvArgs()
@@ -103,8 +103,8 @@ def rowconv(x, w, y, *, T, Cc, N, sr=1, roff0=0, droff=1, w_ld=None, bias=None, 
         a.win_T, a.win_stride, a.win_pad, a.win_seq_len = win[0], win[1], win[2], win[3]
     a.nb = y.nb
     a.w, a.w_ld = _p(w), (T * Cc if w_ld is None else w_ld)
-    if w_split is not None:              # (device address of w_hi, of w_lo, row stride): TMA-fed weight operand
-        a.w_hi, a.w_lo, a.ws_ld = w_split
+    if w_tiled is not None:              # device address of the pre-split, pre-tiled weight copy (bulk-copy fed)
+        a.w_tiled = w_tiled
     a.N, a.T, a.Cc = N, T, Cc
     a.sr, a.roff0, a.droff = sr, roff0, droff
     a.y, a.y_bs, a.y_ld, a.y_rows = y.ptr, y.bs, y.ld, y.rows
@@ -157,17 +157,23 @@ PACK_FWD, PACK_BWD, PACK_FULL_BWD, UNPACK_GRAD, PACK_BWD_MERGED = 0, 1, 2, 3, 4
 
 
 def pack_table(entries, device):
-    """entries: (w, dst|None, dst_hi|None, dst_lo|None, Cout, Cin, k, stride, kind) -> device table for pack_batch."""
+    """entries: (w, dst|None, dst_tiled|None, Cout, Cin, k, stride, kind[, reserved]) -> device table for pack_batch."""
     import numpy as np
-    dt = np.dtype([("w", "<u8"), ("dst", "<u8"), ("dst_hi", "<u8"), ("dst_lo", "<u8"), ("Cout", "<i4"), ("Cin", "<i4"),
+    dt = np.dtype([("w", "<u8"), ("dst", "<u8"), ("dst_tiled", "<u8"), ("Cout", "<i4"), ("Cin", "<i4"),
                    ("k", "<i4"), ("stride", "<i4"), ("kind", "<i4"), ("reserved", "<i4")])
     arr = np.zeros(len(entries), dtype=dt)
     ptr = lambda t: 0 if t is None else t.data_ptr()
     for i, e in enumerate(entries):
-        w, dst, dh, dl, Cout, Cin, k, stride, kind = e[:9]
-        arr[i] = (w.data_ptr(), ptr(dst), ptr(dh), ptr(dl), Cout, Cin, k, stride, kind, e[9] if len(e) > 9 else 0)
+        w, dst, dtl, Cout, Cin, k, stride, kind = e[:8]
+        arr[i] = (w.data_ptr(), ptr(dst), ptr(dtl), Cout, Cin, k, stride, kind, e[8] if len(e) > 8 else 0)
     t = torch.from_numpy(arr.view(np.uint8).copy()).to(device)
     return t, len(entries)
+
+
+def tiled_floats(N, T, Cc):
+    """Size (floats) of the w_tiled copy of an [N][T*Cc] weight operand (see include/m2d.h)."""
+    R = 64 if N <= 64 else 128
+    return -(-N // R) * T * -(-Cc // 32) * 2 * R * 32
 
 
 def pack_batch(table, n):
