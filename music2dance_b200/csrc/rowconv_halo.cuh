@@ -469,7 +469,7 @@ static int rowconv_halo_dispatch(const m2d_rowconv_args& a, int M, int mode, cud
     const long long tiles = tiles_m * cdiv(a.N, TC_BNMAX);
     int splits = 1;
     if (tiles < kNumSMs && nunits >= 2) {
-        long long want = cdiv(kNumSMs, tiles);
+        long long want = kNumSMs / tiles;                    // keep the launch inside ONE wave of CTAs
         splits = (int)(want < nunits ? want : nunits);
         if (splits < 1) splits = 1;
     }

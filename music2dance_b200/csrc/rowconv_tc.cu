@@ -240,32 +240,33 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
         // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
         {
             const uint32_t idesc = tf32_idesc(TC_BM, bn);
+            // the lo plane follows the hi plane: 128 rows apart when staged by threads, R rows in a tiled block
+            const uint64_t b_plane = (uint64_t)((BTMA ? (uint32_t)tiled_rows(a.N) * 128u : (uint32_t)TC_B_BYTES) >> 4);
+            const uint64_t dA0 = sw128_desc(smem_base);
+            const uint64_t offB = (uint64_t)(((NS == 3 ? 2 : 1) * TC_A_BYTES) >> 4);
+            uint64_t dA = dA0;
+            int st = 0;
+            uint32_t ph = 0;
             for (int it = 0; it < nk; ++it) {
-                const int st = it % STAGES;
-                const uint32_t ph = (uint32_t)((it / STAGES) & 1);
                 mbar_wait(bar_full + 8 * st, ph);
                 tc_fence_after();
                 if (elect_one()) {
-                const uint32_t sA = smem_base + (uint32_t)st * STAGE_BYTES;
-                const uint32_t sB = sA + (NS == 3 ? 2 : 1) * TC_A_BYTES;
-                // the lo plane follows the hi plane: 128 rows apart when staged by threads, R rows in a tiled block
-                const uint32_t b_plane = BTMA ? (uint32_t)tiled_rows(a.N) * 128u : (uint32_t)TC_B_BYTES;
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k) {
-                    const uint64_t ah = sw128_desc(sA + 32 * k), bh = sw128_desc(sB + 32 * k);
-                    if (NS == 3) {
-                        const uint64_t al = sw128_desc(sA + TC_A_BYTES + 32 * k);
-                        const uint64_t bl = sw128_desc(sB + b_plane + 32 * k);
-                        umma_tf32(tmem, al, bh, idesc, (it | k) != 0);
-                        umma_tf32(tmem, ah, bl, idesc, 1);
-                        umma_tf32(tmem, ah, bh, idesc, 1);
-                    } else {
-                        umma_tf32(tmem, ah, bh, idesc, (it | k) != 0);
+                    for (int k = 0; k < TC_BK / 8; ++k) {
+                        const uint64_t ah = dA + 2 * k, bh = ah + offB;
+                        if (NS == 3) {
+                            umma_tf32(tmem, ah + (TC_A_BYTES >> 4), bh, idesc, (it | k) != 0);
+                            umma_tf32(tmem, ah, bh + b_plane, idesc, 1);
+                            umma_tf32(tmem, ah, bh, idesc, 1);
+                        } else {
+                            umma_tf32(tmem, ah, bh, idesc, (it | k) != 0);
+                        }
                     }
-                }
-                umma_commit(bar_empty + 8 * st);     // stage reusable once these MMAs have read it
+                    umma_commit(bar_empty + 8 * st);     // stage reusable once these MMAs have read it
                 }
                 __syncwarp();
+                dA += (uint64_t)(STAGE_BYTES >> 4);
+                if (++st == STAGES) { st = 0; ph ^= 1; dA = dA0; }
             }
             if (elect_one()) umma_commit(bar_acc);   // accumulator complete
         }
@@ -691,30 +692,33 @@ wgrad_tc_kernel(const m2d_wgrad_args a, const int Ktot, const int Ncols) {
         {
             // both operands MN-major: a_major (bit 15) = b_major (bit 16) = 1
             const uint32_t idesc = tf32_idesc(TC_BM, bn) | (1u << 15) | (1u << 16);
+            // descriptors advance incrementally (address field = addr >> 4 in the low 14 bits): no per-instruction
+            // 64-bit assembly, no division on the one thread that feeds the tensor pipe
+            const uint64_t dA0 = sw128b32_desc_mn(smem_base);
+            const uint64_t offB = (uint64_t)(((NS == 3 ? 2 : 1) * TC_A_BYTES) >> 4);
+            uint64_t dA = dA0;
+            int st = 0;
+            uint32_t ph = 0;
             for (int it = 0; it < nk; ++it) {
-                const int st = it % STAGES;
-                const uint32_t ph = (uint32_t)((it / STAGES) & 1);
                 mbar_wait(bar_full + 8 * st, ph);
                 tc_fence_after();
                 if (elect_one()) {
-                const uint32_t sA = smem_base + (uint32_t)st * STAGE_BYTES;
-                const uint32_t sB = sA + (NS == 3 ? 2 : 1) * TC_A_BYTES;
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k) {
-                    const uint64_t ah = sw128b32_desc_mn(sA + 1024 * k), bh = sw128b32_desc_mn(sB + 1024 * k);
-                    if (NS == 3) {
-                        const uint64_t al = sw128b32_desc_mn(sA + TC_A_BYTES + 1024 * k);
-                        const uint64_t bl = sw128b32_desc_mn(sB + TC_B_BYTES + 1024 * k);
-                        umma_tf32(tmem, al, bh, idesc, (it | k) != 0);
-                        umma_tf32(tmem, ah, bl, idesc, 1);
-                        umma_tf32(tmem, ah, bh, idesc, 1);
-                    } else {
-                        umma_tf32(tmem, ah, bh, idesc, (it | k) != 0);
+                    for (int k = 0; k < TC_BK / 8; ++k) {
+                        const uint64_t ah = dA + (1024 >> 4) * k, bh = ah + offB;
+                        if (NS == 3) {
+                            umma_tf32(tmem, ah + (TC_A_BYTES >> 4), bh, idesc, (it | k) != 0);
+                            umma_tf32(tmem, ah, bh + (TC_B_BYTES >> 4), idesc, 1);
+                            umma_tf32(tmem, ah, bh, idesc, 1);
+                        } else {
+                            umma_tf32(tmem, ah, bh, idesc, (it | k) != 0);
+                        }
                     }
-                }
-                umma_commit(bar_empty + 8 * st);
+                    umma_commit(bar_empty + 8 * st);
                 }
                 __syncwarp();
+                dA += (uint64_t)(STAGE_BYTES >> 4);
+                if (++st == STAGES) { st = 0; ph ^= 1; dA = dA0; }
             }
             if (elect_one()) umma_commit(bar_acc);
         }

@@ -752,8 +752,26 @@ class CriticNet:
             c += self.a_layers + [self.a_l6]
         return c + [self.fc1, self.fc2]
 
-    def pack(self):
-        _pack_net(self)
+    def pack(self, split=False):
+        """Refresh the packed weight copies.  split=True (single-GPU fused trainer): the two big layers that
+        the forward reaches last (audio_d.l5 / l6 = 68 % of the critic's parameters) are re-laid out on a side
+        stream and audio_fwd waits for them right before l5, so most of the re-layout overlaps the first
+        convolutions of the next iteration instead of sitting between Adam and the forward."""
+        if not (split and self.par and not self.ablated):
+            _pack_net(self)
+            return
+        if getattr(self, "_pack_tabs", None) is None:
+            late = [self.a_layers[4], self.a_l6]
+            early = [c for c in self.convs() if c not in late]
+            mk = lambda cs: ops.pack_table([e for c in cs for e in c.pack_entries()], self.dev)
+            self._pack_tabs = (mk(early), mk(late))
+            self.s_pack = torch.cuda.Stream(device=self.dev)
+        cur = torch.cuda.current_stream(self.dev)
+        self.s_pack.wait_stream(cur)                         # the optimiser step that produced the new weights
+        with torch.cuda.stream(self.s_pack):
+            ops.pack_batch(*self._pack_tabs[1])
+        ops.pack_batch(*self._pack_tabs[0])
+        self._late_pack = True
 
     def unpack_grads(self):
         _unpack_net_grads(self)
@@ -860,7 +878,10 @@ class CriticNet:
         A = self.cfg["audio_length"]
         x = audio if isinstance(audio, Mat) else Mat.of(audio, n, A, 1)
         sv = {"X": x, "q": []}
-        for l in self.a_layers:
+        for i, l in enumerate(self.a_layers):
+            if i == 4 and getattr(self, "_late_pack", False):
+                torch.cuda.current_stream(self.dev).wait_stream(self.s_pack)      # l5 / l6 copies (pack(split=True))
+                self._late_pack = False
             q = wk.mat(f"{tag}:q{l.name}", n, l.Lout, l.Cout)
             l.fwd(x, q, act=ACT_RELU, ws=wk.scratch)
             sv["q"].append(q)

@@ -73,6 +73,7 @@ class Phase3Trainer:
         # running statistics advance sequentially) run on a side stream and overlap the critic work.
         self.overlap = os.environ.get("M2D_OVERLAP", "1") != "0"
         self.s_gen = torch.cuda.Stream(device=dev)
+        self.split_pack = True          # critic re-layout of the late layers on a side stream (CriticNet.pack)
 
     # ------------------------------------------------------------------ pieces
     def _all_reduce(self, flat):
@@ -83,7 +84,10 @@ class Phase3Trainer:
         n = eng.fp.n_live_padded
         self._all_reduce(eng.fp.grad[:n])
         ops.adam(eng.fp.flat, eng.fp.grad, m, v, n, step, float(lr), gscale=1.0 / self.world)
-        eng.net.pack()
+        if eng is self.de and self.world == 1 and self.overlap and self.split_pack:
+            eng.net.pack(split=True)          # big late layers re-laid out next to the next iteration's first convolutions
+        else:
+            eng.net.pack()
 
     def _gen_forward(self, i):
         """Generator forward of critic iteration i (train-mode BatchNorm, no graph kept)."""
