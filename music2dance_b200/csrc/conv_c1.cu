@@ -1,0 +1,171 @@
+// Single-input-channel strided convolutions with 32 output channels (AudioDiscriminator.l1,
+// default.py:298; WaveGAN-style / U-Net encoders' first layers have the same form): forward,
+// WGAN-GP tangent pass (forward through the stored ReLU mask) and weight gradient.
+//
+// These layers carry 0.1 % of the step's FLOPs but touch the largest activation of the critic
+// (B x 19200 x 32 floats = 17 MB at B = 7), i.e. they are HBM-bound: per output row 25 FMAs per channel
+// against 128 bytes written (forward) or read (weight gradient).  On the tensor-core path they cost
+// 42-74 us per launch (a K = 25 contraction gathered one scalar at a time); here lane = output channel,
+// the taps of the lane's filter live in registers, the audio segment of the CTA's rows is staged once in
+// shared memory (zero padding resolved while staging) and read back as warp-wide broadcasts, and every
+// row is one coalesced 128-byte store / load.
+#include "common.cuh"
+
+namespace m2d {
+
+constexpr int C1_ROWS = 256;        // output rows per CTA
+constexpr int C1_U = 4;             // rows in flight per warp (independent global loads / stores)
+constexpr int C1_WARPS = 8;
+constexpr int C1_MAXT = 32;
+
+// stage x[b, r0 .. r0 + n) (zero outside [0, x_rows)) into shared memory
+__device__ __forceinline__ void c1_stage(float* xs, const float* __restrict__ xb, int r0, int n, int x_rows) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int r = r0 + i;
+        xs[i] = (r >= 0 && r < x_rows) ? __ldg(xb + r) : 0.f;
+    }
+}
+
+template <int T>
+__global__ void __launch_bounds__(C1_WARPS * 32)
+conv_c1_fwd_kernel(const m2d_rowconv_args a) {
+    extern __shared__ float xs[];
+    const int tiles = (a.y_rows + C1_ROWS - 1) / C1_ROWS;
+    const int b = blockIdx.x / tiles;
+    const int i0 = (blockIdx.x - b * tiles) * C1_ROWS;
+    const int nrows = min(C1_ROWS, a.y_rows - i0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int seg = (nrows - 1) * a.sr + T;
+    c1_stage(xs, a.x + (long long)b * a.x_bs, i0 * a.sr + a.roff0, seg, a.x_rows);
+    float w[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) w[t] = __ldg(a.w + (long long)lane * a.w_ld + t);
+    const float bz = a.bias ? __ldg(a.bias + lane) : 0.f;
+    __syncthreads();
+    for (int r0 = warp; r0 < nrows; r0 += C1_WARPS * C1_U) {
+        float mk[C1_U], acc[C1_U];
+#pragma unroll
+        for (int u = 0; u < C1_U; ++u) {                  // mask loads of the group first: C1_U loads in flight
+            const int r = r0 + u * C1_WARPS;
+            mk[u] = (a.mask_mode && r < nrows)
+                        ? __ldg(a.mask + b * a.m_bs + (long long)(i0 + r) * a.m_ld + lane) : 1.f;
+            acc[u] = bz;
+        }
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+#pragma unroll
+            for (int u = 0; u < C1_U; ++u) acc[u] = fmaf(xs[min(r0 + u * C1_WARPS, nrows - 1) * a.sr + t], w[t], acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < C1_U; ++u) {
+            const int r = r0 + u * C1_WARPS;
+            if (r >= nrows) continue;
+            float v = apply_act(acc[u], a.act);
+            if (a.mask_mode) v *= act_deriv(mk[u], a.mask_mode);
+            a.y[b * a.y_bs + (long long)(i0 + r) * a.y_ld + lane] = v;
+        }
+    }
+}
+
+// partial[cta][co][t] = sum over the CTA's rows of dy[b,i,co] * x[b, i*sr + roff0 + t]
+template <int T>
+__global__ void __launch_bounds__(C1_WARPS * 32)
+conv_c1_wgrad_kernel(const m2d_wgrad_args a) {
+    extern __shared__ float xs[];
+    const int tiles = (a.dy_rows + C1_ROWS - 1) / C1_ROWS;
+    const int b = blockIdx.x / tiles;
+    const int i0 = (blockIdx.x - b * tiles) * C1_ROWS;
+    const int nrows = min(C1_ROWS, a.dy_rows - i0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int seg = (nrows - 1) * a.sr + T;
+    c1_stage(xs, a.x + (long long)b * a.x_bs, i0 * a.sr + a.roff0, seg, a.x_rows);
+    float* red = xs + ((seg + 3) & ~3);               // [C1_WARPS][T][32]
+    float acc[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) acc[t] = 0.f;
+    __syncthreads();
+    const float* dyb = a.dy + (long long)b * a.dy_bs + lane;
+    for (int r0 = warp; r0 < nrows; r0 += C1_WARPS * C1_U) {
+        float d[C1_U];
+#pragma unroll
+        for (int u = 0; u < C1_U; ++u) {                  // C1_U independent row loads in flight
+            const int r = r0 + u * C1_WARPS;
+            d[u] = r < nrows ? __ldg(dyb + (long long)(i0 + r) * a.dy_ld) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < C1_U; ++u) {
+            const float* p = xs + min(r0 + u * C1_WARPS, nrows - 1) * a.sr;
+#pragma unroll
+            for (int t = 0; t < T; ++t) acc[t] = fmaf(d[u], p[t], acc[t]);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) red[(warp * T + t) * 32 + lane] = acc[t];
+    __syncthreads();
+    float* part = a.ws + (long long)blockIdx.x * 32 * T;
+    for (int idx = threadIdx.x; idx < 32 * T; idx += blockDim.x) {
+        const int t = idx >> 5, co = idx & 31;
+        float s = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < C1_WARPS; ++wv) s += red[(wv * T + t) * 32 + co];      // fixed order: deterministic
+        part[co * T + t] = s;
+    }
+}
+
+// dw[co, 0, t] = beta*dw + scale * sum over CTAs (fixed order) of partial[cta][co][t]
+__global__ void conv_c1_wgrad_finalize(const float* __restrict__ part, int nparts, int n, float* dw, float scale,
+                                       float beta) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int p = 0;
+    for (; p + 4 <= nparts; p += 4) {
+        s0 += part[(long long)p * n + idx];
+        s1 += part[(long long)(p + 1) * n + idx];
+        s2 += part[(long long)(p + 2) * n + idx];
+        s3 += part[(long long)(p + 3) * n + idx];
+    }
+    for (; p < nparts; ++p) s0 += part[(long long)p * n + idx];
+    float v = ((s0 + s1) + (s2 + s3)) * scale;
+    if (beta != 0.f) v += beta * dw[idx];
+    dw[idx] = v;
+}
+
+template <int T>
+static void launch_fwd(const m2d_rowconv_args& a, int grid, int smem, cudaStream_t st) {
+    conv_c1_fwd_kernel<T><<<grid, C1_WARPS * 32, smem, st>>>(a);
+}
+template <int T>
+static void launch_wgrad(const m2d_wgrad_args& a, int grid, int smem, cudaStream_t st) {
+    conv_c1_wgrad_kernel<T><<<grid, C1_WARPS * 32, smem, st>>>(a);
+}
+
+// Returns 1 if the call is not of this form (caller continues with the general kernels).
+int conv_c1_fwd_dispatch(const m2d_rowconv_args& a, cudaStream_t st) {
+    if (a.Cc != 1 || a.N != 32 || a.win_T > 0 || a.droff != 1 || a.sr < 1 || a.add || a.y2 || a.x_ld != 1) return 1;
+    if (a.T != 25) return 1;                          // instantiated filter length (audio_d.l1, WaveGAN-style l1)
+    const int tiles = (a.y_rows + C1_ROWS - 1) / C1_ROWS;
+    const int smem = ((C1_ROWS - 1) * a.sr + a.T) * 4;
+    if (smem > 48 * 1024) return 1;
+    const int grid = a.nb * tiles;
+    launch_fwd<25>(a, grid, smem, st);
+    return check_launch("conv_c1_fwd");
+}
+
+int conv_c1_wgrad_dispatch(const m2d_wgrad_args& a, cudaStream_t st) {
+    if (a.Cc != 1 || a.Cout != 32 || a.win_T > 0 || a.droff != 1 || a.sr < 1 || a.x_ld != 1 || !a.ws) return 1;
+    if (a.T != 25) return 1;
+    const int tiles = (a.dy_rows + C1_ROWS - 1) / C1_ROWS;
+    const int grid = a.nb * tiles;
+    const int seg = (C1_ROWS - 1) * a.sr + a.T;
+    const int smem = (((seg + 3) & ~3) + C1_WARPS * a.T * 32) * 4;
+    if (smem > 48 * 1024 || a.ws_floats < (long long)grid * 32 * a.T) return 1;
+    launch_wgrad<25>(a, grid, smem, st);
+    int rc = check_launch("conv_c1_wgrad");
+    if (rc) return rc;
+    const int n = 32 * a.T;
+    conv_c1_wgrad_finalize<<<(n + 255) / 256, 256, 0, st>>>(a.ws, grid, n, a.dw, a.scale, a.beta);
+    return check_launch("conv_c1_wgrad_finalize");
+}
+
+}  // namespace m2d
