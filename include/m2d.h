@@ -235,6 +235,14 @@ int m2d_pose_losses(const float* real, const float* fake, float* dfake, int B, i
                     float beta, float eta, int accumulate, double* acc, void* stream);
 /* relu / leaky / tanh derivative applied in place from stored activations */
 int m2d_act_bwd(float* d, const float* y, long long n, int mask_mode, void* stream);
+/* Input pipeline: SequenceDataset.__getitem__ + collate_fn (utils.py:91-101,128-144) and the H2D
+ * copies of phase3/train.py:191-193 on a DEVICE-RESIDENT dataset.  poses / music hold every sequence back to back
+ * (float32; offsets in floats); batch entry b becomes frames [start[b], start[b]+T) of sequence seq[b]
+ * (real[b, t, :O]) and samples [start[b]*ratio, +A) of its music (audio[b, :A]).  Bit-exact (pure indexing); the
+ * caller guarantees start[b] + T <= frames of the sequence and start[b]*ratio + A <= samples of its music. */
+int m2d_crop_batch(const float* poses, const long long* pose_off, const float* music, const long long* music_off,
+                   const int* seq, const int* start, int B, int T, int O, int ratio, int A, float* real,
+                   float* audio, void* stream);
 /* out = alpha * a * b * c elementwise on strided row matrices [M][C]: the second-order term of the
  * gradient penalty through a tanh code activation (autograd double backward of default.py:333,303
  * inside losses.py:40-44) */

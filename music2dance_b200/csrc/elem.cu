@@ -441,6 +441,25 @@ __global__ void slice_audio_kernel(const float* __restrict__ audio, float* __res
     }
 }
 
+// SequenceDataset.__getitem__ + collate_fn (utils.py:91-101,128-144) on a device-resident dataset: batch entry b
+// is frames [start, start + T) of sequence seq[b] and audio samples [start*ratio, start*ratio + A) of its music.
+// Pure indexing: bit-exact.  blockIdx.y = batch entry; blockIdx.x strides over the entry's T*O + A floats.
+__global__ void crop_batch_kernel(const float* __restrict__ poses, const long long* __restrict__ pose_off,
+                                  const float* __restrict__ music, const long long* __restrict__ music_off,
+                                  const int* __restrict__ seq, const int* __restrict__ start, int TO, int O,
+                                  int ratio, int A, float* __restrict__ real, float* __restrict__ audio) {
+    const int b = blockIdx.y;
+    const int s = seq[b], st = start[b];
+    const float* p = poses + pose_off[s] + (long long)st * O;
+    const float* m = music + music_off[s] + (long long)st * ratio;
+    float* r = real + (long long)b * TO;
+    float* a = audio + (long long)b * A;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < TO + A; i += gridDim.x * blockDim.x) {
+        if (i < TO) r[i] = p[i];
+        else a[i - TO] = m[i - TO];
+    }
+}
+
 // ---------------------------------------------------------------- Adam
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, const int* step, float lr, float b1,
@@ -667,6 +686,18 @@ extern "C" int m2d_slice_audio(const float* audio, float* out, int nseq, int A, 
     dim3 grid((unsigned)(cdiv(W, 256) < 8 ? cdiv(W, 256) : 8), (unsigned)nwin, (unsigned)nseq);
     slice_audio_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(audio, out, A, nwin, W, stride, pad_left);
     return check_launch("slice_audio");
+}
+
+extern "C" int m2d_crop_batch(const float* poses, const long long* pose_off, const float* music,
+                              const long long* music_off, const int* seq, const int* start, int B, int T, int O,
+                              int ratio, int A, float* real, float* audio, void* stream) {
+    M2D_REQUIRE(poses && pose_off && music && music_off && seq && start && real && audio, "crop_batch: null pointer");
+    M2D_REQUIRE(B > 0 && B <= 65535 && T > 0 && O > 0 && ratio > 0 && A > 0, "crop_batch: bad dims");
+    const int per = T * O + A;
+    dim3 grid((unsigned)((per + 1023) / 1024 < 64 ? (per + 1023) / 1024 : 64), (unsigned)B);
+    crop_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(poses, pose_off, music, music_off, seq, start, T * O, O,
+                                                             ratio, A, real, audio);
+    return check_launch("crop_batch");
 }
 
 extern "C" int m2d_adam(float* p, const float* g, float* m, float* v, long long n, int* step, float lr,

@@ -324,6 +324,12 @@ def slice_audio(audio, out, nseq, A, nwin, W, stride, pad_left):
     call("m2d_slice_audio", _p(audio), _p(out), nseq, A, nwin, W, stride, pad_left, _stream())
 
 
+def crop_batch(poses, pose_off, music, music_off, seq, start, B, T, O, ratio, A, real, audio):
+    LAUNCHES[0] += 1
+    call("m2d_crop_batch", _p(poses), _p(pose_off), _p(music), _p(music_off), _p(seq), _p(start), B, T, O, ratio, A,
+         _p(real), _p(audio), _stream())
+
+
 def adam(p, g, m, v, n, step, lr, b1=0.9, b2=0.999, eps=1e-8, gscale=1.0):
     LAUNCHES[0] += 2
     call("m2d_adam", _p(p), _p(g), _p(m), _p(v), n, _p(step), lr, b1, b2, eps, gscale, _stream())
