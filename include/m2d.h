@@ -233,6 +233,9 @@ int m2d_gp_finalize(const double* ss0, const double* ss1, int B, float* gp, floa
  * dfake = (+= if accumulate) beta*dL1/dfake + eta*dTV/dfake */
 int m2d_pose_losses(const float* real, const float* fake, float* dfake, int B, int T, int C,
                     float beta, float eta, int accumulate, double* acc, void* stream);
+/* losses.py:85-89 (jerkiness, the smoothness metric of phase3/test.py:85-100) on channels-last poses [B,T,C]:
+ * acc[0] += sum over b, t < T-3, c of (x[t+3] - 3 x[t+2] + 3 x[t+1] - x[t])^2;  jerkiness = acc[0] / (B (T-3)) */
+int m2d_jerkiness(const float* x, int B, int T, int C, double* acc, void* stream);
 /* relu / leaky / tanh derivative applied in place from stored activations */
 int m2d_act_bwd(float* d, const float* y, long long n, int mask_mode, void* stream);
 /* Input pipeline: SequenceDataset.__getitem__ + collate_fn (utils.py:91-101,128-144) and the H2D

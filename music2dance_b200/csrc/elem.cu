@@ -278,6 +278,23 @@ __global__ void pose_losses_kernel(const float* __restrict__ real, const float* 
     block_atomic_add(s2, acc + 1);
 }
 
+// losses.py:85-89 jerkiness on channels-last poses [B,T,C]: acc[0] += sum_{b, t < T-3, c} (third difference)^2
+__global__ void jerk_kernel(const float* __restrict__ x, int B, int T, int C, double* acc) {
+    const long long n = (long long)B * (T - 3) * C;
+    double s = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const long long r = i / C;
+        const int t = (int)(r % (T - 3));
+        const long long b = r / (T - 3);
+        const float* p = x + (b * T + t) * C + c;
+        const float d = p[3 * C] - 3.f * p[2 * C] + 3.f * p[C] - p[0];
+        s += (double)d * (double)d;
+    }
+    block_atomic_add(s, acc);
+}
+
 __global__ void act_bwd_kernel(float* d, const float* __restrict__ y, long long n, int mode) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x)
@@ -606,6 +623,12 @@ extern "C" int m2d_pose_losses(const float* real, const float* fake, float* dfak
     pose_losses_kernel<<<grid1d(n, 256, 2), 256, 0, (cudaStream_t)stream>>>(real, fake, dfake, B, T, C, beta,
                                                                         eta, accumulate, acc);
     return check_launch("pose_losses");
+}
+
+extern "C" int m2d_jerkiness(const float* x, int B, int T, int C, double* acc, void* stream) {
+    M2D_REQUIRE(x && acc && B > 0 && T > 3 && C > 0, "jerkiness: bad args (needs T > 3)");
+    jerk_kernel<<<grid1d((long long)B * (T - 3) * C, 256, 2), 256, 0, (cudaStream_t)stream>>>(x, B, T, C, acc);
+    return check_launch("jerkiness");
 }
 
 extern "C" int m2d_act_bwd(float* d, const float* y, long long n, int mask_mode, void* stream) {

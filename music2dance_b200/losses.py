@@ -88,6 +88,19 @@ class _TVFn(torch.autograd.Function):
         return (ctx.d * g).transpose(1, 2)
 
 
+def jerkiness(sequence):
+    """Smoothness metric of phase3/test.py:85-100 (losses.py:85-89): squared third temporal difference, summed
+    over the coordinates, averaged over batch and time, for (B, C, T) input.  No gradient (evaluation only)."""
+    if not sequence.is_cuda:
+        raise RuntimeError("jerkiness needs CUDA tensors (no CPU fallback)")
+    B, C, T = sequence.shape
+    with torch.cuda.device(sequence.device):
+        x = sequence.detach().transpose(1, 2).contiguous().float()
+        acc = torch.zeros(1, dtype=torch.float64, device=sequence.device)
+        ops.jerkiness(x, B, T, C, acc)
+        return (acc[0] / (B * (T - 3))).float()
+
+
 def tv_loss(sequence):
     """Total-variation regulariser: mean |x[:,:,1:] - x[:,:,:-1]| for (B, C, T) input."""
     if not sequence.is_cuda:

@@ -272,6 +272,11 @@ def pose_losses(real, fake, dfake, B, T, Cn, beta, eta, accumulate, acc):
          _stream())
 
 
+def jerkiness(x, B, T, Cn, acc):
+    LAUNCHES[0] += 1
+    call("m2d_jerkiness", _p(x), B, T, Cn, _p(acc), _stream())
+
+
 def act_bwd(d, y, n, mode):
     LAUNCHES[0] += 1
     call("m2d_act_bwd", _p(d), _p(y), n, mode, _stream())

@@ -278,6 +278,24 @@ class Phase3Trainer:
                 elif kind == "g":
                     self._all_reduce(self.ge.fp.grad[:self.ge.fp.n_live_padded])
 
+    def validate(self, real, audio, noise):
+        """Validation pass of phase3/train.py:245-261: eval-mode generator (BatchNorm running statistics) on one
+        batch, mean |real - fake|.  real (Bv,T,23,3)|(Bv,T,69), audio (Bv,A), noise (Bv,T,Nz) (the reference draws
+        it with torch.randn on the CPU generator; pass that tensor for parity).  Returns (l1 0-d tensor, fake
+        (Bv*T, 69)).  Uses its own buffers, never touches optimiser state or running statistics."""
+        Bv = real.shape[0]
+        f = dict(dtype=torch.float32, device=self.dev)
+        with torch.cuda.device(self.dev):
+            r = real.to(**f).reshape(Bv, self.T, self.O).contiguous()
+            a = audio.to(**f).reshape(Bv, self.A).contiguous()
+            z = noise.to(**f).reshape(Bv, self.T, self.Nz).contiguous()
+            fake = torch.empty(Bv * self.T, self.O, **f)
+            self.ge.ensure_packed()
+            self.G.forward(a, z, Bv, self.T, train=False, out=Mat.of(fake, 1, Bv * self.T, self.O))
+            acc = torch.zeros(2, dtype=torch.float64, device=self.dev)
+            ops.pose_losses(r, fake, None, Bv, self.T, self.O, 0.0, 0.0, False, acc)
+            return (acc[0] / (Bv * self.T * self.O)).float(), fake
+
     def logs(self):
         """Scalars of the last train step (device->host read; synchronises)."""
         c = self.log_c.cpu()

@@ -438,6 +438,23 @@ def gradient_penalty(P, cfg, real, fake, audio, alpha):
     return ((n0 - 1) ** 2).mean() + ((n1 - 1) ** 2).mean(), g0.detach(), g1.detach()
 
 
+def jerkiness(seq):
+    """losses.py:85-89 for (B, C, T) input."""
+    d = seq[:, :, 3:] - 3 * seq[:, :, 2:-1] + 3 * seq[:, :, 1:-2] - seq[:, :, :-3]
+    return (d ** 2).sum(dim=1).mean()
+
+
+def validation_l1(G, cfg, real_bt, audio, noise):
+    """phase3/train.py:245-261 for one validation batch: eval-mode generator, mean |real - fake|.
+    Returns (l1, fake (B, 69, T))."""
+    B, T, Oo = real_bt.shape[0], cfg["stick_length"], cfg["output_size"]
+    with torch.no_grad():
+        sl = slice_audio_batch(audio, cfg["audio_feat_samples"], cfg["cutting_stride"], cfg["pad_samples"])
+        real = real_bt.reshape(B, T, Oo).permute(0, 2, 1)
+        fake = generator_forward(G, cfg, sl, noise, train=False).view(B, T, Oo).permute(0, 2, 1)
+        return float((real - fake).abs().mean()), fake
+
+
 def tv_loss(seq):
     """losses.py:76-82: mean |x[t+1]-x[t]| over (B,C,T-1)."""
     return (seq[:, :, 1:] - seq[:, :, :-1]).abs().mean()
