@@ -228,6 +228,8 @@ int m2d_sum(const float* x, long long n, double* out, void* stream);
  * scal[0] = gp, kappa0[b] = dGP/d||.|| chain factor (2/B)(n-1)/n, same for kappa1 */
 int m2d_gp_finalize(const double* ss0, const double* ss1, int B, float* gp, float* kappa0,
                     float* kappa1, void* stream);
+/* losses.py:47-50 (lp=True, the phase2 trainers): gp = mean(max(0, ||g|| - 1)^2), kappa0[b] = (2/B) max(0, n-1)/n */
+int m2d_gp_finalize_lp(const double* ss0, int B, float* gp, float* kappa0, void* stream);
 /* train.py:226,233 + losses.py:76-82 on channels-last poses [B,T,C]:
  * acc[0] += sum|real-fake|, acc[1] += sum|f[t+1]-f[t]|;
  * dfake = (+= if accumulate) beta*dL1/dfake + eta*dTV/dfake */

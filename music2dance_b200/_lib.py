@@ -83,6 +83,7 @@ SIGNATURES = {
     "m2d_rows_sumsq": [_P, _I, _L, _P, _P],
     "m2d_sum": [_P, _L, _P, _P],
     "m2d_gp_finalize": [_P, _P, _I, _P, _P, _P, _P],
+    "m2d_gp_finalize_lp": [_P, _I, _P, _P, _P],
     "m2d_pose_losses": [_P, _P, _P, _I, _I, _I, _F, _F, _I, _P, _P],
     "m2d_jerkiness": [_P, _I, _I, _I, _P, _P],
     "m2d_act_bwd": [_P, _P, _L, _I, _P],

@@ -250,6 +250,24 @@ __global__ void gp_finalize_kernel(const double* ss0, const double* ss1, int B, 
     if (threadIdx.x == 0) gp[0] = (float)(total / (double)B);
 }
 
+// losses.py:47-50, WGAN-LP: bgrad = max(0, ||g||_2 - 1) (no epsilon under the root), penalty = mean(bgrad^2);
+// kappa[b] = d penalty / d g[b,:] / g[b,:] = (2/B) bgrad / ||g||  (0 where the norm is below 1)
+__global__ void gp_finalize_lp_kernel(const double* ss0, int B, float* gp, float* k0) {
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float n0 = sqrtf((float)ss0[b]);
+        float d0 = n0 - 1.f;
+        d0 = d0 < 0.f ? 0.f : d0;
+        acc += (double)(d0 * d0);
+        k0[b] = d0 > 0.f ? (2.f / (float)B) * d0 / n0 : 0.f;
+    }
+    __shared__ double total;
+    if (threadIdx.x == 0) total = 0.0;
+    __syncthreads();
+    block_atomic_add(acc, &total);
+    if (threadIdx.x == 0) gp[0] = (float)(total / (double)B);
+}
+
 __device__ __forceinline__ float sgn(float v) { return (v > 0.f) - (v < 0.f); }
 
 __global__ void pose_losses_kernel(const float* __restrict__ real, const float* __restrict__ fake,
@@ -614,6 +632,12 @@ extern "C" int m2d_gp_finalize(const double* ss0, const double* ss1, int B, floa
     M2D_REQUIRE(ss0 && gp && kappa0 && B > 0 && (!ss1 || kappa1), "gp_finalize: bad args");
     gp_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(ss0, ss1, B, gp, kappa0, kappa1);
     return check_launch("gp_finalize");
+}
+
+extern "C" int m2d_gp_finalize_lp(const double* ss0, int B, float* gp, float* kappa0, void* stream) {
+    M2D_REQUIRE(ss0 && gp && kappa0 && B > 0, "gp_finalize_lp: bad args");
+    gp_finalize_lp_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(ss0, B, gp, kappa0);
+    return check_launch("gp_finalize_lp");
 }
 
 extern "C" int m2d_pose_losses(const float* real, const float* fake, float* dfake, int B, int T, int C,

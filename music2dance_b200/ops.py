@@ -266,6 +266,11 @@ def gp_finalize(ss0, ss1, B, gp, k0, k1):
     call("m2d_gp_finalize", _p(ss0), _p(ss1), B, _p(gp), _p(k0), _p(k1), _stream())
 
 
+def gp_finalize_lp(ss0, B, gp, k0):
+    LAUNCHES[0] += 1
+    call("m2d_gp_finalize_lp", _p(ss0), B, _p(gp), _p(k0), _stream())
+
+
 def pose_losses(real, fake, dfake, B, T, Cn, beta, eta, accumulate, acc):
     LAUNCHES[0] += 1
     call("m2d_pose_losses", _p(real), _p(fake), _p(dfake), B, T, Cn, beta, eta, int(accumulate), _p(acc),
