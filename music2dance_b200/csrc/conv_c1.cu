@@ -61,8 +61,10 @@ conv_c1_fwd_kernel(const m2d_rowconv_args a) {
             const int r = r0 + u * C1_WARPS;
             if (r >= nrows) continue;
             float v = apply_act(acc[u], a.act);
+            const long long yo = b * a.y_bs + (long long)(i0 + r) * a.y_ld + lane;
+            if (a.y2) a.y2[yo] = v;
             if (a.mask_mode) v *= act_deriv(mk[u], a.mask_mode);
-            a.y[b * a.y_bs + (long long)(i0 + r) * a.y_ld + lane] = v;
+            a.y[yo] = v;
         }
     }
 }
@@ -142,7 +144,7 @@ static void launch_wgrad(const m2d_wgrad_args& a, int grid, int smem, cudaStream
 
 // Returns 1 if the call is not of this form (caller continues with the general kernels).
 int conv_c1_fwd_dispatch(const m2d_rowconv_args& a, cudaStream_t st) {
-    if (a.Cc != 1 || a.N != 32 || a.win_T > 0 || a.droff != 1 || a.sr < 1 || a.add || a.y2 || a.x_ld != 1) return 1;
+    if (a.Cc != 1 || a.N != 32 || a.win_T > 0 || a.droff != 1 || a.sr < 1 || a.add || a.x_ld != 1) return 1;
     if (a.T != 25) return 1;                          // instantiated filter length (audio_d.l1, WaveGAN-style l1)
     const int tiles = (a.y_rows + C1_ROWS - 1) / C1_ROWS;
     const int smem = ((C1_ROWS - 1) * a.sr + a.T) * 4;

@@ -850,18 +850,20 @@ class CriticNet:
         n = acts["y"].nb
         self.s_fconv.wgrad(dl["fconv"].as_rows(n, 1), acts["y"], wk.scratch, acc=A(self.s_fconv), **kw)
 
-    def pose_tangent(self, sv, V, n, tag, t_code):
-        """JVP of the pose branch along V [n,T,O] with the ReLU masks of `sv` (no biases)."""
+    def pose_tangent(self, sv, V, n, tag, t_code, inplace=False):
+        """JVP of the pose branch along V [n,T,O] with the ReLU masks of `sv` (no biases).
+        inplace: the tangent activations overwrite the forward activations they correspond to (t0 -> r0, t1 -> r1,
+        ty -> y; the r2 masks stay), so that `sv` afterwards holds the layer inputs of the penalty's weight gradients."""
         wk, T, Ch = self.wk, self.T, self.Ch
-        t0 = wk.mat(f"{tag}:t0", n, T, Ch)
+        t0 = sv["r0"] if inplace else wk.mat(f"{tag}:t0", n, T, Ch)
         self.s_conv1.fwd(V, t0, bias=False, ws=wk.scratch, mask=sv["r0"], mask_mode=ACT_RELU)
         tv = {"X": V, "r0": t0, "blk": []}
         x = t0
         for b, (c1, c2) in enumerate(self.s_blocks):
-            _, r1, r2, _ = sv["blk"][b]
-            t1 = wk.mat(f"{tag}:tb{b}1", n, T, Ch)
+            _, r1, r2, y_fw = sv["blk"][b]
+            t1 = r1 if inplace else wk.mat(f"{tag}:tb{b}1", n, T, Ch)
             c1.fwd(x, t1, bias=False, ws=wk.scratch, mask=r1, mask_mode=ACT_RELU)
-            ty = wk.mat(f"{tag}:tb{b}y", n, T, Ch)
+            ty = y_fw if inplace else wk.mat(f"{tag}:tb{b}y", n, T, Ch)
             c2.fwd(t1, ty, bias=False, ws=wk.scratch, mask=r2, mask_mode=ACT_RELU, add=x)
             tv["blk"].append((x, t1, None, ty))
             x = ty
@@ -871,19 +873,29 @@ class CriticNet:
         return tv
 
     # ---------------------------------------------------------------- audio branch
-    def audio_fwd(self, audio, n, tag):
-        """audio: tensor [n, A] (C=1 channels-last == raw); sv["code"] dense [1,n,code]."""
+    def audio_fwd(self, audio, n, tag, dup=False):
+        """audio: tensor [n, A] (C=1 channels-last == raw); sv["code"] dense [1,n,code].
+        dup: every activation buffer has 2n batch entries and the forward writes BOTH halves (second copy through
+        the epilogue's y2 output): the fused backward (wgan.critic_backward_fused) back-propagates the Wasserstein
+        and the penalty upstreams as ONE batch of 2n entries through the same ReLU masks, then overwrites the second
+        half in place with the tangent activations so that one weight-gradient GEMM per layer covers both terms."""
         wk = self.wk
         code_out = wk.mat(f"{tag}:code_a", 1, n, self.code)
         A = self.cfg["audio_length"]
         x = audio if isinstance(audio, Mat) else Mat.of(audio, n, A, 1)
-        sv = {"X": x, "q": []}
+        sv = {"X": x, "q": [], "q2": []}
         for i, l in enumerate(self.a_layers):
             if i == 4 and getattr(self, "_late_pack", False):
                 torch.cuda.current_stream(self.dev).wait_stream(self.s_pack)      # l5 / l6 copies (pack(split=True))
                 self._late_pack = False
-            q = wk.mat(f"{tag}:q{l.name}", n, l.Lout, l.Cout)
-            l.fwd(x, q, act=ACT_RELU, ws=wk.scratch)
+            if dup:
+                q2 = wk.mat(f"{tag}:q2{l.name}", 2 * n, l.Lout, l.Cout)
+                q = q2.batch_slice(0, n)
+                l.fwd(x, q, act=ACT_RELU, ws=wk.scratch, y2=q2.batch_slice(n, 2 * n))
+                sv["q2"].append(q2)
+            else:
+                q = wk.mat(f"{tag}:q{l.name}", n, l.Lout, l.Cout)
+                l.fwd(x, q, act=ACT_RELU, ws=wk.scratch)
             sv["q"].append(q)
             x = q
         self.a_l6.fwd(x, code_out.as_rows(n, 1), act=self.act, ws=wk.scratch)
@@ -927,14 +939,16 @@ class CriticNet:
         n = x.nb
         self.a_l6.wgrad(dl["l6"].as_rows(n, 1), x, wk.scratch, acc=wk.acc_slot(self.a_l6.Cout), **kw)
 
-    def audio_tangent(self, sv, V, n, tag, t_code):
+    def audio_tangent(self, sv, V, n, tag, t_code, inplace=False):
+        """inplace: sv["q"][i] are copies of the forward activations that serve as ReLU masks and are overwritten by
+        the tangent activations (every output element is read and written by the same thread of the epilogue)."""
         wk = self.wk
         A = self.cfg["audio_length"]
         x = V if isinstance(V, Mat) else Mat.of(V, n, A, 1)
         x0 = x
         tq = []
         for i, l in enumerate(self.a_layers):
-            t = wk.mat(f"{tag}:t{l.name}", n, l.Lout, l.Cout)
+            t = sv["q"][i] if inplace else wk.mat(f"{tag}:t{l.name}", n, l.Lout, l.Cout)
             l.fwd(x, t, bias=False, ws=wk.scratch, mask=sv["q"][i], mask_mode=ACT_RELU)
             tq.append(t)
             x = t

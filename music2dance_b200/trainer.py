@@ -23,7 +23,9 @@ import torch
 
 from . import dp, ops
 from .ops import Mat
-from .wgan import critic_forward, gradient_penalty_pass, rows, wasserstein_backward
+from .nets import ACT_ID
+from .wgan import (critic_backward_fused, critic_forward, critic_forward_fused, gradient_penalty_pass, rows,
+                   wasserstein_backward)
 
 LOG_CRITIC = ("loss_critic", "gp", "w_dist", "err_real", "err_fake")
 LOG_GEN = ("loss_gen", "l1", "tv", "err_real", "err_fake")
@@ -74,6 +76,8 @@ class Phase3Trainer:
         self.overlap = os.environ.get("M2D_OVERLAP", "1") != "0"
         self.s_gen = torch.cuda.Stream(device=dev)
         self.split_pack = True          # critic re-layout of the late layers on a side stream (CriticNet.pack)
+        # one backward sweep per critic iteration (wgan.critic_backward_fused); M2D_FUSED_BWD=0: two chains
+        self.fused_backward = os.environ.get("M2D_FUSED_BWD", "1") != "0"
 
     # ------------------------------------------------------------------ pieces
     def _all_reduce(self, flat):
@@ -114,12 +118,25 @@ class Phase3Trainer:
         ops.interp(real, fake_c, self.in_alpha[i], X3, B, per)
         ops.axpby(real, None, rows(X3, B, 2 * B), B * per, 1.0, 0.0)
         ops.axpby(fake_c, None, rows(X3, 2 * B, n3), B * per, 1.0, 0.0)
+        gamma = float(self.cfg["gamma"])
+        if self.fused_backward and D.act == ACT_ID:
+            # one backward sweep for the Wasserstein terms and the penalty (wgan.critic_backward_fused)
+            fw = critic_forward_fused(D, X3, None if D.ablated else audio, B, "c")
+            sums = wk.acc_slot(4)
+            d = fw["d"]
+            ops.sum_(rows(d, B, 2 * B), B, sums[0:1])
+            ops.sum_(rows(d, 2 * B, n3), B, sums[1:2])
+            critic_backward_fused(D, fw, B, audio, gamma, self.gp_buf, self.k0, self.k1)
+            ops.wgan_scalars(sums, self.gp_buf, B, 1, 1, gamma, 0.0, 0, self.log_c[i])
+            D.unpack_grads()
+            if update:
+                self._adam(self.de, self.mD, self.vD, self.stepD, self.cfg["lr_critic"])
+            return
         fw = critic_forward(D, X3, None if D.ablated else audio, n3, B, "c", groups=3)
         sums = wk.acc_slot(4)
         d = fw["d"]
         ops.sum_(rows(d, B, 2 * B), B, sums[0:1])
         ops.sum_(rows(d, 2 * B, n3), B, sums[1:2])
-        gamma = float(self.cfg["gamma"])
         # two independent backward chains over the same forward state: the Wasserstein terms (second
         # stream pair; they OVERWRITE the gradient buffers) and the gradient penalty (backward-data,
         # tangent pass; its weight gradients ACCUMULATE once the first chain is done)

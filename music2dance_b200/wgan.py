@@ -16,6 +16,8 @@ The gradient penalty is evaluated without autograd:
 """
 from __future__ import annotations
 
+import torch
+
 from . import ops
 from .nets import ACT_ID, ACT_RELU, ACT_TANH
 from .ops import Mat
@@ -131,6 +133,188 @@ def gradient_penalty_pass(D, fw, B, tag, scale, beta, gp_out, k0, k1, weight_gra
         D.pose_bwd(dict(svp), e_s, B, f"{tag}2", scale=scale, beta=1.0, wgrads=True, bbeta=beta, pre_act=True)
         D.join()
     return out
+
+
+def critic_forward_fused(D, X3, audio, B, tag):
+    """critic_forward for the fused backward below: pose branch on the 3B rows [interpolates; real; fake], audio
+    branch once on B samples with duplicated activation buffers (CriticNet.audio_fwd(dup=True))."""
+    wk = D.wk
+    n3 = 3 * B
+    sa = wk.mat(f"{tag}:sa", 1, n3, D.F)
+    sva = None
+    if not D.ablated:
+        with D.fork():
+            sva = D.audio_fwd(audio, B, tag, dup=True)
+            for g in range(3):
+                ops.copy2d(sva["code"], rows(sa, g * B, (g + 1) * B).cols_slice(D.code, D.F))
+    svp = D.pose_fwd(X3, n3, tag)
+    ops.copy2d(svp["code"], sa.cols_slice(0, D.code))
+    D.join()
+    u, d = D.fusion_fwd(sa, n3, tag)
+    return dict(svp=svp, sva=sva, sa=sa, u=u, d=d)
+
+
+def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f"):
+    """Critic gradients of  err_fake - err_real + gamma * gp  (phase3/train.py:204-215) in ONE backward sweep.
+
+    Rows of the forward state: [0,B) interpolates, [B,2B) real, [2B,3B) fake.  The Wasserstein terms and the
+    penalty are back-propagated together — pose branch: one backward-data pass over all 3B rows (upstream 1 on
+    the interpolates, -1/B / +1/B on real / fake); audio branch (evaluated once on B samples): one pass over 2B
+    batch entries [Wasserstein upstream; penalty upstream] through the same ReLU masks (second copy of the
+    activations).  After the per-sample norms, v = gamma * kappa * g goes through the tangent pass IN PLACE: the
+    tangent activations overwrite the interpolates' forward activations (pose) / the mask copies (audio), so that
+    afterwards every layer has ONE stacked input operand [tangent; forward] matching its stacked deltas
+    [penalty; Wasserstein], and a single weight-gradient GEMM per layer produces
+        dW = sum delta_w (x) x  +  gamma * sum delta_gp (x) t.
+    Against the two separate chains (wasserstein_backward + gradient_penalty_pass) this halves the backward-data
+    and weight-gradient launches of an iteration.  Biases: Wasserstein rows only (Q5).  Piecewise-linear critic
+    with identity code activation only (activ='id'); other settings use the two-chain path."""
+    assert D.act == ACT_ID
+    wk, T, O, code = D.wk, D.T, D.O, D.code
+    n3 = 3 * B
+    A1 = lambda c: wk.acc_slot(c)
+    dd = wk.vec(f"{tag}:dd", n3)
+    ops.fill(dd[:B], B, 1.0)
+    ops.fill(dd[B:2 * B], B, -1.0 / B)
+    ops.fill(dd[2 * B:], B, 1.0 / B)
+    ddm = Mat(dd, 1, n3, 1)
+    u, sa = fw["u"], fw["sa"]
+    D.fc2.wgrad(rows(ddm, B, n3), rows(u, B, n3), wk.scratch, beta=0.0, bbeta=0.0, acc=A1(1))
+    dh, dsa = D.fusion_bwd(ddm, u, n3, tag)
+    D.fc1.wgrad(rows(dh, B, n3), rows(sa, B, n3), wk.scratch, beta=0.0, bbeta=0.0, acc=A1(128))
+    g1 = ss1 = None
+    sva = fw["sva"]
+    if not D.ablated:
+        Alen = D.cfg["audio_length"]
+        ss1 = wk.acc_slot(B)
+        g1 = wk.mat(f"{tag}:aud2", 2 * B, Alen, 1)                 # [audio; v1]: stacked input operand of l1
+        with D.fork():
+            d_a2 = wk.mat(f"{tag}:d_a2", 1, 2 * B, code)
+            ops.copy2d(rows(dsa, B, 2 * B).cols_slice(code, D.F), rows(d_a2, 0, B))
+            ops.copy2d(rows(dsa, 2 * B, n3).cols_slice(code, D.F), rows(d_a2, 0, B), accumulate=True)
+            ops.copy2d(rows(dsa, 0, B).cols_slice(code, D.F), rows(d_a2, B, 2 * B))
+            sv2 = {"q": sva["q2"], "code": None, "X": None}
+            dla = D.audio_bwd(sv2, d_a2, 2 * B, tag, wgrads=False, dX=None)
+            l1 = D.a_layers[0]
+            gv = g1.batch_slice(B, 2 * B)
+            if l1.merged:
+                l1.dgrad(dla[0].batch_slice(B, 2 * B), gv, ws=wk.scratch)
+            else:
+                ops.conv_dgrad_c1(dla[0].batch_slice(B, 2 * B), l1.w, gv.t[B * Alen:], nb=B, Lout=l1.Lout, Cout=l1.Cout,
+                                  k=l1.k, stride=l1.s, pad=l1.p, Lin=l1.Lin)
+            ops.rows_sumsq(gv, B, Alen, ss1)
+            ops.copy2d(Mat.of(audio.reshape(-1), 1, B, Alen) if not isinstance(audio, Mat) else audio.flat_rows(),
+                       Mat(g1.t, 1, B, Alen, Alen))
+    d_s3 = wk.mat(f"{tag}:d_s3", 1, n3, code)
+    ops.copy2d(dsa.cols_slice(0, code), d_s3)
+    svp = fw["svp"]
+    dlp = D.pose_bwd(svp, d_s3, n3, tag, wgrads=False, dX=None)
+    X3 = svp["X"]
+    g0 = wk.mat(f"{tag}:g0", B, T, O)
+    D.s_conv1.dgrad(rows(dlp["conv1"], 0, B), g0, ws=wk.scratch)
+    ss0 = wk.acc_slot(B)
+    ops.rows_sumsq(g0, B, T * O, ss0)
+    D.join()
+    ops.gp_finalize(ss0, ss1, B, gp_out, k0, k1)
+    # v = gamma * kappa * g, written where the layer-1 weight gradients read their input
+    kg = wk.vec(f"{tag}:kg", 2 * B)
+    ops.axpby(k0, None, kg[:B], B, gamma, 0.0)
+    t_sa = wk.mat(f"{tag}:t_sa", 1, B, D.F)
+    main = torch.cuda.current_stream(D.dev)
+    par = D.par
+    # The weight-gradient GEMMs are leaves of the dependency graph: each needs its deltas (ready) and ONE tangent
+    # activation.  They run on their own streams (s_wa: audio, s_w: pose), every launch waiting only for the
+    # tangent layer that produces its input, so they fill the gaps of the (latency-bound) tangent chains.
+    s_ta = D.s_aud if par else main
+    s_wa = D.s_wa if par else main
+    s_wp = D.s_w if par else main
+
+    def after(ev_stream):
+        ev = torch.cuda.Event()
+        ev.record(ev_stream)
+        return ev
+
+    if not D.ablated:
+        ops.axpby(k1, None, kg[B:], B, gamma, 0.0)
+        if par:
+            s_ta.wait_stream(main)
+            s_wa.wait_stream(main)
+        with torch.cuda.stream(s_ta):
+            gv = g1.batch_slice(B, 2 * B)
+            ops.scale_rows(gv, kg[B:], gv, B, Alen)
+            evs = [after(s_ta)]
+            x = gv
+            for i, l in enumerate(D.a_layers):                    # tangent pass in place over the mask copies
+                t = sva["q2"][i].batch_slice(B, 2 * B)
+                l.fwd(x, t, bias=False, ws=wk.scratch, mask=t, mask_mode=ACT_RELU)
+                evs.append(after(s_ta))
+                x = t
+            t_a = wk.mat(f"{tag}:t_a", 1, B, code)
+            D.a_l6.fwd(x, t_a.as_rows(B, 1), bias=False, ws=wk.scratch)
+            ops.copy2d(t_a, t_sa.cols_slice(code, D.F))
+        with torch.cuda.stream(s_wa):
+            # one weight-gradient GEMM per audio layer over the 2B stacked entries; biases from the Wasserstein half
+            x = g1
+            ws_a = wk.scratch                                      # per-stream scratch (Workspace.scratch)
+            for i, l in enumerate(D.a_layers):
+                ops.colsum(dla[i].batch_slice(0, B).flat_rows(), l.gb, A1(l.Cout), scale=1.0, beta=0.0)
+                if par:
+                    s_wa.wait_event(evs[i])
+                l.wgrad(dla[i], x, ws_a, scale=1.0, beta=0.0, bias=False)
+                x = sva["q2"][i]
+            ops.colsum(rows(d_a2, 0, B), D.a_l6.gb, A1(D.a_l6.Cout), scale=1.0, beta=0.0)
+            if par:
+                s_wa.wait_event(evs[len(D.a_layers)])
+            D.a_l6.wgrad(d_a2.as_rows(2 * B, 1), x, ws_a, scale=1.0, beta=0.0, bias=False)
+    # pose branch: tangent in place on the current stream, weight gradients over all 3B entries on s_w
+    Xi = rows(X3, 0, B)
+    ops.scale_rows(g0, kg[:B], Xi, B, T * O)                       # interpolates are no longer needed: X3[0:B] = v0
+    if par:
+        s_wp.wait_stream(main)
+    sp = slice_pose_saves(svp, 0, B)
+    pending = []                                                   # (conv, deltas, input operand, event)
+
+    def wg(conv, dl, x_in, ev):
+        pending.append((conv, dl, x_in, ev))
+
+    wg(D.s_conv1, dlp["conv1"], X3, after(main))
+    t0 = sp["r0"]
+    D.s_conv1.fwd(Xi, t0, bias=False, ws=wk.scratch, mask=t0, mask_mode=ACT_RELU)
+    ev = after(main)
+    x = t0
+    for b, (c1, c2) in enumerate(D.s_blocks):
+        x_fw, r1_fw, r2_fw, y_fw = svp["blk"][b]
+        _, r1, r2, y = sp["blk"][b]
+        wg(c1, dlp[f"b{b}c1"], x_fw, ev)
+        c1.fwd(x, r1, bias=False, ws=wk.scratch, mask=r1, mask_mode=ACT_RELU)
+        ev = after(main)
+        wg(c2, dlp[f"b{b}c2"], r1_fw, ev)
+        c2.fwd(r1, y, bias=False, ws=wk.scratch, mask=r2, mask_mode=ACT_RELU, add=x)
+        ev = after(main)
+        x = y
+    wg(D.s_fconv, d_s3.as_rows(n3, 1), svp["y"], ev)
+    t_s = wk.mat(f"{tag}:t_s", 1, B, code)
+    D.s_fconv.fwd(x, t_s.as_rows(B, 1), bias=False, ws=wk.scratch)
+    ops.copy2d(t_s, t_sa.cols_slice(0, code))
+    with torch.cuda.stream(s_wp):
+        ws_p = wk.scratch
+        for conv, dl, x_in, ev in pending:
+            dlr = dl if conv is D.s_fconv else rows(dl, B, n3).flat_rows()
+            ops.colsum(rows(d_s3, B, n3) if conv is D.s_fconv else dlr, conv.gb, A1(conv.Cout), scale=1.0, beta=0.0)
+            if par:
+                s_wp.wait_event(ev)
+            conv.wgrad(dl, x_in, ws_p, scale=1.0, beta=0.0, bias=False)
+    if par and not D.ablated:
+        main.wait_stream(s_ta)
+    # fusion MLP: penalty part through the tangent of the codes
+    t_h = wk.mat(f"{tag}:t_h", 1, B, 128)
+    D.fc1.fwd(t_sa, t_h, bias=False, ws=wk.scratch, mask=rows(u, 0, B), mask_mode=ACT_RELU)
+    ops.colsum(t_h, D.fc2.gw, A1(128), scale=1.0, beta=1.0)
+    D.fc1.wgrad(rows(dh, 0, B), t_sa, wk.scratch, scale=1.0, beta=1.0, bias=False)
+    if par:
+        if not D.ablated:
+            main.wait_stream(s_wa)
+        main.wait_stream(s_wp)
 
 
 def wasserstein_backward(D, fw, r0, nR, signs, B, tag, beta, dX_rows=None, dX=None, param_grads=True):
