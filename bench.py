@@ -417,8 +417,8 @@ def run_b200(args):
         kt.install()
         saved_flag = tr.use_graphs
         tr.use_graphs = False
-        saved_ov = (tr.overlap, tr.D.par)
-        tr.overlap, tr.D.par = False, False             # one stream: every launch is timed alone
+        saved_ov = (tr.overlap, tr.D.par, tr.G.par)
+        tr.overlap, tr.D.par, tr.G.par = False, False, False   # one stream: every launch is timed alone
         tr.load_batches(*devs[0])
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(dev)
@@ -433,7 +433,7 @@ def run_b200(args):
         torch.cuda.synchronize(dev)
         eager_ms = e0.elapsed_time(e1)
         tr.use_graphs = saved_flag
-        tr.overlap, tr.D.par = saved_ov
+        tr.overlap, tr.D.par, tr.G.par = saved_ov
         kt.remove()
         fams = kt.summary()
         top = max(fams, key=lambda f: fams[f]["ms"])

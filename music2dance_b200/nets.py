@@ -587,6 +587,8 @@ class GeneratorNet:
         self.wk = Workspace(self.dev)
         self.nbt = [v for k, v in P.items() if k.endswith("num_batches_tracked")]
         self.nbt_flat = P.get("__nbt_flat__")
+        self.par = os.environ.get("M2D_OVERLAP", "1") != "0"
+        self.s_noise = torch.cuda.Stream(device=self.dev) if self.par else None
 
     def convs(self):
         c = self.enc.convs() + self.rnn.convs() + self.nrnn.convs() + [self.fc1, self.last]
@@ -618,11 +620,21 @@ class GeneratorNet:
             src, win = audio, (T, w[1], w[2], audio.shape[-1], w[4])
         self.src, self.win, self.B, self.T = src, win, B, T
         enc_out = wk.mat("g:enc", nb, 1, self.I)
-        self.enc.fwd(src, nb, win, wk, train, enc_out)
         z = wk.mat("g:z", 1, nb, self.Lat)
-        self.rnn.fwd(enc_out.as_rows(1, nb), z.cols_slice(0, self.H), B, T, wk, save=True)
         nz = Mat.of(noise, 1, nb, self.Nz)
-        self.nrnn.fwd(nz, z.cols_slice(self.H, self.Lat), B, T, wk, save=True)
+        # the noise GRU (120 dependent steps on B CTAs) only meets the audio path at the decoder input: side stream
+        side = self.s_noise if self.par else None
+        cur = torch.cuda.current_stream(self.dev)
+        if side is not None:
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self.nrnn.fwd(nz, z.cols_slice(self.H, self.Lat), B, T, wk, save=True)
+        self.enc.fwd(src, nb, win, wk, train, enc_out)
+        self.rnn.fwd(enc_out.as_rows(1, nb), z.cols_slice(0, self.H), B, T, wk, save=True)
+        if side is not None:
+            cur.wait_stream(side)
+        else:
+            self.nrnn.fwd(nz, z.cols_slice(self.H, self.Lat), B, T, wk, save=True)
         c = wk.mat("g:dec_c0", 1, nb, self.S)
         self.fc1.fwd(z, c, ws=wk.scratch)
         d = wk.mat("g:dec_d0", 1, nb, self.S)

@@ -179,9 +179,7 @@ def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f"):
     ops.fill(dd[2 * B:], B, 1.0 / B)
     ddm = Mat(dd, 1, n3, 1)
     u, sa = fw["u"], fw["sa"]
-    D.fc2.wgrad(rows(ddm, B, n3), rows(u, B, n3), wk.scratch, beta=0.0, bbeta=0.0, acc=A1(1))
-    dh, dsa = D.fusion_bwd(ddm, u, n3, tag)
-    D.fc1.wgrad(rows(dh, B, n3), rows(sa, B, n3), wk.scratch, beta=0.0, bbeta=0.0, acc=A1(128))
+    dh, dsa = D.fusion_bwd(ddm, u, n3, tag)                       # the branches' upstreams first: they start at once
     g1 = ss1 = None
     sva = fw["sva"]
     if not D.ablated:
@@ -209,6 +207,8 @@ def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f"):
     ops.copy2d(dsa.cols_slice(0, code), d_s3)
     svp = fw["svp"]
     dlp = D.pose_bwd(svp, d_s3, n3, tag, wgrads=False, dX=None)
+    D.fc2.wgrad(rows(ddm, B, n3), rows(u, B, n3), wk.scratch, beta=0.0, bbeta=0.0, acc=A1(1))
+    D.fc1.wgrad(rows(dh, B, n3), rows(sa, B, n3), wk.scratch, beta=0.0, bbeta=0.0, acc=A1(128))
     X3 = svp["X"]
     g0 = wk.mat(f"{tag}:g0", B, T, O)
     D.s_conv1.dgrad(rows(dlp["conv1"], 0, B), g0, ws=wk.scratch)
