@@ -280,7 +280,7 @@ def run_b200(args):
         ge.build()
     if world > 1:
         dist.barrier()
-    from oracle import phase3_oracle as O          # configuration + synthetic-data generator only
+    from music2dance_b200 import config as O       # configuration + synthetic inputs (the product arm never imports oracle/)
     from music2dance_b200 import ops
     from music2dance_b200.archis.default import SequenceDiscriminator, SequenceGenerator
     from music2dance_b200.trainer import Phase3Trainer

@@ -67,3 +67,15 @@ def test_cpu_inputs_fail_loudly():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):
             utils.slice_audio_batch(torch.zeros(2, 6400), 3200, 640, 2560)
+
+
+def test_product_config_matches_oracle_config():
+    """music2dance_b200/config.py (product side: bench.py, tools/) restates the same default.yaml constants and
+    synthetic inputs as the oracle's; the product never imports oracle/, so the two are pinned to each other here."""
+    import torch
+    from music2dance_b200 import config as C
+    from oracle import phase3_oracle as O
+    for over in ({}, {"enc_type": "wavegan"}, {"ablated": True, "activ": "tanh"}):
+        assert C.make_cfg(**over) == O.make_cfg(**over)
+    a, b = C.synthetic_batch(C.make_cfg(), 2, 5), O.synthetic_batch(O.make_cfg(), 2, 5)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))

@@ -11,7 +11,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import phase3_oracle as O                                                        # noqa: E402
+from music2dance_b200 import config as O                                                    # noqa: E402
 from music2dance_b200.archis.default import SequenceDiscriminator, SequenceGenerator       # noqa: E402
 from music2dance_b200.trainer import Phase3Trainer                                          # noqa: E402
 
