@@ -5,6 +5,7 @@
 // Data layout: channels-last row matrices (see include/m2d.h).  Tiling: 256 threads
 // per CTA, BM x 64 output tile, K-steps of 16, register micro-tile (BM/16) x 4,
 // double-buffered shared memory with register prefetch.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace m2d {
@@ -222,6 +223,109 @@ __global__ void rowconv_splitk_epilogue(const m2d_rowconv_args a, const int M, c
         int n = (int)(idx - (long long)m * a.N);
         epi_store(a, m, n, v);
     }
+}
+
+// split-K epilogue for few outputs and many splits (weight-streaming layers at small batch: 7 x 100 outputs from
+// 148 partials): one WARP per output, lanes stride over the splits, fixed-order shuffle tree (deterministic)
+__global__ void rowconv_splitk_epilogue_warp(const m2d_rowconv_args a, const int M, const int splits) {
+    const long long total = (long long)M * a.N;
+    const int lane = threadIdx.x & 31;
+    const long long idx = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    if (idx >= total) return;
+    float s = 0.f;
+    for (int z = lane; z < splits; z += 32) s += a.ws[(long long)z * total + idx];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        const int m = (int)(idx / a.N);
+        epi_store(a, m, (int)(idx - (long long)m * a.N), s);
+    }
+}
+
+// Skinny GEMM: a handful of rows (M <= MR) against a long contraction whose operands are both K-contiguous
+// (audio_d.l6 / stick_d.fconv as Linear over (tap, channel), their tangent passes, at the reference batch):
+// pure weight streaming.  grid.x = K splits over the whole chip; a CTA stages its K chunk of the M activation rows
+// in shared memory, each warp takes output columns n = warp, warp + 8, ..., its lanes stride over the chunk with
+// 16-byte loads of the weight row (coalesced) and keep M partial dot products in registers; warp-shuffle reduce,
+// partials [split][m][n] to the workspace, then the warp-per-output epilogue.
+template <int MR>
+__global__ void __launch_bounds__(NT)
+skinny_gemm_kernel(const m2d_rowconv_args a, const int M, const long long K, const int KC) {
+    extern __shared__ float As[];                       // [MR][KC]
+    const long long k0 = (long long)blockIdx.x * KC;
+    const int kc = (int)min((long long)KC, K - k0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int idx = tid; idx < MR * (KC / 4); idx += NT) {
+        const int m = idx / (KC / 4), k4 = (idx - m * (KC / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < M && k4 < kc) {
+            const int b = m / a.y_rows, i = m - b * a.y_rows;
+            v = __ldg(reinterpret_cast<const float4*>(a.x + (long long)b * a.x_bs +
+                                                      (long long)(i * a.sr + a.roff0) * a.x_ld + k0 + k4));
+        }
+        *reinterpret_cast<float4*>(As + m * KC + k4) = v;
+    }
+    __syncthreads();
+    float* part = a.ws + (long long)blockIdx.x * M * a.N;
+    constexpr int NU = MR <= 8 ? 4 : 2;                 // weight rows in flight per warp (independent 16-byte loads)
+    for (int nb = warp * NU; nb < a.N; nb += (NT / 32) * NU) {
+        float acc[NU][MR];
+#pragma unroll
+        for (int u = 0; u < NU; ++u)
+#pragma unroll
+            for (int m = 0; m < MR; ++m) acc[u][m] = 0.f;
+        for (int k4 = lane * 4; k4 < kc; k4 += 128) {
+            float4 w4[NU];
+#pragma unroll
+            for (int u = 0; u < NU; ++u)
+                w4[u] = nb + u < a.N ? __ldg(reinterpret_cast<const float4*>(a.w + (long long)(nb + u) * a.w_ld + k0 + k4))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int m = 0; m < MR; ++m) {
+                const float4 x4 = *reinterpret_cast<const float4*>(As + m * KC + k4);
+#pragma unroll
+                for (int u = 0; u < NU; ++u)
+                    acc[u][m] = fmaf(x4.x, w4[u].x, fmaf(x4.y, w4[u].y, fmaf(x4.z, w4[u].z, fmaf(x4.w, w4[u].w, acc[u][m]))));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NU; ++u)
+#pragma unroll
+            for (int m = 0; m < MR; ++m) {
+                float s = acc[u][m];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0 && m < M && nb + u < a.N) part[(long long)m * a.N + nb + u] = s;
+            }
+    }
+}
+
+// Returns 1 if the shape is not a skinny K-contiguous GEMM (caller continues with the tiled kernels).
+static int skinny_dispatch(const m2d_rowconv_args& a, int M, cudaStream_t st) {
+    static const bool enabled = !(getenv("M2D_SKINNY") && getenv("M2D_SKINNY")[0] == '0');
+    if (!enabled) return 1;
+    const long long K = (long long)a.T * a.Cc;
+    if (M > 16 || K < 2048 || a.win_T > 0 || a.Cc == 1 || !a.ws || a.droff != 1) return 1;
+    // both operands contiguous along K: single tap, or a full-length convolution over dense rows
+    const bool kcontig = a.T == 1 || (a.x_ld == a.Cc && a.y_rows == 1 && a.roff0 == 0 && a.x_rows >= a.T);
+    if (!kcontig || a.T * a.Cc > a.w_ld || K % 4 || a.x_ld % 4 || a.x_bs % 4 || a.w_ld % 4 || !aligned16(a.x) ||
+        !aligned16(a.w))
+        return 1;
+    if (a.T == 1 && (a.roff0 < 0 || (a.y_rows - 1) * a.sr + a.roff0 >= a.x_rows)) return 1;
+    int splits = kNumSMs;
+    long long KC = (cdiv(K, splits) + 3) / 4 * 4;
+    if (KC < 128) KC = 128;
+    splits = (int)cdiv(K, KC);
+    const int MR = M <= 8 ? 8 : 16;
+    if (a.ws_floats < (long long)splits * M * a.N || MR * KC * 4 > 48 * 1024) return 1;
+    const int smem = (int)(MR * KC * 4);
+    if (MR == 8) skinny_gemm_kernel<8><<<splits, NT, smem, st>>>(a, M, K, (int)KC);
+    else skinny_gemm_kernel<16><<<splits, NT, smem, st>>>(a, M, K, (int)KC);
+    int rc = check_launch("skinny_gemm");
+    if (rc) return rc;
+    const long long threads = (long long)M * a.N * 32;
+    rowconv_splitk_epilogue_warp<<<(unsigned)cdiv(threads, 256), 256, 0, st>>>(a, M, splits);
+    return check_launch("rowconv_splitk_epilogue_warp");
 }
 
 template <int BM, bool VEC, bool C1>
@@ -588,6 +692,10 @@ extern "C" int m2d_rowconv(const m2d_rowconv_args* ap, void* stream) {
     }
     if (mode != M2D_GEMM_FP32) {
         int rc = rowconv_tc_dispatch(a, M, mode, st);
+        if (rc <= 0) return rc;
+    }
+    {   // a handful of rows against a long K-contiguous contraction: weight streaming over the whole chip
+        int rc = skinny_dispatch(a, M, st);
         if (rc <= 0) return rc;
     }
     const bool c1 = a.Cc == 1;

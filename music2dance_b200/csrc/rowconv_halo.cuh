@@ -280,9 +280,9 @@ rowconv_halo_kernel(const m2d_rowconv_args a, const HaloPlan plan, const int tpb
     int row_lo = 0, row_hi = TC_BM;
     if (Z > 1) {
         cluster_sync_all();
-        const int RB = TC_BM / Z;
+        const int RB = (TC_BM + Z - 1) / Z;              // any cluster size 2..8, not only powers of two
         row_lo = (int)cluster_rank() * RB;
-        row_hi = row_lo + RB;
+        row_hi = min(TC_BM, row_lo + RB);
     }
     const bool vy = vecN && (a.y_ld & 3) == 0 && (a.y_bs & 3) == 0 && aligned16d(a.y) &&
                     (!a.y2 || aligned16d(a.y2)) &&
@@ -416,7 +416,7 @@ static int launch_halo(const m2d_rowconv_args& a, const HaloPlan& plan, int tpb,
                        int NA, int NB, int brows, const CUtensorMap* mx) {
     auto kern = rowconv_halo_kernel<NS, TRACE>;
     static bool configured = false;
-    static int zmax = 1;
+    static int zok[9] = {0};                            // max co-resident clusters of size z (queried once; 0: not schedulable)
     const int smem_max = HL_SMEM_BUDGET + 1024;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
@@ -424,12 +424,36 @@ static int launch_halo(const m2d_rowconv_args& a, const HaloPlan& plan, int tpb,
             set_error("rowconv_halo: smem attribute (%d B): %s", smem_max, cudaGetErrorString(e));
             return M2D_ERR_CUDA;
         }
-        zmax = max_cluster_z(kern, smem_max, 8, false, HL_THREADS);
+        zok[1] = kNumSMs;
+        for (int z = 2; z <= 8; ++z) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(1, 1, (unsigned)z);
+            cfg.blockDim = dim3(HL_THREADS);
+            cfg.dynamicSmemBytes = (size_t)smem_max;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 1;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = (unsigned)z;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            int n = 0;
+            zok[z] = (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) ? n : 0;
+            (void)cudaGetLastError();
+        }
         configured = true;
     }
     const int smem = NA * HL_A_STAGE + NB * 2 * brows * 128 + 1024;
-    int Z = 1;
-    while (Z * 2 <= want_splits && Z * 2 <= zmax) Z *= 2;
+    // largest cluster size <= want_splits whose clusters are all co-resident (odd sizes fragment the GPCs: fewer
+    // clusters fit than SMs / z); if none fits in one wave, the largest schedulable size
+    const long long clusters = (long long)a.nb * tpb * cdiv(a.N, TC_BNMAX);
+    int Z = want_splits < 8 ? want_splits : 8;
+    while (Z > 1 && !(zok[Z] > 0 && clusters <= zok[Z])) --Z;
+    if (Z < 1) Z = 1;
+    if (Z == 1 && want_splits > 1) {
+        Z = want_splits < 8 ? want_splits : 8;
+        while (Z > 1 && !zok[Z]) --Z;
+    }
     dim3 grid((unsigned)(a.nb * tpb), (unsigned)cdiv(a.N, TC_BNMAX), (unsigned)Z);
     // bring-up trace: 16 counters per CTA into the caller's workspace (see tools/halo_probe.py trace)
     long long* trace = nullptr;

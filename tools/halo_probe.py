@@ -109,6 +109,32 @@ def timing(mode):
                   f"  halo={nh // 3}", flush=True)
 
 
+def full(mode):
+    """Full-length convolutions at the reference batch (weight streaming): audio_d.l6 and stick_d.fconv forward."""
+    ops.set_gemm_mode(mode)
+    ws = torch.empty(1 << 24, device=DEV)
+    flush = torch.empty(64 << 20, device=DEV)
+    for name, (Cin, Cout, k, B) in [("audio_d.l6 B7", (512, 100, 75, 7)), ("stick_d.fconv 3B=21", (128, 100, 120, 21)),
+                                    ("audio_d.l6 B14", (512, 100, 75, 14))]:
+        lay, w, b = layer(Cin, Cout, k, 1, 0, k)
+        X = Mat.of(torch.randn(B, k, Cin, device=DEV), B, k, Cin)
+        Y = Mat.of(torch.empty(B, 1, Cout, device=DEV), B, 1, Cout)
+        for flushed in (True, False):
+            ts = []
+            for _ in range(12):
+                if flushed:
+                    flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                lay.fwd(X, Y, act=0, ws=ws)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1) * 1e3)
+            ts.sort()
+            print(f"{name:22s} fwd {mode} {'L2 flushed' if flushed else 'L2 warm   '}: median {ts[6]:7.1f} us  min {ts[0]:7.1f} us"
+                  f"  ({Cout * k * Cin * 4 / ts[6] * 1e-3:6.1f} GB/s of weights)", flush=True)
+
+
 def prof(mode):
     """Two forward launches per shape (the second one is the one to read) for `ncu -k regex:rowconv_halo`."""
     ops.set_gemm_mode(mode)
@@ -148,4 +174,4 @@ def trace(mode):
 
 
 if __name__ == "__main__":
-    {"check": check, "timing": timing, "prof": prof, "trace": trace}[sys.argv[1]](sys.argv[2] if len(sys.argv) > 2 else "tf32x3")
+    {"check": check, "timing": timing, "prof": prof, "trace": trace, "full": full}[sys.argv[1]](sys.argv[2] if len(sys.argv) > 2 else "tf32x3")
