@@ -769,20 +769,36 @@ class CriticNet:
         the forward reaches last (audio_d.l5 / l6 = 68 % of the critic's parameters) are re-laid out on a side
         stream and audio_fwd waits for them right before l5, so most of the re-layout overlaps the first
         convolutions of the next iteration instead of sitting between Adam and the forward."""
-        if not (split and self.par and not self.ablated):
+        if not (split and self.can_split_pack()):
             _pack_net(self)
             return
+        self.pack_late_fork()
+        self.pack_early()
+
+    def can_split_pack(self):
+        return self.par and not self.ablated
+
+    def _split_tabs(self):
         if getattr(self, "_pack_tabs", None) is None:
             late = [self.a_layers[4], self.a_l6]
             early = [c for c in self.convs() if c not in late]
             mk = lambda cs: ops.pack_table([e for c in cs for e in c.pack_entries()], self.dev)
             self._pack_tabs = (mk(early), mk(late))
             self.s_pack = torch.cuda.Stream(device=self.dev)
+        return self._pack_tabs
+
+    def pack_early(self):
+        """Re-layout of everything but audio_d.l5 / l6 on the current stream."""
+        ops.pack_batch(*self._split_tabs()[0])
+
+    def pack_late_fork(self):
+        """Re-layout of audio_d.l5 / l6 on the side stream, ordered after the current stream (the optimiser step
+        that produced the weights); the next audio_fwd joins it right before l5."""
+        tabs = self._split_tabs()
         cur = torch.cuda.current_stream(self.dev)
-        self.s_pack.wait_stream(cur)                         # the optimiser step that produced the new weights
+        self.s_pack.wait_stream(cur)
         with torch.cuda.stream(self.s_pack):
-            ops.pack_batch(*self._pack_tabs[1])
-        ops.pack_batch(*self._pack_tabs[0])
+            ops.pack_batch(*tabs[1])
         self._late_pack = True
 
     def unpack_grads(self):

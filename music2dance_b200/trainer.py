@@ -32,7 +32,7 @@ LOG_GEN = ("loss_gen", "l1", "tv", "err_real", "err_fake")
 
 
 class Phase3Trainer:
-    def __init__(self, gen, critic, cfg, batch_size, use_graphs=True, process_group=None):
+    def __init__(self, gen, critic, cfg, batch_size, use_graphs=True, process_group=None, per_iteration_graphs=False):
         dev = next(gen.parameters()).device
         assert dev.type == "cuda", "Phase3Trainer needs the modules on a CUDA device"
         self.dev, self.cfg, self.B = dev, cfg, batch_size
@@ -49,6 +49,9 @@ class Phase3Trainer:
         self.ge.packed_version, self.de.packed_version = self.ge.fp.version(), self.de.fp.version()
         self.pg = process_group
         self.world = dp.world_size(process_group)
+        # multi-GPU runs replay one graph per critic iteration (the all-reduce sits between graphs); the flag selects
+        # that structure on a single GPU too (tests exercise it without a second device)
+        self.per_iter = per_iteration_graphs or self.world > 1
         B, T, O, A, Nz, nc = self.B, self.T, self.O, self.A, self.Nz, self.nc
         f = dict(dtype=torch.float32, device=dev)
         # staged inputs of one train step (device resident)
@@ -88,7 +91,7 @@ class Phase3Trainer:
         n = eng.fp.n_live_padded
         self._all_reduce(eng.fp.grad[:n])
         ops.adam(eng.fp.flat, eng.fp.grad, m, v, n, step, float(lr), gscale=1.0 / self.world)
-        if eng is self.de and self.world == 1 and self.overlap and self.split_pack:
+        if eng is self.de and not self.per_iter and self.overlap and self.split_pack:
             eng.net.pack(split=True)          # big late layers re-laid out next to the next iteration's first convolutions
         else:
             eng.net.pack()
@@ -187,11 +190,13 @@ class Phase3Trainer:
         """Warm up once eagerly (allocates every workspace buffer), then capture the step
         in CUDA graphs; model / optimiser state is restored afterwards."""
         saved = [t.clone() for t in self._state()]
+        if self.D.can_split_pack():
+            self.D._split_tabs()                 # device tables of the split re-layout: built outside capture
         torch.cuda.synchronize(self.dev)
         self._run_eager()
         torch.cuda.synchronize(self.dev)
         graphs = []
-        if self.world == 1:
+        if not self.per_iter:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._run_eager()
@@ -206,11 +211,17 @@ class Phase3Trainer:
                     fn()
                 return g
 
+            # critic re-layout split across graphs: the Adam graph refreshes everything but audio_d.l5 / l6, the NEXT
+            # graph that evaluates the critic forks their re-layout at its start (joined before l5 by audio_fwd)
+            split = self.overlap and self.split_pack and self.D.can_split_pack()
+
             def critic_and_next_forward(i):
                 if not self.overlap:
                     self.critic_iteration(i, update=False)
                     return
                 main = torch.cuda.current_stream()
+                if split and i > 0:
+                    self.D.pack_late_fork()
                 self.s_gen.wait_stream(main)
                 with torch.cuda.stream(self.s_gen):
                     if i + 1 < self.nc:
@@ -223,7 +234,10 @@ class Phase3Trainer:
             def adam_d():
                 ops.adam(self.de.fp.flat, self.de.fp.grad, self.mD, self.vD, self.de.fp.n_live_padded,
                          self.stepD, float(self.cfg["lr_critic"]), gscale=1.0 / self.world)
-                self.de.net.pack()
+                if split:
+                    self.D.pack_early()
+                else:
+                    self.de.net.pack()
 
             def adam_g():
                 ops.adam(self.ge.fp.flat, self.ge.fp.grad, self.mG, self.vG, self.ge.fp.n_live_padded,
@@ -235,7 +249,12 @@ class Phase3Trainer:
             for i in range(self.nc):
                 graphs.append(("c", cap(lambda i=i: critic_and_next_forward(i))))
                 graphs.append(("cu", cap(adam_d)))
-            graphs.append(("g", cap(lambda: self.generator_update(update=False, gen_inline=not self.overlap))))
+            def gen_update():
+                if split:
+                    self.D.pack_late_fork()                  # weights of the last critic Adam step
+                self.generator_update(update=False, gen_inline=not self.overlap)
+
+            graphs.append(("g", cap(gen_update)))
             graphs.append(("gu", cap(adam_g)))
         torch.cuda.synchronize(self.dev)
         with torch.no_grad():
@@ -247,7 +266,7 @@ class Phase3Trainer:
         self.graphs = graphs
 
     def _run_eager(self):
-        if not self.overlap or self.world > 1:
+        if not self.overlap or self.per_iter:
             for i in range(self.nc):
                 self.critic_iteration(i)
             self.generator_update()

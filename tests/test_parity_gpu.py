@@ -232,6 +232,31 @@ def test_fused_trainer_vs_oracle(variant, B, nc, graphs):
                 assert float(d.mean()) < TOL_DRIFT_LR * lr * steps + 1e-6 * float(P[k].abs().max()), (k, float(d.mean()))
 
 
+def test_per_iteration_graphs_match_single_graph():
+    """The multi-GPU step structure (one CUDA graph per critic iteration, optimiser / re-layout graphs in between,
+    generator forwards pipelined one iteration ahead, audio_d.l5 / l6 re-layout forked into the next graph) run on ONE
+    GPU must reproduce the single-graph step: same kernels, same order per stream -> same losses to fp32 noise."""
+    from music2dance_b200.trainer import Phase3Trainer
+    cfg = O.make_cfg(n_critic_steps=3)
+    B = 2
+    logs = []
+    for per_iter in (False, True):
+        gen, critic = build(cfg)
+        tr = Phase3Trainer(gen, critic, cfg, B, use_graphs=True, per_iteration_graphs=per_iter)
+        out = []
+        for step in range(3):
+            bs = [O.synthetic_batch(cfg, B, 7000 + step * 3 + i) for i in range(3)]
+            tr.load_batches(*[torch.stack([b[j] for b in bs]) for j in range(4)], bs[-1][4])
+            tr.train_step()
+            out.append(tr.logs())
+        logs.append(out)
+    for a, b in zip(*logs):
+        for ca, cb in zip(a["critic"], b["critic"]):
+            for k in ("loss_critic", "gp", "w_dist"):
+                scalar_check(cb[k], ca[k], 1e-3, f"per-iteration graphs {k}")
+        scalar_check(b["gen"]["loss_gen"], a["gen"]["loss_gen"], 1e-3, "per-iteration graphs loss_gen")
+
+
 def test_critic_batch_additivity():
     """Data-parallel property (no BatchNorm in the critic): the critic gradients of a batch
     equal the mean of the gradients of its two halves — what the all-reduce relies on."""
