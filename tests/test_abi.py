@@ -79,3 +79,42 @@ def test_product_config_matches_oracle_config():
         assert C.make_cfg(**over) == O.make_cfg(**over)
     a, b = C.synthetic_batch(C.make_cfg(), 2, 5), O.synthetic_batch(O.make_cfg(), 2, 5)
     assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_error_convention_without_gpu():
+    """Argument validation happens before any CUDA call: bad arguments return a negative m2d_status and leave a
+    message in m2d_last_error() (no exception crosses the C boundary, nothing is launched) — checkable on a CPU box."""
+    import ctypes as C
+    import __graft_entry__ as ge
+    from music2dance_b200 import _lib
+    ge.build()
+    lib = _lib.load()
+    a = _lib.RowConvArgs()                                  # all pointers NULL
+    rc = lib.m2d_rowconv(C.byref(a), None)
+    assert rc == -1 and b"null pointer" in lib.m2d_last_error()          # M2D_ERR_BAD_ARG
+    w = _lib.WgradArgs()
+    assert lib.m2d_wgrad(C.byref(w), None) == -1 and b"wgrad" in lib.m2d_last_error()
+    assert lib.m2d_crop_batch(None, None, None, None, None, None, 1, 120, 69, 640, 76800, None, None, None) == -1
+    assert lib.m2d_jerkiness(None, 1, 3, 69, None, None) == -1           # needs T > 3
+    assert b"jerkiness" in lib.m2d_last_error()
+    assert lib.m2d_adam(None, None, None, None, 0, None, 1e-3, 0.9, 0.999, 1e-8, 1.0, None) == -1
+    with __import__("pytest").raises(RuntimeError, match="libm2d_b200"):
+        _lib.call("m2d_gp_finalize_lp", None, 0, None, None, None)        # the Python wrapper raises with the message
+
+
+def test_dropin_modules_refuse_cpu_tensors():
+    """No CPU fallback: the drop-in entry points raise on CPU inputs instead of computing something else."""
+    import pytest
+    import torch
+    from music2dance_b200.losses import gradient_penalty, jerkiness, tv_loss
+    from music2dance_b200.utils import slice_audio_batch
+    x = torch.zeros(2, 69, 120)
+    for fn in (lambda: tv_loss(x), lambda: jerkiness(x),
+               lambda: gradient_penalty(None, 2, x, x, x, is_seq=True, lp=False)):
+        with pytest.raises(RuntimeError, match="CUDA"):
+            fn()
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            slice_audio_batch(torch.zeros(2, 76800), 3200, 640, 2560)
+    with pytest.raises(NotImplementedError):
+        gradient_penalty(None, 2, x, x, is_seq=False)                      # phase1 branch lives in phase1.Phase1Trainer

@@ -1,13 +1,11 @@
 #!/bin/bash
-# quick validation: kernel-level tests, parity suite, one bench line
+# fused-trainer parity tests + one bench line per batch size
 set -u
 mkdir -p gpurun_out
-python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
-timeout 900 python -m pytest tests/test_ops_gpu.py -q -x 2>&1 | tail -n 12 > gpurun_out/pytest_ops.log
-timeout 1200 python -m pytest tests/test_parity_gpu.py -q 2>&1 | grep -E "^E  .*Error|^FAILED|passed|failed" > gpurun_out/pytest_parity.log
+timeout 900 python -m pytest tests/test_parity_gpu.py -q -x -k "fused or additivity" 2>&1 | tail -n 4
 timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
 timeout 600 python bench.py --batch 64 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_b64.json 2>> gpurun_out/bench.err
-cat gpurun_out/pytest_ops.log; tail -n 25 gpurun_out/pytest_parity.log; tail -n 3 gpurun_out/bench.err
+tail -n 3 gpurun_out/bench.err
 for f in bench bench_b64; do python - "$f" <<'PY'
 import json,sys
 try:
