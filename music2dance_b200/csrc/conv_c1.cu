@@ -138,6 +138,69 @@ conv_c1_wgrad_finalize(const float* __restrict__ part, int nparts, int n, float*
     }
 }
 
+// Backward-data to the single input channel (the WGAN-GP audio gradient dD/d audio, losses.py:40-44 through
+// audio_d.l1): dx[b, j] = sum_{co, t : 4 i - PAD + t = j} dy[b, i, co] * w[co, t].  One warp per group of 4
+// consecutive samples j = 4m + p: lane = output channel, the lane's 25 taps in registers; the 7 rows i = m - d
+// (d = -3..3) that touch the group are read once (coalesced 128-byte rows, L1 reuse between neighbouring groups)
+// and every tap is used exactly once: t = 4d + p + PAD.  The four sums are reduced over the 32 channels with a
+// folded butterfly (6 shuffles for 4 values) and written as one 16-byte segment.
+template <int T, int PAD>
+__global__ void __launch_bounds__(256)
+conv_c1_dgrad4_kernel(const float* __restrict__ dy, const float* __restrict__ w, int w_ld, float* __restrict__ dx,
+                      int Lout, int Lin, long long groups) {
+    const int lane = threadIdx.x & 31;
+    float wr[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) wr[t] = __ldg(w + (long long)lane * w_ld + t);
+    const int gpb = Lin / 4;
+    constexpr int DLO = -((3 + PAD) / 4), DHI = (T - 1 - PAD) >= 0 ? (T - 1 - PAD) / 4 : -1;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long g = warp0; g < groups; g += nwarps) {
+        const int b = (int)(g / gpb), m = (int)(g - (long long)b * gpb);
+        const float* dyb = dy + ((long long)b * Lout) * 32 + lane;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float v[DHI - DLO + 1];
+#pragma unroll
+        for (int d = DLO; d <= DHI; ++d) {                  // all row loads first: independent, in flight together
+            const int i = m - d;
+            v[d - DLO] = (i >= 0 && i < Lout) ? __ldg(dyb + (long long)i * 32) : 0.f;
+        }
+#pragma unroll
+        for (int d = DLO; d <= DHI; ++d)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                constexpr int dummy = 0;
+                const int t = 4 * d + p + PAD;              // compile-time after unrolling
+                if (t >= 0 && t < T) acc[p] = fmaf(v[d - DLO], wr[t], acc[p]);
+                (void)dummy;
+            }
+        // folded reduction over the 32 channels: halves hold outputs {0,1} / {2,3}, then quarters one output each
+        const bool up = lane & 16;
+        float s0 = __shfl_xor_sync(0xffffffffu, up ? acc[0] : acc[2], 16);
+        float s1 = __shfl_xor_sync(0xffffffffu, up ? acc[1] : acc[3], 16);
+        float a = (up ? acc[2] : acc[0]) + s0, c = (up ? acc[3] : acc[1]) + s1;
+        const bool q = lane & 8;
+        float s2 = __shfl_xor_sync(0xffffffffu, q ? a : c, 8);
+        float r = (q ? c : a) + s2;
+        r += __shfl_xor_sync(0xffffffffu, r, 4);
+        r += __shfl_xor_sync(0xffffffffu, r, 2);
+        r += __shfl_xor_sync(0xffffffffu, r, 1);
+        if ((lane & 7) == 0) dx[(long long)b * Lin + 4 * m + 2 * (lane >> 4) + ((lane >> 3) & 1)] = r;
+    }
+}
+
+// Returns 1 if the layer is not of this form.
+int conv_c1_dgrad_dispatch(const float* dy, int nb, int Lout, int Cout, const float* w, int k, int stride, int pad,
+                           float* dx, int Lin, cudaStream_t st) {
+    if (Cout != 32 || k != 25 || stride != 4 || Lin % 4 || (pad != 11 && pad != 0)) return 1;
+    const long long groups = (long long)nb * (Lin / 4);
+    const int blocks = (int)(cdiv(groups, 8) < 16 * kNumSMs ? cdiv(groups, 8) : 16 * kNumSMs);
+    if (pad == 11) conv_c1_dgrad4_kernel<25, 11><<<blocks, 256, 0, st>>>(dy, w, k, dx, Lout, Lin, groups);
+    else conv_c1_dgrad4_kernel<25, 0><<<blocks, 256, 0, st>>>(dy, w, k, dx, Lout, Lin, groups);
+    return check_launch("conv_c1_dgrad4");
+}
+
 template <int T>
 static void launch_fwd(const m2d_rowconv_args& a, int grid, int smem, cudaStream_t st) {
     conv_c1_fwd_kernel<T><<<grid, C1_WARPS * 32, smem, st>>>(a);

@@ -663,6 +663,8 @@ int rowconv_tc_dispatch(const m2d_rowconv_args& a, int M, int mode, cudaStream_t
 int wgrad_tc_dispatch(const m2d_wgrad_args& a, int Ktot, int Ncols, int mode, cudaStream_t st);
 int conv_c1_fwd_dispatch(const m2d_rowconv_args& a, cudaStream_t st);
 int conv_c1_wgrad_dispatch(const m2d_wgrad_args& a, cudaStream_t st);
+int conv_c1_dgrad_dispatch(const float* dy, int nb, int Lout, int Cout, const float* w, int k, int stride, int pad,
+                           float* dx, int Lin, cudaStream_t st);
 int gemm_mode();
 }  // namespace m2d
 
@@ -806,6 +808,10 @@ extern "C" int m2d_conv_dgrad_c1(const float* dy, int nb, int Lout, int Cout, co
                                  int stride, int pad, float* dx, int Lin, void* stream) {
     M2D_REQUIRE(dy && w && dx && nb > 0 && Lout > 0 && Cout > 0 && k > 0 && stride > 0 && Lin > 0,
                 "conv_dgrad_c1: bad args");
+    {   // 32 channels, k = 25, stride 4 (audio_d.l1): one warp per 4 output samples, taps in registers
+        int rc = conv_c1_dgrad_dispatch(dy, nb, Lout, Cout, w, k, stride, pad, dx, Lin, (cudaStream_t)stream);
+        if (rc <= 0) return rc;
+    }
     dim3 grid((unsigned)cdiv(Lin, 256), (unsigned)nb);
     size_t smem = (size_t)k * Cout * sizeof(float);
     M2D_REQUIRE(smem <= 48 * 1024, "conv_dgrad_c1: k*Cout too large");

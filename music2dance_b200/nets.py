@@ -947,15 +947,20 @@ class CriticNet:
             dl[i - 1] = dn
         sv["delta"] = dl
         if dX is not None:
-            l1 = self.a_layers[0]
-            if l1.merged:                                # tensor-core path: N = stride columns per coarse sample
-                l1.dgrad(dl[0], Mat(dX, n, l1.Lin, 1), ws=wk.scratch)
-            else:
-                ops.conv_dgrad_c1(dl[0], l1.w, dX, nb=n, Lout=l1.Lout, Cout=l1.Cout, k=l1.k, stride=l1.s,
-                                  pad=l1.p, Lin=l1.Lin)
+            self.l1_dgrad(dl[0], dX, n)
         if wgrads:
             self.audio_wgrads(dl, sv["X"], sv["q"], scale, beta, bias=True, bbeta=bbeta)
         return dl
+
+    def l1_dgrad(self, d0, dX, n):
+        """Gradient w.r.t. the raw audio (the penalty's g1): d0 Mat [n, Lout, 32] -> dX tensor or Mat [n, A]."""
+        l1, wk = self.a_layers[0], self.wk
+        fast = l1.Cout == 32 and l1.k == 25 and l1.s == 4 and l1.Lin % 4 == 0 and l1.p in (0, 11)
+        if l1.merged and not fast:                       # tensor-core path: N = stride columns per coarse sample
+            l1.dgrad(d0, dX if isinstance(dX, Mat) else Mat(dX, n, l1.Lin, 1), ws=wk.scratch)
+        else:                                            # conv_c1.cu: one warp per 4 samples, taps in registers
+            ops.conv_dgrad_c1(d0, l1.w, dX, nb=n, Lout=l1.Lout, Cout=l1.Cout, k=l1.k, stride=l1.s,
+                              pad=l1.p, Lin=l1.Lin)
 
     def audio_wgrads(self, dl, X, q, scale, beta, bias, bbeta=None):
         wk = self.wk

@@ -193,13 +193,8 @@ def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f"):
             ops.copy2d(rows(dsa, 0, B).cols_slice(code, D.F), rows(d_a2, B, 2 * B))
             sv2 = {"q": sva["q2"], "code": None, "X": None}
             dla = D.audio_bwd(sv2, d_a2, 2 * B, tag, wgrads=False, dX=None)
-            l1 = D.a_layers[0]
             gv = g1.batch_slice(B, 2 * B)
-            if l1.merged:
-                l1.dgrad(dla[0].batch_slice(B, 2 * B), gv, ws=wk.scratch)
-            else:
-                ops.conv_dgrad_c1(dla[0].batch_slice(B, 2 * B), l1.w, gv.t[B * Alen:], nb=B, Lout=l1.Lout, Cout=l1.Cout,
-                                  k=l1.k, stride=l1.s, pad=l1.p, Lin=l1.Lin)
+            D.l1_dgrad(dla[0].batch_slice(B, 2 * B), gv, B)
             ops.rows_sumsq(gv, B, Alen, ss1)
             ops.copy2d(Mat.of(audio.reshape(-1), 1, B, Alen) if not isinstance(audio, Mat) else audio.flat_rows(),
                        Mat(g1.t, 1, B, Alen, Alen))
