@@ -253,6 +253,16 @@ int m2d_crop_batch(const float* poses, const long long* pose_off, const float* m
  * inside losses.py:40-44) */
 int m2d_mul3(const float* a, int lda, const float* b, int ldb, const float* c, int ldc, float* out, int ldo,
              long long M, int C, float alpha, void* stream);
+/* Label conditioning of the phase2 conditional networks (phase2/archis/conditional.py:19-21 generator,
+ * :45-46 critic): nn.Embedding(4,4) lookup + expand over the T rows of a sequence + torch.cat, written directly
+ * into the label columns y[(b*T+t)*ldy + e] of the concatenated channels-last operand; labels are int64 like the
+ * reference's LongTensor.  *err (device int, may be NULL) is set to 1 when a label is outside [0, n_classes)
+ * (the reference raises an index error).  m2d_embed_grad = backward of the lookup:
+ * dtable[c,e] = beta*dtable[c,e] + scale * sum over the rows of the sequences labelled c (deterministic). */
+int m2d_embed_rows(const float* table, const long long* labels, float* y, int ldy, int B, int T, int E,
+                   int n_classes, int* err, void* stream);
+int m2d_embed_grad(const float* dy, int ldd, const long long* labels, float* dtable, int B, int T, int E,
+                   int n_classes, float scale, float beta, void* stream);
 /* MaxPool1d(2,2) and Upsample(x2, linear, align_corners=False) on channels-last rows
  * (default.py:236-237) */
 int m2d_maxpool2(const float* x, int ldx, float* y, int ldy, int nb, int Lin, int C, void* stream);

@@ -94,6 +94,8 @@ SIGNATURES = {
     "m2d_upsample2": [_P, _I, _P, _I, _I, _I, _I, _P],
     "m2d_upsample2_bwd": [_P, _I, _P, _I, _I, _I, _I, _I, _P],
     "m2d_copy2d": [_P, _I, _P, _I, _L, _I, _I, _P],
+    "m2d_embed_rows": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
+    "m2d_embed_grad": [_P, _I, _P, _P, _I, _I, _I, _I, _F, _F, _P],
     "m2d_transpose_bcl": [_P, _P, _I, _I, _I, _P],
     "m2d_wgan_scalars": [_P, _P, _I, _L, _L, _F, _F, _I, _P, _P],
     "m2d_slice_audio": [_P, _P, _I, _I, _I, _I, _I, _I, _P],

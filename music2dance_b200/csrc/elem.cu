@@ -332,6 +332,50 @@ __global__ void mul3_kernel(const float* __restrict__ a, int lda, const float* _
     }
 }
 
+// ---------------------------------------------------------------- label embedding (phase2 conditional)
+// y[(b*T + t)*ldy + e] = table[labels[b]*E + e]: the label code of sequence b broadcast over its T rows
+// (nn.Embedding lookup + unsqueeze + expand + cat of phase2/archis/conditional.py:19-21,45-46 written straight
+// into the concatenated operand's label columns).  err[0] is set if a label is outside [0, n_classes).
+__global__ void embed_rows_kernel(const float* __restrict__ table, const long long* __restrict__ labels, float* y,
+                                  int ldy, int T, int E, int n_classes, long long total, int* err) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int e = (int)(i % E);
+        long long r = i / E;
+        long long lab = labels[r / T];
+        if (lab < 0 || lab >= n_classes) {
+            if (err) *err = 1;
+            y[r * ldy + e] = 0.f;
+        } else {
+            y[r * ldy + e] = table[lab * E + e];
+        }
+    }
+}
+
+// dtable[c, e] = beta * dtable[c, e] + scale * sum_{b: labels[b] == c} sum_t dy[(b*T + t)*ldd + e]
+// (backward of the lookup above).  One CTA per (class, column); fixed-order fp64 tree -> deterministic.
+__global__ void embed_grad_kernel(const float* __restrict__ dy, int ldd, const long long* __restrict__ labels,
+                                  float* dtable, int B, int T, int E, float scale, float beta) {
+    int c = blockIdx.x / E, e = blockIdx.x % E;
+    double acc = 0.0;
+    for (int b = 0; b < B; ++b) {
+        if (labels[b] != c) continue;                      // uniform across the CTA
+        const float* p = dy + (long long)b * T * ldd + e;
+        for (int t = threadIdx.x; t < T; t += blockDim.x) acc += (double)p[(long long)t * ldd];
+    }
+    __shared__ double red[256];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        float* o = dtable + c * E + e;
+        *o = (beta == 0.f ? 0.f : beta * *o) + scale * (float)red[0];
+    }
+}
+
 // ---------------------------------------------------------------- pool / upsample
 __global__ void maxpool2_kernel(const float* __restrict__ x, int ldx, float* y, int ldy, int Lin,
                                 int Lout, int C, long long total) {
@@ -667,6 +711,22 @@ extern "C" int m2d_mul3(const float* a, int lda, const float* b, int ldb, const 
     long long total = M * C;
     mul3_kernel<<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, c, ldc, out, ldo, C, total, alpha);
     return check_launch("mul3");
+}
+
+extern "C" int m2d_embed_rows(const float* table, const long long* labels, float* y, int ldy, int B, int T, int E,
+                              int n_classes, int* err, void* stream) {
+    M2D_REQUIRE(table && labels && y && B > 0 && T > 0 && E > 0 && ldy >= E && n_classes > 0, "embed_rows: bad args");
+    long long total = (long long)B * T * E;
+    embed_rows_kernel<<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(table, labels, y, ldy, T, E, n_classes, total,
+                                                                      err);
+    return check_launch("embed_rows");
+}
+
+extern "C" int m2d_embed_grad(const float* dy, int ldd, const long long* labels, float* dtable, int B, int T, int E,
+                              int n_classes, float scale, float beta, void* stream) {
+    M2D_REQUIRE(dy && labels && dtable && B > 0 && T > 0 && E > 0 && ldd >= E && n_classes > 0, "embed_grad: bad args");
+    embed_grad_kernel<<<n_classes * E, 256, 0, (cudaStream_t)stream>>>(dy, ldd, labels, dtable, B, T, E, scale, beta);
+    return check_launch("embed_grad");
 }
 
 extern "C" int m2d_maxpool2(const float* x, int ldx, float* y, int ldy, int nb, int Lin, int C,

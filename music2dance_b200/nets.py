@@ -821,9 +821,20 @@ class CriticNet:
             c2.fwd(r1, y, act=ACT_RELU, ws=wk.scratch, add=x, y2=r2)
             sv["blk"].append((x, r1, r2, y))
             x = y
+        x = self._drop(x, sv, n, f"{tag}:yd")
         self.s_fconv.fwd(x, code_out.as_rows(n, 1), act=self.act, ws=wk.scratch)
         sv["y"], sv["code"] = x, code_out
         return sv
+
+    def _drop(self, x, sv, n, name):
+        """Hook in front of the full-length convolution: identity here; the phase2 conditional critic applies its
+        Dropout mask (phase2/archis/conditional.py:48)."""
+        return x
+
+    def _fconv_dgrad(self, sv, d_code, n, dc2, e):
+        """e = d/d(last block output), dc2 = e masked by the ReLU of the last block's conv2 — one fused launch."""
+        self.s_fconv.dgrad(d_code.as_rows(n, 1), dc2, ws=self.wk.scratch, y2=e, mask=sv["blk"][-1][2],
+                           mask_mode=ACT_RELU)
 
     def pose_bwd(self, sv, d_code, n, tag, scale=1.0, beta=0.0, wgrads=True, dX=None, bbeta=None, pre_act=False):
         """d_code Mat [1,n,code] = gradient w.r.t. the pose code (post-activ; modified in
@@ -837,9 +848,8 @@ class CriticNet:
         e = wk.mat(f"{tag}:e_top", n, T, Ch)
         nb = len(self.s_blocks)
         # gradient w.r.t. last block output y; masked copy = delta of its conv2
-        x_last, r1_last, r2_last, _ = sv["blk"][-1]
         dc2 = wk.mat(f"{tag}:b{nb - 1}dc2", n, T, Ch)
-        self.s_fconv.dgrad(d_code.as_rows(n, 1), dc2, ws=wk.scratch, y2=e, mask=r2_last, mask_mode=ACT_RELU)
+        self._fconv_dgrad(sv, d_code, n, dc2, e)
         for b in range(nb - 1, -1, -1):
             x, r1, r2, y = sv["blk"][b]
             c1, c2 = self.s_blocks[b]
@@ -896,6 +906,7 @@ class CriticNet:
             tv["blk"].append((x, t1, None, ty))
             x = ty
         m = dict(mask=sv["code"].as_rows(n, 1), mask_mode=self.act) if self.act != ACT_ID else {}
+        x = self._drop(x, sv, n, f"{tag}:tyd")
         self.s_fconv.fwd(x, t_code.as_rows(n, 1), bias=False, ws=wk.scratch, **m)
         tv["y"] = x
         return tv

@@ -318,6 +318,22 @@ def copy2d(x, y, accumulate=False):
     call("m2d_copy2d", x.ptr, x.ld, y.ptr, y.ld, x.M, x.cols, int(accumulate), _stream())
 
 
+def embed_rows(table, labels, y, B, T, n_classes, err=None):
+    """y[(b*T+t), :E] = table[labels[b]] for a Mat `y` that is the label-column slice of a concatenated operand
+    (conditional.py:19-21,45-46); labels int64 on the device."""
+    assert labels.is_cuda and labels.dtype == torch.int64 and labels.is_contiguous() and labels.numel() == B
+    LAUNCHES[0] += 1
+    call("m2d_embed_rows", _p(table), labels.data_ptr(), y.ptr, y.ld, B, T, y.cols, n_classes, _p(err), _stream())
+
+
+def embed_grad(dy, labels, dtable, B, T, n_classes, scale=1.0, beta=0.0):
+    """dtable[c] (+)= scale * sum of the rows of `dy` (label-column slice) belonging to sequences labelled c."""
+    assert labels.is_cuda and labels.dtype == torch.int64 and labels.numel() == B
+    LAUNCHES[0] += 1
+    call("m2d_embed_grad", dy.ptr, dy.ld, labels.data_ptr(), _p(dtable), B, T, dy.cols, n_classes, scale, beta,
+         _stream())
+
+
 def transpose_bcl(x, y, nb, R, Cn):
     """[b, R, C] -> [b, C, R] (dense)."""
     LAUNCHES[0] += 1

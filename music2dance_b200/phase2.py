@@ -130,12 +130,15 @@ def _net_of(module, cls):
 class _GenNet:
     """GRU stack + FrameDecoder (the decoder code mirrors nets.GeneratorNet)."""
 
+    EXTRA_IN = 0                  # columns concatenated to the noise in front of the GRU (conditional: label code)
+
     def __init__(self, module):
         ops.check_device(torch.cuda.current_device())
         self.fp = FlatParams(module)
         P, G = self.fp.P, self.fp.G
         self.dev = self.fp.device
-        self.I, self.H, self.S, self.O = module.input_size, module.latent_size, module.size, module.output_size
+        self.I, self.H, self.S, self.O = module.input_size + self.EXTRA_IN, module.latent_size, module.size, \
+            module.output_size
         S = self.S
         self.rnn = GRUStack(P, G, "noise_gen.rnn", self.I, self.H, module.n_cells)
         self.fc1 = _conv_from(P, G, "decoder.fc1", self.H, S, 1, 1, 0, 1)
@@ -159,11 +162,13 @@ class _GenNet:
             c.pack()
         self.packed_version = self.fp.version()
 
-    def forward(self, noise, B, T, train):
+    def forward(self, noise, B, T, train, mask=None):
+        """noise: tensor (B, T, I) or an already assembled Mat [1, B*T, I]; mask: Mat [1, B*T, S] 0/1 dropout mask in
+        front of ``lastfc`` (phase2/archis/conditional.py:127; None = no dropout)."""
         wk, S, nb = self.wk, self.S, B * T
         wk.acc_reset()
         z = wk.mat("g:z", 1, nb, self.H)
-        self.rnn.fwd(Mat.of(noise, 1, nb, self.I), z, B, T, wk, save=True)
+        self.rnn.fwd(noise if isinstance(noise, Mat) else Mat.of(noise, 1, nb, self.I), z, B, T, wk, save=True)
         c = wk.mat("g:c0", 1, nb, S)
         self.fc1.fwd(z, c, ws=wk.scratch)
         d = wk.mat("g:d0", 1, nb, S)
@@ -182,19 +187,27 @@ class _GenNet:
             self.dec.append((d, cl, r))
             d = dn
         fake = wk.mat("g:fake", 1, nb, self.O)
+        self.mask = mask
+        if mask is not None:
+            hd = wk.mat("g:hd", 1, nb, S)
+            ops.mul3(d, mask, mask, hd, alpha=2.0)                     # x * m / (1 - p): m is 0/1, so m*m = m
+            d = hd
         self.last.fwd(d, fake, ws=wk.scratch)
         self.d_last, self.B, self.T = d, B, T
         if train and self.nbt_flat is not None:
             self.nbt_flat.add_(1)
         return fake
 
-    def backward(self, dfake):
+    def backward(self, dfake, e_x=None):
+        """e_x: optional Mat [1, B*T, I] receiving the gradient w.r.t. the GRU input (label-code columns)."""
         wk, B, T, S = self.wk, self.B, self.T, self.S
         nb = B * T
         wk.acc_reset()
         self.last.wgrad(dfake, self.d_last, wk.scratch, acc=wk.acc_slot(self.O))
         e = wk.mat("g:e", 1, nb, S)
         self.last.dgrad(dfake, e, ws=wk.scratch)
+        if self.mask is not None:
+            ops.mul3(e, self.mask, self.mask, e, alpha=2.0)
         for i in range(len(self.blocks) - 1, -1, -1):
             _, _, live, bnl = self.blocks[i]
             d, cl, r = self.dec[i + 1]
@@ -210,7 +223,7 @@ class _GenNet:
         self.fc1.wgrad(dc, z, wk.scratch, acc=wk.acc_slot(S))
         e_z = wk.mat("g:e_z", 1, nb, self.H)
         self.fc1.dgrad(dc, e_z, ws=wk.scratch)
-        self.rnn.bwd(e_z, B, T, wk)
+        self.rnn.bwd(e_z, B, T, wk, e_x=e_x)
         for cv in self.convs():
             cv.unpack_grad()
 
@@ -219,13 +232,15 @@ class _CriticNet(CriticNet):
     """conv1 + n TemporalBlocks + lastconv = the pose branch of nets.CriticNet with a one-channel code and no
     fusion MLP; inherits pose_fwd / pose_bwd / pose_wgrads / pose_tangent."""
 
+    EXTRA_IN = 0                  # input channels concatenated to the poses (conditional: label code)
+
     def __init__(self, module):                                    # noqa: super().__init__ intentionally not called
         ops.check_device(torch.cuda.current_device())
         self.fp = FlatParams(module)
         P, G = self.fp.P, self.fp.G
         self.dev = self.fp.device
         self.cfg, self.ablated, self.par = {}, True, False
-        Oo, Ch, T = module.channels_in, module.channels_h, module.seqlen
+        Oo, Ch, T = module.channels_in + self.EXTRA_IN, module.channels_h, module.seqlen
         self.O, self.Ch, self.code, self.T = Oo, Ch, 1, T
         k0 = P["conv1.weight"].shape[-1]
         self.s_conv1 = _conv_from(P, G, "conv1", Oo, Ch, k0, 1, (k0 - 1) // 2, T)
@@ -260,10 +275,12 @@ class _CriticNet(CriticNet):
 class Phase2Trainer:
     """Fused phase2 step (phase2/train.py:131-171) on explicit random inputs (noise, alpha)."""
 
+    GEN_NET, CRITIC_NET = _GenNet, _CriticNet
+
     def __init__(self, gen, critic, cfg, batch_size):
         self.cfg, self.B = cfg, batch_size
         self.gen, self.critic = gen, critic
-        self.Gn, self.Dn = _net_of(gen, _GenNet), _net_of(critic, _CriticNet)
+        self.Gn, self.Dn = _net_of(gen, self.GEN_NET), _net_of(critic, self.CRITIC_NET)
         self.dev = self.Gn.dev
         f = dict(dtype=torch.float32, device=self.dev)
         nD, nG = self.Dn.fp.n_live_padded, self.Gn.fp.n_live_padded
