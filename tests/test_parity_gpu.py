@@ -166,11 +166,12 @@ def test_generator_backward_smooth(variant):
     assert err < TOL_FP32, f"eval-mode generator output rel err {err:.3e}"
 
 
-def test_generator_long_sequence():
-    """Generator is length-agnostic (phase3/test.py:49: 30 s = 750 frames)."""
-    cfg = O.make_cfg()
+@pytest.mark.parametrize("variant,T", [("default", 750), ("wavegan", 3000), ("unet", 750)])
+def test_generator_long_sequence(variant, T):
+    """Generator is length-agnostic (phase3/test.py:49: 30 s = 750 frames; BASELINE configs[4]: WaveGAN-style
+    encoder on long sequences, here 2 minutes = 3000 frames in one call)."""
+    cfg = O.make_cfg(**VARIANTS[variant])
     gen, _ = build(cfg)
-    T = 750
     g = torch.Generator().manual_seed(22)
     audio = (torch.rand(1, T * 640, generator=g) - 0.5) * 0.6
     noise = torch.randn(1, T, cfg["noise_size"], generator=g)
