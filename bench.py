@@ -496,6 +496,9 @@ def run_b200(args):
                 "config": {"workload": workload_name(args, cfg), "global_batch": B * world, "gemm": args.gemm,
                            "sequences_per_step": (nc) * B * world, "parallelism": f"dp{world}",
                            "cuda_graphs": not args.no_graphs,
+                           "graph_structure": ("eager" if args.no_graphs else "one graph per critic iteration, NCCL "
+                                               "all-reduce between graphs" if tr.per_iter else
+                                               "one graph per train step"),
                            "l2": (f"L2 flushed between steps by a {2 * L2_BYTES >> 20} MiB write ({flush_ms:.3f} ms, inside the "
                                   f"timed region); inputs rotate over {NSETS} staged sets; per-iteration working set "
                                   f"(weights + Adam moments {(tr.de.fp.n_live_padded * 16) >> 20} MiB + activations "
