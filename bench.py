@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=7, help="sequences per GPU per iteration (default.yaml: 7)")
     ap.add_argument("--enc", default="default", choices=["default", "wavegan", "unet"])
-    ap.add_argument("--gemm", default="tf32x3", choices=["fp32", "tf32", "tf32x3"],
+    ap.add_argument("--gemm", default="tf32x3", choices=["fp32", "tf32", "tf32bf16", "tf32x3"],
                     help="arithmetic of the GEMM family (include/m2d.h): tcgen05 3xTF32 split (default, fp32-grade), "
                          "tcgen05 single-pass TF32, or CUDA-core fp32")
     ap.add_argument("--no-graphs", action="store_true")
@@ -491,6 +491,8 @@ def run_b200(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_res / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
                 "dtype": {"fp32": "f32", "tf32": "tf32 (fp32 accumulate)",
+                          "tf32bf16": "tf32 hi*hi + bf16 cross terms on tcgen05, fp32 accumulate (fp32-grade; weight "
+                                      "gradients 3xTF32)",
                           "tf32x3": "tf32x3 (3xTF32 operand split on tcgen05, fp32 accumulate; fp32-grade)"}[args.gemm],
                 "data": "synthetic",
                 "config": {"workload": workload_name(args, cfg), "global_batch": B * world, "gemm": args.gemm,

@@ -50,9 +50,14 @@ int m2d_check_device(int dev);
  *   TF32   : tcgen05 tensor cores, operands rounded to TF32 (round-to-nearest), fp32 accumulate
  *   TF32X3 : tcgen05 tensor cores, 3xTF32 operand split (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo):
  *            fp32-grade results on the tensor pipe — the default
+ *   TF32_BF16 : tcgen05 tensor cores, a_hi*b_hi as TF32 plus both cross terms as ONE BF16 contraction over
+ *            [bf16(a_hi) | bf16(a_lo)] x [bf16(b_lo) | bf16(b_hi)] (kind::f16, K = 16 per instruction): 2/3 of the
+ *            tensor-pipe work of TF32X3 at fp32-grade operand error (6-7e-7, tools/split_precision_study.py);
+ *            row convolutions only — weight gradients stay TF32X3.  Opt-in; weights must be re-packed
+ *            (m2d_pack_batch) after switching to or from this mode: the lo plane of w_tiled changes format
  * Shapes the tensor-core kernels do not cover (N < 8, tiny problems, weight gradients with
  * Cout or Cc not a multiple of 4) run on the FP32 kernels in every mode. */
-enum { M2D_GEMM_FP32 = 0, M2D_GEMM_TF32 = 1, M2D_GEMM_TF32X3 = 3 };
+enum { M2D_GEMM_FP32 = 0, M2D_GEMM_TF32 = 1, M2D_GEMM_TF32_BF16 = 2, M2D_GEMM_TF32X3 = 3 };
 /* number of m2d_rowconv calls served by the TMA halo-tile kernel so far (diagnostics / tests) */
 long long m2d_halo_launch_count(void);
 int m2d_set_gemm_mode(int mode);

@@ -11,12 +11,13 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
-// default: 3xTF32 on the tensor cores; the environment variable M2D_GEMM (fp32 | tf32 | tf32x3),
+// default: 3xTF32 on the tensor cores; the environment variable M2D_GEMM (fp32 | tf32 | tf32bf16 | tf32x3),
 // read once at load, lets a whole test / bench run be repeated in another arithmetic
 static int initial_gemm_mode() {
     const char* e = getenv("M2D_GEMM");
     if (e && !strcmp(e, "fp32")) return M2D_GEMM_FP32;
     if (e && !strcmp(e, "tf32")) return M2D_GEMM_TF32;
+    if (e && !strcmp(e, "tf32bf16")) return M2D_GEMM_TF32_BF16;
     return M2D_GEMM_TF32X3;
 }
 static int g_gemm_mode = initial_gemm_mode();
@@ -24,7 +25,7 @@ int gemm_mode() { return g_gemm_mode; }
 }  // namespace m2d
 
 extern "C" int m2d_set_gemm_mode(int mode) {
-    if (mode != M2D_GEMM_FP32 && mode != M2D_GEMM_TF32 && mode != M2D_GEMM_TF32X3) {
+    if (mode != M2D_GEMM_FP32 && mode != M2D_GEMM_TF32 && mode != M2D_GEMM_TF32_BF16 && mode != M2D_GEMM_TF32X3) {
         m2d::set_error("set_gemm_mode: unknown mode %d", mode);
         return M2D_ERR_BAD_ARG;
     }

@@ -1,6 +1,7 @@
 // Shared helpers for libm2d_b200 (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdint>

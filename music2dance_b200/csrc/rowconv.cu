@@ -529,7 +529,25 @@ __device__ __forceinline__ float rna_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
-__global__ void __launch_bounds__(256) pack_batch_kernel(const m2d_pack_desc* __restrict__ table) {
+// hi / lo values of element `v` into the tiled block that holds float index `pidx` (the hi plane).  TF32X3: lo plane
+// = rna_tf32(v - hi) at pidx + R*32.  TF32_BF16 (`mixed`): the lo plane holds, per 128-byte row, the weight side of
+// the BF16 cross-term contraction [bf16(lo) x 32 | bf16(hi) x 32] in the same 16-byte-chunk swizzle.
+__device__ __forceinline__ void store_tiled_split(float* dst_tiled, long long pidx, int R, float v, bool mixed) {
+    const float h = rna_tf32(v);
+    dst_tiled[pidx] = h;
+    if (!mixed) {
+        dst_tiled[pidx + R * 32] = rna_tf32(v - h);
+        return;
+    }
+    const long long blk = pidx / (64LL * R);
+    const int f = (int)(pidx - blk * 64LL * R);                 // float index inside the hi plane
+    const int nl = f >> 5, j = ((f >> 2) & 7) ^ (nl & 7), kk = 4 * j + (f & 3);
+    __nv_bfloat16* plane = reinterpret_cast<__nv_bfloat16*>(dst_tiled + blk * 64LL * R + R * 32);
+    const int sw = nl & 7;
+    plane[nl * 64 + ((((kk >> 3) ^ sw) << 3) | (kk & 7))] = __float2bfloat16_rn(v - h);
+    plane[nl * 64 + (((((32 + kk) >> 3) ^ sw) << 3) | (kk & 7))] = __float2bfloat16_rn(h);
+}
+__global__ void __launch_bounds__(256) pack_batch_kernel(const m2d_pack_desc* __restrict__ table, const bool mixed) {
     const m2d_pack_desc d = table[blockIdx.y];
     const float* __restrict__ w = d.w;
     const int Cout = d.Cout, Cin = d.Cin, k = d.k, stride = d.stride;
@@ -572,11 +590,8 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const m2d_pack_desc* __
             const float v = w[idx];
             if (d.dst) d.dst[row * Tm * Cout + (long long)qp * Cout + co] = v;
             if (d.dst_tiled) {
-                const float h = rna_tf32(v);
                 const int R = tiled_rows(stride * Cin);
-                const long long pidx = tiled_index((int)row, qp, co, Tm, Cout, R);
-                d.dst_tiled[pidx] = h;
-                d.dst_tiled[pidx + R * 32] = rna_tf32(v - h);
+                store_tiled_split(d.dst_tiled, tiled_index((int)row, qp, co, Tm, Cout, R), R, v, mixed);
             }
             continue;
         }
@@ -619,11 +634,7 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const m2d_pack_desc* __
             pidx = poff + tiled_index(ci, q, co, Trho, Cout, R_);
         }
         if (d.dst) d.dst[idx] = v;
-        if (d.dst_tiled) {
-            const float h = rna_tf32(v);
-            d.dst_tiled[pidx] = h;
-            d.dst_tiled[pidx + R_ * 32] = rna_tf32(v - h);
-        }
+        if (d.dst_tiled) store_tiled_split(d.dst_tiled, pidx, R_, v, mixed);
     }
 }
 
@@ -800,7 +811,7 @@ extern "C" int m2d_pack_conv_bwd(const float* w, float* wd, int Cout, int Cin, i
 extern "C" int m2d_pack_batch(const m2d_pack_desc* table, int n, void* stream) {
     M2D_REQUIRE(table && n > 0, "pack_batch: bad args");
     dim3 grid(148, (unsigned)n);
-    pack_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table);
+    pack_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table, gemm_mode() == M2D_GEMM_TF32_BF16);
     return check_launch("pack_batch");
 }
 

@@ -126,6 +126,10 @@ rowconv_halo_kernel(const m2d_rowconv_args a, const HaloPlan plan, const int tpb
                 if (NS == 3)
                     *reinterpret_cast<float4*>(lo + 16 * idx) =
                         make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+                if (NS == 2) {      // BF16 plane [bf16(hi) | bf16(lo)]: the sweep is physical, recover the logical chunk
+                    const int r = idx >> 3;
+                    store_bf16_pair(lo, r, (idx & 7) ^ (r & 7), h, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
+                }
             }
             fence_proxy_async_smem();
             __syncwarp();
@@ -141,6 +145,7 @@ rowconv_halo_kernel(const m2d_rowconv_args a, const HaloPlan plan, const int tpb
             // address field of a descriptor is (addr >> 4) in its low 14 bits, so "+ 32*k bytes" is "+ 2*k" and a
             // row shift of the halo tile is "+ 8 per row" on the 64-bit value.
             const uint32_t idesc = tf32_idesc(TC_BM, bn);
+            const uint32_t idesc16 = bf16_idesc(TC_BM, bn);
             const uint64_t dB0 = sw128_desc(smem_base + off_b);
             const uint64_t dBstep = (uint64_t)((2u * b_plane) >> 4), dBlo = (uint64_t)(b_plane >> 4);
             uint64_t dB = dB0;
@@ -173,6 +178,11 @@ rowconv_halo_kernel(const m2d_rowconv_args a, const HaloPlan plan, const int tpb
                                 umma_tf32(tmem, ah, bh, idesc, k == 0 ? acc : 1u);
                             }
                         }
+                        if (NS == 2) {      // both cross terms: [bf16(a_hi) | bf16(a_lo)] x [bf16(b_lo) | bf16(b_hi)], K = 64
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(tmem, dA + (HL_TILE >> 4) + 2 * k, dB + dBlo + 2 * k, idesc16, 1);
+                        }
                         umma_commit(b_empty + 8 * st);
                     }
                     __syncwarp();
@@ -194,7 +204,7 @@ rowconv_halo_kernel(const m2d_rowconv_args a, const HaloPlan plan, const int tpb
         {
             const long long nt_base = (long long)blockIdx.y * a.T * cch;
             const long long blk = tiled_block_floats(brows);
-            const uint32_t bytes = (NS == 3 ? 2u : 1u) * b_plane;
+            const uint32_t bytes = (uint32_t)tc_planes(NS) * b_plane;
             int st = 0;
             uint32_t bph = 1;                                   // fresh "empty" barriers pass the first round
             for (int n = 0; n < nu; ++n) {
@@ -499,6 +509,7 @@ static int rowconv_halo_dispatch(const m2d_rowconv_args& a, int M, int mode, cud
     }
     ++g_halo_launches;
     static const int trace_on = halo_env("M2D_HALO_TRACE", 0);
+    if (mode == M2D_GEMM_TF32_BF16) return launch_halo<2, false>(a, plan, tpb, splits, st, NA, NB, brows, mx);
     if (trace_on)
         return mode == 3 ? launch_halo<3, true>(a, plan, tpb, splits, st, NA, NB, brows, mx)
                          : launch_halo<1, true>(a, plan, tpb, splits, st, NA, NB, brows, mx);

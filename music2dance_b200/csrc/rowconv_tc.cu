@@ -197,13 +197,17 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
             }
         };
 
-        auto split_store = [&](uint8_t* hi_tile, uint8_t* lo_tile, int r, float4 v) {
+        auto split_store = [&](uint8_t* hi_tile, uint8_t* lo_tile, int r, float4 v, bool weight) {
             const uint32_t off = sw128_off(r, j);
             float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
             *reinterpret_cast<float4*>(hi_tile + off) = h;
             if (NS == 3) {
                 float4 l = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
                 *reinterpret_cast<float4*>(lo_tile + off) = l;
+            }
+            if (NS == 2) {      // BF16 plane: [bf16(hi) | bf16(lo)] for the activations, [bf16(lo) | bf16(hi)] for the weights
+                const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                store_bf16_pair(lo_tile, r, j, weight ? l : h, weight ? h : l);
             }
         };
 
@@ -212,13 +216,13 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
             const uint32_t ph = (uint32_t)((it / STAGES) & 1);
             mbar_wait(bar_empty + 8 * st, ph ^ 1);
             uint8_t* sA = smem + (size_t)st * STAGE_BYTES;
-            uint8_t* sB = sA + (NS == 3 ? 2 : 1) * TC_A_BYTES;
+            uint8_t* sB = sA + tc_planes(NS) * TC_A_BYTES;
 #pragma unroll
-            for (int q = 0; q < TC_RPT; ++q) split_store(sA, sA + TC_A_BYTES, rsub + RS * q, pa[q]);
+            for (int q = 0; q < TC_RPT; ++q) split_store(sA, sA + TC_A_BYTES, rsub + RS * q, pa[q], false);
             if (!BTMA) {
 #pragma unroll
                 for (int q = 0; q < TC_RPT; ++q)
-                    if (rsub + RS * q < bn) split_store(sB, sB + TC_B_BYTES, rsub + RS * q, pb[q]);
+                    if (rsub + RS * q < bn) split_store(sB, sB + TC_B_BYTES, rsub + RS * q, pb[q], true);
             }
             fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
             mbar_arrive(bar_full + 8 * st);
@@ -240,10 +244,11 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
         // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
         {
             const uint32_t idesc = tf32_idesc(TC_BM, bn);
+            const uint32_t idesc16 = bf16_idesc(TC_BM, bn);
             // the lo plane follows the hi plane: 128 rows apart when staged by threads, R rows in a tiled block
             const uint64_t b_plane = (uint64_t)((BTMA ? (uint32_t)tiled_rows(a.N) * 128u : (uint32_t)TC_B_BYTES) >> 4);
             const uint64_t dA0 = sw128_desc(smem_base);
-            const uint64_t offB = (uint64_t)(((NS == 3 ? 2 : 1) * TC_A_BYTES) >> 4);
+            const uint64_t offB = (uint64_t)((tc_planes(NS) * TC_A_BYTES) >> 4);
             uint64_t dA = dA0;
             int st = 0;
             uint32_t ph = 0;
@@ -262,6 +267,11 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
                             umma_tf32(tmem, ah, bh, idesc, (it | k) != 0);
                         }
                     }
+                    if (NS == 2) {      // both cross terms as one BF16 contraction over the 64-element rows of the BF16 planes
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tmem, dA + (TC_A_BYTES >> 4) + 2 * k, dA + offB + b_plane + 2 * k, idesc16, 1);
+                    }
                     umma_commit(bar_empty + 8 * st);     // stage reusable once these MMAs have read it
                 }
                 __syncwarp();
@@ -275,7 +285,7 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
         // ------------------------------------------------------------------ weight blocks: one bulk copy per stage
         if (BTMA) {
             const int R = tiled_rows(a.N);
-            const uint32_t bytes = (NS == 3 ? 2u : 1u) * (uint32_t)R * 128u;       // hi [+ lo] plane of the block
+            const uint32_t bytes = (uint32_t)tc_planes(NS) * (uint32_t)R * 128u;   // hi [+ lo / BF16] plane of the block
             // block ((nt*T + t)*cchunks + c); Cc == 1: single tap whose channels are the taps (T = 1, c = K step)
             const long long nt_base = (long long)blockIdx.y * (C1 ? 1 : a.T) * (C1 ? nsteps : cchunks);
             for (int it = 0; it < nk; ++it) {
@@ -283,7 +293,7 @@ rowconv_tc_kernel(const m2d_rowconv_args a, const int M, const int nsteps, const
                 const uint32_t ph = (uint32_t)((it / STAGES) & 1);
                 const float* src = a.w_tiled + (nt_base + s_begin + it) * tiled_block_floats(R);
                 mbar_wait(bar_empty + 8 * st, ph ^ 1);
-                const uint32_t sB = smem_base + (uint32_t)st * STAGE_BYTES + (NS == 3 ? 2 : 1) * TC_A_BYTES;
+                const uint32_t sB = smem_base + (uint32_t)st * STAGE_BYTES + tc_planes(NS) * TC_A_BYTES;
                 if (elect_one()) {
                     mbar_arrive_expect_tx(bar_full + 8 * st, bytes);
                     bulk_load(sB, src, bytes, bar_full + 8 * st);
@@ -542,9 +552,11 @@ int rowconv_tc_dispatch(const m2d_rowconv_args& a, int M, int mode, cudaStream_t
     }
     // weight operand by bulk copy when the caller supplies the pre-split, pre-tiled copy
     if (a.w_tiled && aligned16(a.w_tiled)) {
+        if (mode == M2D_GEMM_TF32_BF16) return launch_tc_shape<2, true>(a, M, nsteps, cchunks, splits, st, c1, vec);
         return mode == 3 ? launch_tc_shape<3, true>(a, M, nsteps, cchunks, splits, st, c1, vec)
                          : launch_tc_shape<1, true>(a, M, nsteps, cchunks, splits, st, c1, vec);
     }
+    if (mode == M2D_GEMM_TF32_BF16) return launch_tc_shape<2, false>(a, M, nsteps, cchunks, splits, st, c1, vec);
     return mode == 3 ? launch_tc_shape<3, false>(a, M, nsteps, cchunks, splits, st, c1, vec)
                      : launch_tc_shape<1, false>(a, M, nsteps, cchunks, splits, st, c1, vec);
 }
@@ -836,7 +848,8 @@ int wgrad_tc_dispatch(const m2d_wgrad_args& a, int Ktot, int Ncols, int mode, cu
     long long want = cdiv(2 * kNumSMs, tiles);
     int splits = (int)(want < nsteps / 2 ? want : nsteps / 2);
     if (splits < 1) splits = 1;
-    return mode == 3 ? launch_wgrad_tc<3>(a, Ktot, Ncols, splits, st) : launch_wgrad_tc<1>(a, Ktot, Ncols, splits, st);
+    // TF32_BF16 applies to the row convolutions only: weight gradients (MN-major operands) stay 3xTF32
+    return mode != M2D_GEMM_TF32 ? launch_wgrad_tc<3>(a, Ktot, Ncols, splits, st) : launch_wgrad_tc<1>(a, Ktot, Ncols, splits, st);
 }
 
 }  // namespace m2d

@@ -16,8 +16,12 @@ constexpr int TC_THREADS = TC_PRODUCERS + 64;   // + MMA-issuer warp + TMA-issue
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;        // 16 KiB
 constexpr int TC_B_BYTES = TC_BNMAX * TC_BK * 4;     // 16 KiB
 
-__host__ __device__ constexpr int tc_stage_bytes(int ns) { return (ns == 3 ? 2 : 1) * (TC_A_BYTES + TC_B_BYTES); }
-__host__ __device__ constexpr int tc_stages(int ns) { return ns == 3 ? 3 : 4; }
+// NS = operand-split scheme of a kernel instance: 1 = one TF32 product (hi plane only), 3 = 3xTF32 (hi + TF32 lo
+// plane), 2 = TF32 hi*hi + ONE BF16 contraction for both cross terms (hi plane + a BF16 plane of the same size:
+// [bf16(hi) | bf16(lo)] per 128-byte row for the activation operand, [bf16(lo) | bf16(hi)] for the weights)
+__host__ __device__ constexpr int tc_planes(int ns) { return ns >= 2 ? 2 : 1; }
+__host__ __device__ constexpr int tc_stage_bytes(int ns) { return tc_planes(ns) * (TC_A_BYTES + TC_B_BYTES); }
+__host__ __device__ constexpr int tc_stages(int ns) { return ns >= 2 ? 3 : 4; }
 // stages + epilogue staging tile never coexist: the C tile (128 x 129 floats) reuses the stages
 __host__ __device__ constexpr int tc_smem_bytes(int ns) { return tc_stages(ns) * tc_stage_bytes(ns) + 1024; }
 
@@ -80,6 +84,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
         "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same, kind::f16 (BF16 operands, K = 16 per instruction, fp32 accumulate into the same TMEM columns)
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
@@ -124,6 +139,25 @@ __device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
 // N >> 3 @ bit 17, M >> 4 @ bit 24
 __device__ __forceinline__ uint32_t tf32_idesc(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// kind::f16 with D = F32, A = B = BF16 (format 1), both K-major
+__device__ __forceinline__ uint32_t bf16_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// 4 consecutive channels (16-byte chunk j of row r of an fp32 K-major tile) -> the BF16 plane of the mixed
+// scheme: 4 x bf16(first) into row positions 4j.., 4 x bf16(second) into 32 + 4j.. (8 bytes each), same swizzle.
+// Activation operand: first = hi, second = lo; weight operand: first = lo, second = hi.
+__device__ __forceinline__ void store_bf16_pair(uint8_t* plane, int r, int j, const float4 first, const float4 second) {
+    const int sw = r & 7;
+    uint8_t* row = plane + (r >> 3) * 1024 + sw * 128 + 8 * (j & 1);
+    __nv_bfloat162 f0 = __floats2bfloat162_rn(first.x, first.y), f1 = __floats2bfloat162_rn(first.z, first.w);
+    __nv_bfloat162 s0 = __floats2bfloat162_rn(second.x, second.y), s1 = __floats2bfloat162_rn(second.z, second.w);
+    uint2 fv, sv;
+    fv.x = *reinterpret_cast<uint32_t*>(&f0); fv.y = *reinterpret_cast<uint32_t*>(&f1);
+    sv.x = *reinterpret_cast<uint32_t*>(&s0); sv.y = *reinterpret_cast<uint32_t*>(&s1);
+    *reinterpret_cast<uint2*>(row + ((((j >> 1)) ^ sw) << 4)) = fv;
+    *reinterpret_cast<uint2*>(row + (((4 + (j >> 1)) ^ sw) << 4)) = sv;
 }
 
 constexpr int TC_CLD = TC_BNMAX + 4;      // C staging tile row stride (floats): 16-byte aligned rows, conflict-free float4 access

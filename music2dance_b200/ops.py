@@ -361,12 +361,13 @@ def adam(p, g, m, v, n, step, lr, b1=0.9, b2=0.999, eps=1e-8, gscale=1.0):
     call("m2d_adam", _p(p), _p(g), _p(m), _p(v), n, _p(step), lr, b1, b2, eps, gscale, _stream())
 
 
-GEMM_MODES = {"fp32": 0, "tf32": 1, "tf32x3": 3}
+GEMM_MODES = {"fp32": 0, "tf32": 1, "tf32bf16": 2, "tf32x3": 3}
 
 
 def set_gemm_mode(mode):
     """Arithmetic of the GEMM family: 'fp32' (CUDA cores), 'tf32' (tcgen05, one TF32 product),
-    'tf32x3' (tcgen05, 3xTF32 split, fp32-grade; the default).  See include/m2d.h."""
+    'tf32x3' (tcgen05, 3xTF32 split, fp32-grade; the default), 'tf32bf16' (TF32 hi*hi + BF16 cross terms, opt-in;
+    packed weights must be refreshed after switching to / from it).  See include/m2d.h."""
     call("m2d_set_gemm_mode", GEMM_MODES[mode] if isinstance(mode, str) else int(mode))
 
 

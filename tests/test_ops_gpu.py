@@ -16,7 +16,7 @@ DEV = "cuda:0"
 # 3xTF32 accumulates in TMEM through K/8 sequential tensor-core additions (truncating adder): at the
 # longest contraction of the model (audio_d.l6, K = 38400, 8-way cluster split) the measured error is
 # 3.2e-5 of max|y|; every K <= 6400 case stays below 6e-6.
-MODE_TOL = {"fp32": 3e-5, "tf32x3": 5e-5, "tf32": 3e-3}
+MODE_TOL = {"fp32": 3e-5, "tf32x3": 5e-5, "tf32bf16": 5e-5, "tf32": 3e-3}
 CUR = {"mode": "tf32x3"}
 
 
@@ -37,7 +37,7 @@ def ncl(m, B, L, C):
     return m.t.view(B, L, C).permute(0, 2, 1).cpu()
 
 
-@pytest.fixture(scope="module", params=["fp32", "tf32x3", "tf32"])
+@pytest.fixture(scope="module", params=["fp32", "tf32x3", "tf32bf16", "tf32"])
 def lib(request):
     from music2dance_b200 import ops
     ops.check_device(0)
