@@ -118,3 +118,25 @@ def test_dropin_modules_refuse_cpu_tensors():
             slice_audio_batch(torch.zeros(2, 76800), 3200, 640, 2560)
     with pytest.raises(NotImplementedError):
         gradient_penalty(None, 2, x, x, is_seq=False)                      # phase1 branch lives in phase1.Phase1Trainer
+
+
+def test_gemm_mode_names_match_header_enum():
+    """ops.GEMM_MODES (the strings bench.py --gemm / M2D_GEMM accept) against the enum of include/m2d.h, and the
+    mode setter's argument check (host-only: no kernel is launched)."""
+    import re
+
+    from music2dance_b200 import _lib, ops
+    hdr = open(os.path.join(ROOT, "include", "m2d.h")).read()
+    enum = dict((k, int(v)) for k, v in re.findall(r"M2D_GEMM_(\w+) = (\d+)", hdr))
+    assert enum == {"FP32": 0, "TF32": 1, "TF32_BF16": 2, "TF32X3": 3}
+    assert ops.GEMM_MODES == {"fp32": enum["FP32"], "tf32": enum["TF32"], "tf32bf16": enum["TF32_BF16"],
+                              "tf32x3": enum["TF32X3"]}
+    lib = _lib.load()
+    before = lib.m2d_get_gemm_mode()
+    try:
+        for name, v in ops.GEMM_MODES.items():
+            ops.set_gemm_mode(name)
+            assert lib.m2d_get_gemm_mode() == v and ops.get_gemm_mode() == name
+        assert lib.m2d_set_gemm_mode(7) != 0 and b"unknown mode" in lib.m2d_last_error()
+    finally:
+        lib.m2d_set_gemm_mode(before)
