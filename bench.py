@@ -39,6 +39,7 @@ if ROOT not in sys.path:
 METRIC = "phase3 WGAN-GP train steps/sec (seq=120)"
 UNIT = "train steps/s"
 L2_BYTES = 126 << 20
+TRAFFIC_FILE = "r02_traffic.json"
 
 
 def parse():
@@ -57,7 +58,17 @@ def parse():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-device-dataset", action="store_true",
                     help="skip the e2e_device_dataset measurement (input pipeline on a device-resident dataset)")
-    ap.add_argument("--cpu-budget-s", type=float, default=150.0)
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0,
+                    help="wall-clock bound of the reference arm (steps / warm-up are cut down to fit, never below 3 / 1)")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference: host CPU (the reference arm) or cuda:0 through PyTorch eager + cuDNN/cuBLAS "
+                         "(used by the torch_eager_gpu leg)")
+    ap.add_argument("--ref-tf32", action="store_true", help="--ref-device cuda: allow TF32 in cuDNN / cuBLAS")
+    ap.add_argument("--no-eager-gpu", action="store_true", help="skip the torch_eager_gpu leg (reference modules on cuda:0)")
+    ap.add_argument("--no-throughput-regime", action="store_true",
+                    help="skip the throughput_regime sub-record (a second, short run at --regime-batch per GPU)")
+    ap.add_argument("--regime-batch", type=int, default=64)
+    ap.add_argument("--sub", action="store_true", help=argparse.SUPPRESS)      # child run: no nested legs
     return ap.parse_args()
 
 
@@ -78,64 +89,118 @@ def workload_name(args, cfg):
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of phase3/train.py:186-237 (reference = PyTorch CPU eager)
+# reference arm: the reference's own modules (oracle/_ref, staged by oracle/build_ref.py) through the loop body of
+# phase3/train.py:186-237 — PyTorch CPU eager on the host cores, or eager + cuDNN/cuBLAS on cuda:0
 # ----------------------------------------------------------------------------------------------
 
-def cpu_step_time(cfg, B, budget_s, full_steps=0):
-    """Time the CPU path.  Returns (seconds per train step, description of the sample)."""
+def reference_time(cfg, B, device, steps, warmup, budget_s, tf32=False):
+    """Returns (seconds per train step, description of the sample, cores, kind, detail dict)."""
+    from oracle import ref_arm
+    if ref_arm.ref_root() is not None:
+        r = ref_arm.time_steps(cfg, B, device, steps, warmup, budget_s, tf32=tf32)
+        sample = (f"{r['steps_timed']} full train steps ({cfg['n_critic_steps']} critic iterations + 1 generator update "
+                  f"each) at batch {B} after {r['warmup_done']} warm-up step(s), median; fresh synthetic batches, "
+                  f"windowing on the CPU and H2D copies inside the step as in train.py:189-193")
+        return r["s_per_step"], sample, r["cores"], "reference", r
+    # the staged reference is missing (oracle/build_ref.py never ran): the oracle port, full steps as well
     import torch
     from oracle import phase3_oracle as O
+    assert device == "cpu", "the oracle port is a CPU restatement"
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
     G, D = O.init_generator_params(cfg), O.init_critic_params(cfg)
     ad, ag = O.AdamState(D, cfg["lr_critic"]), O.AdamState(G, cfg["lr_gen"])
-    nc = cfg["n_critic_steps"]
-    b = O.synthetic_batch(cfg, B, 1234)
-    O.critic_iteration(G, D, cfg, b[0], b[1], b[2], b[3], ad)           # warm-up (thread pools, allocator)
     t0 = time.perf_counter()
-    O.critic_iteration(G, D, cfg, b[0], b[1], b[2], b[3], ad)
-    t_c1 = time.perf_counter() - t0
-    est = nc * t_c1 * 1.15
-    if full_steps and full_steps * est <= budget_s:
-        ts = []
-        for s in range(full_steps):
-            t0 = time.perf_counter()
-            O.train_step(G, D, cfg, B, s, ag, ad)
-            ts.append(time.perf_counter() - t0)
-        ts.sort()
-        return ts[len(ts) // 2], f"{full_steps} full train steps ({nc} critic iterations + 1 generator update each), median", cores
-    n_c = max(1, min(nc, int(budget_s * 0.6 / max(t_c1, 1e-3))))
-    t0 = time.perf_counter()
-    for i in range(n_c):
-        bb = O.synthetic_batch(cfg, B, 2000 + i)
-        O.critic_iteration(G, D, cfg, bb[0], bb[1], bb[2], bb[3], ad)
-    t_c = (time.perf_counter() - t0) / n_c
-    t0 = time.perf_counter()
-    O.generator_update(G, D, cfg, b[0], b[1], b[4], ag)
-    t_g = time.perf_counter() - t0
-    return nc * t_c + t_g, (f"{n_c} critic iteration(s) + 1 generator update at batch {B} (data generation included), "
-                            f"extrapolated to {nc} + 1"), cores
+    O.train_step(G, D, cfg, B, 0, ag, ad)
+    est = time.perf_counter() - t0
+    k = int(max(3, min(steps, (budget_s - est) / max(est, 1e-6))))
+    ts = []
+    for i in range(k):
+        t0 = time.perf_counter()
+        O.train_step(G, D, cfg, B, 1 + i, ag, ad)
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    return ts[len(ts) // 2], f"{k} full train steps of the oracle port at batch {B} after 1 warm-up step, median", cores, "port", \
+        {"steps_timed": k, "warmup_done": 1}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import phase3_oracle as O
+    from music2dance_b200 import config as O
     cfg = O.make_cfg(enc_type=args.enc)
-    total = args.steps + args.warmup
-    t_step, sample, cores = cpu_step_time(cfg, args.batch, args.cpu_budget_s,
-                                          full_steps=total if total <= 6 else 0)
+    t0 = time.perf_counter()
+    t_step, sample, cores, kind, det = reference_time(cfg, args.batch, args.ref_device, args.steps, args.warmup,
+                                                      args.cpu_budget_s, tf32=args.ref_tf32)
     v = 1.0 / t_step
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args, cfg), "device": "host CPU (PyTorch eager fp32)"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+    where = ("host CPU (PyTorch eager fp32)" if args.ref_device == "cpu" else
+             "cuda:0 (PyTorch eager, cuDNN/cuBLAS, " + ("TF32 allowed" if args.ref_tf32 else "fp32, TF32 off") + ")")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": det["steps_timed"], "steps_requested": args.steps, "warmup": det["warmup_done"],
+            "warmup_requested": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if not args.ref_tf32 else "tf32", "data": "synthetic",
+            "config": {"workload": workload_name(args, cfg), "device": where, "global_batch": args.batch,
+                       "note": "one process at the per-GPU batch: the reference has no multi-GPU path; compare with the "
+                               "N = 1 line only"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+            "detail": {k: det[k] for k in ("p10_s", "p90_s", "threads", "source", "torch", "logs") if k in det}}
     print(json.dumps(line), flush=True)
+
+
+def child_line(extra, timeout_s):
+    """Run this script again in a child process (own CUDA context, memory released afterwards) and return its JSON line."""
+    import subprocess
+    cmd = [sys.executable, os.path.abspath(__file__)] + extra
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"error": (r.stderr or r.stdout)[-400:]}
+    except Exception as e:                                                  # noqa: BLE001
+        return {"error": repr(e)[:400]}
+
+
+def measure_tf32_peak(torch, dev, seconds=3.0):
+    """Dense TF32 tensor-pipe peak of this GPU the way MEASURED_PEAKS.json measures bf16: cuBLAS 8192^3 fp32 matmul
+    with TF32 allowed — best of 10 (burst) and back to back for `seconds` (sustained, under the power cap)."""
+    n = 8192
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        c = torch.empty(n, n, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize(dev)
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b, out=c)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(10, int(seconds * 1e3 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        fl = 2.0 * n ** 3
+        return {"tf32_tflops": fl / (best * 1e-3) / 1e12, "tf32_tflops_sustained": fl * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12,
+                "how": f"torch.matmul fp32 {n}^3 with allow_tf32 (cuBLAS): best of 10 (burst) and {reps} back to back (sustained)"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
 
 
 # ----------------------------------------------------------------------------------------------
@@ -439,25 +504,27 @@ def run_b200(args):
         top = max(fams, key=lambda f: fams[f]["ms"])
         d = fams[top]
         tensor_bound = d["flops"] / max(d["bytes"], 1.0) > 100.0
+        tfp = measure_tf32_peak(torch, dev) if tensor_bound else None
         if tensor_bound:
             ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
-            # TF32 dense peak = half the bf16 rate (same tensor pipe, K = 8 instead of 16 per instruction)
-            peak = pk["bf16_tflops_sustained"] / 2.0
+            peak = tfp["tf32_tflops_sustained"]          # kernels timed inside a long step: the sustained figure
             roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": None}
+                    "traffic": None, "tf32_peak_measured": tfp}
         else:
             ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
             peak = pk["hbm_gbs"]
             roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None}
-        # DRAM bytes per launch of the same kernel family from the committed ncu capture (tools/gpu_traffic.sh);
-        # null when the capture does not cover the dominant family
+        # DRAM bytes per launch of the same kernel family from the committed ncu capture of THIS tree
+        # (tools/gpu_traffic.sh -> tools/summarize_traffic.py); null when the capture is stale (its launch count of
+        # the family differs from the one just counted) or does not cover the dominant family
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_tc_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)) as f:
                 tj = json.load(f)
-            if args.batch == 7 and args.enc == "default" and top in tj:
-                roof["traffic"] = tj[top]["traffic_bytes_per_launch"]
-                roof["traffic_source"] = ("profiles/r01_tc_traffic.json: mean dram__bytes_read+write per launch over the "
-                                          f"{tj[top]['launches']} {top} tensor-core launches of one train step")
+            key = f"{top}:b{args.batch}:{args.enc}:{args.gemm}"
+            if key in tj and tj[key]["launches_per_step"] == d["launches"]:
+                roof["traffic"] = tj[key]["traffic_bytes_per_launch"]
+                roof["traffic_source"] = (f"profiles/{TRAFFIC_FILE}: mean dram__bytes_read+write per launch over the "
+                                          f"{tj[key]['launches_per_step']} {top} launches of one train step (ncu, same tree)")
         except (OSError, ValueError, KeyError):
             pass
         roof.update({"kernel": top, "launches_per_step": d["launches"],
@@ -465,10 +532,11 @@ def run_b200(args):
                      "share_of_eager_step": d["ms"] / eager_ms,
                      "measured_in": "one instrumented eager train step, single stream (multi-stream overlap off), "
                                     "CUDA events around every launch of the family",
-                     "peak_source": pk["source"] + ("; TF32 dense peak taken as half the measured sustained bf16 rate "
-                                                    "(no TF32 figure in the file); gemm mode " + args.gemm +
-                                                    (" issues 3 tensor-core products per algorithmic product"
-                                                     if args.gemm == "tf32x3" else "") if tensor_bound else ""),
+                     "peak_source": (("measured in this run: " + tfp["how"] + "; gemm mode " + args.gemm +
+                                      {"tf32x3": " issues 3 tensor-core products per algorithmic product",
+                                       "tf32bf16": " issues 2 TF32-equivalent tensor-core products per algorithmic product "
+                                                   "(row convolutions; weight gradients 3)"}.get(args.gemm, ""))
+                                     if tensor_bound else pk["source"]),
                      "algorithmic_gflop_per_launch": d["flops"] / d["launches"] / 1e9,
                      "algorithmic_bytes_per_launch": d["bytes"] / d["launches"]})
         for f in fams.values():
@@ -480,8 +548,33 @@ def run_b200(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        t_step, sample, cores = cpu_step_time(cfg, B, 25.0)
-        cpu = {"value": 1.0 / t_step, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        t_step, sample, cores, kind, _ = reference_time(cfg, B, "cpu", 3, 1, 30.0)
+        cpu = {"value": 1.0 / t_step, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+
+    # The bar a user of the reference gets on this GPU today: the reference's stock modules through
+    # PyTorch eager + cuDNN/cuBLAS on cuda:0, fp32 (TF32 off) and with TF32 allowed.  Child processes, after every timed
+    # region of this run; never the product path.
+    eager = None
+    if rank == 0 and world == 1 and not args.sub and not args.no_eager_gpu:
+        eager = {}
+        for tag, extra in (("fp32", []), ("tf32", ["--ref-tf32"])):
+            ln = child_line(["--impl", "reference", "--ref-device", "cuda", "--batch", str(B), "--enc", args.enc,
+                             "--steps", "10", "--warmup", "3", "--cpu-budget-s", "60"] + extra, 240)
+            eager[tag] = ({"value": ln["value"], "unit": UNIT, "ms_per_step": ln["ms_per_step"], "steps": ln["steps"],
+                           "warmup": ln["warmup"], "kind": ln["cpu_baseline"]["kind"], "device": ln["config"]["device"],
+                           "last_step_logs": ln.get("detail", {}).get("logs")} if "value" in ln else ln)
+    regime = None
+    if rank == 0 and world == 1 and not args.sub and not args.no_throughput_regime and args.regime_batch != B:
+        ln = child_line(["--batch", str(args.regime_batch), "--enc", args.enc, "--gemm", args.gemm, "--steps", "5",
+                         "--warmup", "3", "--sub", "--no-cpu-baseline", "--no-device-dataset"], 400)
+        if "value" in ln:
+            regime = {"batch_per_gpu": args.regime_batch, "value": ln["value"], "unit": UNIT,
+                      "ms_per_step": ln["ms_per_step"], "sequences_per_s": ln["sequences_per_s"],
+                      "e2e": ln["e2e"], "roofline": ln.get("roofline"), "clocks": ln.get("clocks"),
+                      "kernel_families": {k: {kk: v[kk] for kk in ("launches", "ms", "tflops", "gbs", "share_of_eager_step")}
+                                          for k, v in (ln.get("kernel_families") or {}).items()}}
+        else:
+            regime = ln
 
     if rank == 0:
         v = world * args.steps / (ms_res * 1e-3)
@@ -510,6 +603,10 @@ def run_b200(args):
                 "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
                 "clocks": clocks, "clocks_e2e": clocks_e2e,
                 "sequences_per_s": v * nc * B,
+                "value_definition": ("train steps/s summed over the ranks: every rank runs batch-B train steps on its own "
+                                     "shard with all-reduced gradients (weak scaling), i.e. optimizer steps/s x n_gpus; "
+                                     "sequences_per_s = value x n_critic x batch is the size-independent companion"),
+                "optimizer_steps_per_s": v / world,
                 "last_step_logs": {"loss_critic": logs["critic"][-1]["loss_critic"], "gp": logs["critic"][-1]["gp"],
                                    "loss_gen": logs["gen"]["loss_gen"]}}
         if e2e_ds is not None:
@@ -519,6 +616,10 @@ def run_b200(args):
             line["kernel_families"] = fams
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if eager is not None:
+            line["torch_eager_gpu"] = eager
+        if regime is not None:
+            line["throughput_regime"] = regime
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -297,6 +297,10 @@ int m2d_slice_audio(const float* audio, float* out, int nseq, int A, int nwin, i
 int m2d_adam(float* p, const float* g, float* m, float* v, long long n, int* step,
              float lr, float beta1, float beta2, float eps, float gscale, void* stream);
 
+/* Diagnostics (tools/step_timeline.py): *slot = %globaltimer (ns) when `stream` reaches this point; graph-capturable,
+ * so the replayed train step can be cut into phases without a profiler attached. */
+int m2d_timestamp(unsigned long long* slot, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,6 +100,7 @@ SIGNATURES = {
     "m2d_wgan_scalars": [_P, _P, _I, _L, _L, _F, _F, _I, _P, _P],
     "m2d_slice_audio": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "m2d_adam": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _P],
+    "m2d_timestamp": [_P, _P],
 }
 _RESTYPE = {"m2d_wgrad_min_ws": i64, "m2d_halo_launch_count": i64}
 _NOCHECK = {"m2d_wgrad_min_ws", "m2d_version", "m2d_get_gemm_mode", "m2d_halo_launch_count"}     # return a value, not a status

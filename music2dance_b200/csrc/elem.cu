@@ -561,6 +561,11 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 __global__ void tick_kernel(int* step) { *step += 1; }
+__global__ void timestamp_kernel(unsigned long long* slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *slot = t;
+}
 
 }  // namespace m2d
 
@@ -814,4 +819,10 @@ extern "C" int m2d_adam(float* p, const float* g, float* m, float* v, long long 
     tick_kernel<<<1, 1, 0, st>>>(step);
     adam_kernel<<<grid1d(n), 256, 0, st>>>(p, g, m, v, n, step, lr, beta1, beta2, eps, gscale);
     return check_launch("adam");
+}
+
+extern "C" int m2d_timestamp(unsigned long long* slot, void* stream) {
+    M2D_REQUIRE(slot, "timestamp: bad args");
+    timestamp_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(slot);
+    return check_launch("timestamp");
 }

@@ -629,8 +629,11 @@ class GeneratorNet:
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 self.nrnn.fwd(nz, z.cols_slice(self.H, self.Lat), B, T, wk, save=True)
+        ops.mark("g:start")
         self.enc.fwd(src, nb, win, wk, train, enc_out)
+        ops.mark("g:enc")
         self.rnn.fwd(enc_out.as_rows(1, nb), z.cols_slice(0, self.H), B, T, wk, save=True)
+        ops.mark("g:rnn")
         if side is not None:
             cur.wait_stream(side)
         else:
@@ -654,6 +657,7 @@ class GeneratorNet:
             d = dn
         fake = out if out is not None else wk.mat("g:fake", 1, nb, self.O)
         self.last.fwd(d, fake, ws=wk.scratch)
+        ops.mark("g:fwd_end")
         self.d_last = d
         if train:
             if self.nbt_flat is not None:
@@ -686,10 +690,13 @@ class GeneratorNet:
         self.fc1.wgrad(dc, z, wk.scratch, acc=wk.acc_slot(self.S))
         e_z = wk.mat("g:e_z", 1, nb, self.Lat)
         self.fc1.dgrad(dc, e_z, ws=wk.scratch)
+        ops.mark("gb:dec")
         self.nrnn.bwd(e_z.cols_slice(self.H, self.Lat), B, T, wk)
         e_enc = wk.mat("g:e_enc", 1, nb, self.I)
         self.rnn.bwd(e_z.cols_slice(0, self.H), B, T, wk, e_x=e_enc)
+        ops.mark("gb:rnn")
         self.enc.bwd(e_enc.as_rows(nb, 1), self.src, nb, self.win, wk)
+        ops.mark("gb:enc")
 
 
 # ===========================================================================
@@ -823,6 +830,7 @@ class CriticNet:
             x = y
         x = self._drop(x, sv, n, f"{tag}:yd")
         self.s_fconv.fwd(x, code_out.as_rows(n, 1), act=self.act, ws=wk.scratch)
+        ops.mark(f"{tag}:pose_fwd_end")
         sv["y"], sv["code"] = x, code_out
         return sv
 
@@ -869,6 +877,7 @@ class CriticNet:
                 c1.dgrad(dc1, dc0, ws=wk.scratch, add=e, add_before_mask=True, mask=sv["r0"], mask_mode=ACT_RELU)
                 dl["conv1"] = dc0
         sv["delta"] = dl
+        ops.mark(f"{tag}:pose_bwd_end")
         if dX is not None:
             self.s_conv1.dgrad(dl["conv1"], dX, ws=wk.scratch)
         if wgrads:
@@ -937,7 +946,9 @@ class CriticNet:
                 l.fwd(x, q, act=ACT_RELU, ws=wk.scratch)
             sv["q"].append(q)
             x = q
+            ops.mark(f"{tag}:aud_fwd_l{i + 1}")
         self.a_l6.fwd(x, code_out.as_rows(n, 1), act=self.act, ws=wk.scratch)
+        ops.mark(f"{tag}:aud_fwd_l6")
         sv["code"] = code_out
         return sv
 
@@ -951,10 +962,12 @@ class CriticNet:
         q = sv["q"]
         d = wk.mat(f"{tag}:dq5", n, q[4].rows, q[4].cols)
         self.a_l6.dgrad(d_code.as_rows(n, 1), d, ws=wk.scratch, mask=q[4], mask_mode=ACT_RELU)
+        ops.mark(f"{tag}:aud_bwd_l6")
         dl[4] = d
         for i in range(4, 0, -1):
             dn = wk.mat(f"{tag}:dq{i}", n, q[i - 1].rows, q[i - 1].cols)
             self.a_layers[i].dgrad(dl[i], dn, ws=wk.scratch, mask=q[i - 1], mask_mode=ACT_RELU)
+            ops.mark(f"{tag}:aud_bwd_l{i + 1}")
             dl[i - 1] = dn
         sv["delta"] = dl
         if dX is not None:

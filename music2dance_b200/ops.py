@@ -380,6 +380,35 @@ def set_gru_impl(v):
     call("m2d_set_gru_impl", int(v))
 
 
+class Trace:
+    """Phase marks inside a (graph-captured) train step: `ops.mark(name)` enqueues a one-thread kernel that writes the
+    device's global timer into a slot; disabled (the default) it is a no-op.  tools/step_timeline.py reads the slots
+    after a replay, so the timeline is the one of the timed configuration, not of a profiler run."""
+
+    def __init__(self, device, slots=4096):
+        self.buf = torch.zeros(slots, dtype=torch.int64, device=device)
+        self.names = []
+
+    def mark(self, name):
+        i = len(self.names)
+        assert i < self.buf.numel()
+        self.names.append((name, torch.cuda.current_stream().cuda_stream))
+        call("m2d_timestamp", self.buf.data_ptr() + 8 * i, _stream())
+
+    def read(self):
+        t = self.buf[:len(self.names)].cpu().tolist()
+        return [(n, s, v) for (n, s), v in zip(self.names, t)]
+
+
+TRACE = [None]
+
+
+def mark(name):
+    tr = TRACE[0]
+    if tr is not None:
+        tr.mark(name)
+
+
 def check_device(dev=0):
     call("m2d_check_device", dev)
     return _lib.load().m2d_version()

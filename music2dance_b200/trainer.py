@@ -91,10 +91,12 @@ class Phase3Trainer:
         n = eng.fp.n_live_padded
         self._all_reduce(eng.fp.grad[:n])
         ops.adam(eng.fp.flat, eng.fp.grad, m, v, n, step, float(lr), gscale=1.0 / self.world)
+        ops.mark("adam")
         if eng is self.de and not self.per_iter and self.overlap and self.split_pack:
             eng.net.pack(split=True)          # big late layers re-laid out next to the next iteration's first convolutions
         else:
             eng.net.pack()
+        ops.mark("pack")
 
     def _gen_forward(self, i):
         """Generator forward of critic iteration i (train-mode BatchNorm, no graph kept)."""
@@ -112,6 +114,7 @@ class Phase3Trainer:
         real, audio = self.in_real[i], self.in_audio[i]
         if gen_inline:
             self._gen_forward(i)
+        ops.mark(f"it{i}:start")
         fake_c = self.fake_c[i]
         wk = D.wk
         wk.acc_reset()
@@ -132,6 +135,7 @@ class Phase3Trainer:
             critic_backward_fused(D, fw, B, audio, gamma, self.gp_buf, self.k0, self.k1)
             ops.wgan_scalars(sums, self.gp_buf, B, 1, 1, gamma, 0.0, 0, self.log_c[i])
             D.unpack_grads()
+            ops.mark("unpack")
             if update:
                 self._adam(self.de, self.mD, self.vD, self.stepD, self.cfg["lr_critic"])
             return
@@ -158,6 +162,7 @@ class Phase3Trainer:
         real, audio = self.in_real[i], self.in_audio[i]
         if gen_inline:
             self._gen_forward_update()
+        ops.mark("gu:start")
         wk = D.wk
         wk.acc_reset()
         n2 = 2 * B
@@ -175,7 +180,9 @@ class Phase3Trainer:
         beta, eta = float(self.cfg["beta"]), float(self.cfg["eta"])
         ops.pose_losses(real, self.fake_g, dfake, B, T, O, beta, eta, True, sums[2:4])
         ops.wgan_scalars(sums, None, B, B * T * O, B * (T - 1) * O, beta, eta, 1, self.log_g)
+        ops.mark("gu:critic_done")
         G.backward(dfake.flat_rows())
+        ops.mark("gu:gen_bwd")
         G.unpack_grads()
         if update:
             self._adam(self.ge, self.mG, self.vG, self.stepG, self.cfg["lr_gen"])

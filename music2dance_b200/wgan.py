@@ -151,6 +151,7 @@ def critic_forward_fused(D, X3, audio, B, tag):
     ops.copy2d(svp["code"], sa.cols_slice(0, D.code))
     D.join()
     u, d = D.fusion_fwd(sa, n3, tag)
+    ops.mark(f"{tag}:fwd_end")
     return dict(svp=svp, sva=sva, sa=sa, u=u, d=d)
 
 
@@ -180,6 +181,7 @@ def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f"):
     ddm = Mat(dd, 1, n3, 1)
     u, sa = fw["u"], fw["sa"]
     dh, dsa = D.fusion_bwd(ddm, u, n3, tag)                       # the branches' upstreams first: they start at once
+    ops.mark(f"{tag}:fusion_bwd")
     g1 = ss1 = None
     sva = fw["sva"]
     if not D.ablated:
@@ -195,6 +197,7 @@ def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f"):
             dla = D.audio_bwd(sv2, d_a2, 2 * B, tag, wgrads=False, dX=None)
             gv = g1.batch_slice(B, 2 * B)
             D.l1_dgrad(dla[0].batch_slice(B, 2 * B), gv, B)
+            ops.mark(f"{tag}:aud_bwd_l1")
             ops.rows_sumsq(gv, B, Alen, ss1)
             ops.copy2d(Mat.of(audio.reshape(-1), 1, B, Alen) if not isinstance(audio, Mat) else audio.flat_rows(),
                        Mat(g1.t, 1, B, Alen, Alen))
@@ -211,6 +214,7 @@ def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f"):
     ops.rows_sumsq(g0, B, T * O, ss0)
     D.join()
     ops.gp_finalize(ss0, ss1, B, gp_out, k0, k1)
+    ops.mark(f"{tag}:gp")
     # v = gamma * kappa * g, written where the layer-1 weight gradients read their input
     kg = wk.vec(f"{tag}:kg", 2 * B)
     ops.axpby(k0, None, kg[:B], B, gamma, 0.0)
@@ -243,10 +247,12 @@ def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f"):
                 t = sva["q2"][i].batch_slice(B, 2 * B)
                 l.fwd(x, t, bias=False, ws=wk.scratch, mask=t, mask_mode=ACT_RELU)
                 evs.append(after(s_ta))
+                ops.mark(f"{tag}:aud_tan_l{i + 1}")
                 x = t
             t_a = wk.mat(f"{tag}:t_a", 1, B, code)
             D.a_l6.fwd(x, t_a.as_rows(B, 1), bias=False, ws=wk.scratch)
             ops.copy2d(t_a, t_sa.cols_slice(code, D.F))
+            ops.mark(f"{tag}:aud_tan_l6")
         with torch.cuda.stream(s_wa):
             # one weight-gradient GEMM per audio layer over the 2B stacked entries; biases from the Wasserstein half
             x = g1
@@ -256,11 +262,13 @@ def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f"):
                 if par:
                     s_wa.wait_event(evs[i])
                 l.wgrad(dla[i], x, ws_a, scale=1.0, beta=0.0, bias=False)
+                ops.mark(f"{tag}:aud_wg_l{i + 1}")
                 x = sva["q2"][i]
             ops.colsum(rows(d_a2, 0, B), D.a_l6.gb, A1(D.a_l6.Cout), scale=1.0, beta=0.0)
             if par:
                 s_wa.wait_event(evs[len(D.a_layers)])
             D.a_l6.wgrad(d_a2.as_rows(2 * B, 1), x, ws_a, scale=1.0, beta=0.0, bias=False)
+            ops.mark(f"{tag}:aud_wg_l6")
     # pose branch: tangent in place on the current stream, weight gradients over all 3B entries on s_w
     Xi = rows(X3, 0, B)
     ops.scale_rows(g0, kg[:B], Xi, B, T * O)                       # interpolates are no longer needed: X3[0:B] = v0
@@ -291,6 +299,7 @@ def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f"):
     t_s = wk.mat(f"{tag}:t_s", 1, B, code)
     D.s_fconv.fwd(x, t_s.as_rows(B, 1), bias=False, ws=wk.scratch)
     ops.copy2d(t_s, t_sa.cols_slice(0, code))
+    ops.mark(f"{tag}:pose_tan_end")
     with torch.cuda.stream(s_wp):
         ws_p = wk.scratch
         for conv, dl, x_in, ev in pending:
@@ -299,6 +308,7 @@ def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f"):
             if par:
                 s_wp.wait_event(ev)
             conv.wgrad(dl, x_in, ws_p, scale=1.0, beta=0.0, bias=False)
+        ops.mark(f"{tag}:pose_wg_end")
     if par and not D.ablated:
         main.wait_stream(s_ta)
     # fusion MLP: penalty part through the tangent of the codes
@@ -310,6 +320,7 @@ def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f"):
         if not D.ablated:
             main.wait_stream(s_wa)
         main.wait_stream(s_wp)
+    ops.mark(f"{tag}:bwd_end")
 
 
 def wasserstein_backward(D, fw, r0, nR, signs, B, tag, beta, dX_rows=None, dX=None, param_grads=True):
