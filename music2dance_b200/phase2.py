@@ -276,6 +276,9 @@ class Phase2Trainer:
     """Fused phase2 step (phase2/train.py:131-171) on explicit random inputs (noise, alpha)."""
 
     GEN_NET, CRITIC_NET = _GenNet, _CriticNet
+    # phase2/train.py:88-89,179-180: both Adam optimisers sit behind MultiStepLR(milestones, gamma=0.8), stepped once
+    # per generator update (after the optimiser step)
+    LR_MILESTONES, LR_GAMMA = (10000, 35000, 50000), 0.8
 
     def __init__(self, gen, critic, cfg, batch_size):
         self.cfg, self.B = cfg, batch_size
@@ -290,14 +293,21 @@ class Phase2Trainer:
         self.stepG = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.log, self.gp = torch.zeros(8, **f), torch.zeros(1, **f)
         self.fake = None
+        self.sched_steps = 0                       # scheduler.step() calls so far (= generator updates applied)
 
     def _dev(self, t):
         return t.to(self.dev, torch.float32).contiguous()
 
+    def lr_factor(self):
+        """MultiStepLR: gamma ** (number of milestones <= scheduler steps taken)."""
+        return self.LR_GAMMA ** sum(1 for ms in self.LR_MILESTONES if ms <= self.sched_steps)
+
     def _adam(self, net, m, v, step, lr):
         n = net.fp.n_live_padded
-        ops.adam(net.fp.flat, net.fp.grad, m, v, n, step, float(lr))
+        ops.adam(net.fp.flat, net.fp.grad, m, v, n, step, float(lr) * self.lr_factor())
         net.pack()
+        if net is self.Gn:
+            self.sched_steps += 1                  # scheduler_critic.step(); scheduler_gen.step() (train.py:179-180)
 
     def _ensure(self):
         for net in (self.Gn, self.Dn):

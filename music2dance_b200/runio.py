@@ -72,7 +72,14 @@ def write_model_descriptions(run_dir, gen, critic):
 
 def train_scalars(logs, err_l1=None):
     """train.py:239-243 — tag -> value with the reference's sign flips (``loss_critic`` and ``w_dist`` are logged
-    negated).  `logs` = the dict ``Phase3Trainer.logs()`` returns (loss_critic, gp, w_dist, loss_gen, l1)."""
+    negated).  `logs` = what ``Phase3Trainer.logs()`` returns: ``{'critic': [one dict per critic iteration],
+    'gen': {...}}``; the reference logs on the iteration where ``total_iterations % n_critic_steps == 0``, i.e. the
+    LAST critic iteration of the train step (train.py:218-219), together with that step's generator update.  A flat
+    dict with the five keys is accepted too."""
+    if "critic" in logs and "gen" in logs:
+        c, g = logs["critic"][-1], logs["gen"]
+        logs = {"loss_critic": c["loss_critic"], "gp": c["gp"], "w_dist": c["w_dist"],
+                "loss_gen": g["loss_gen"], "l1": g["l1"]}
     out = OrderedDict()
     out["loss_critic"] = -float(logs["loss_critic"])
     out["loss_gen"] = float(logs["loss_gen"])

@@ -149,3 +149,26 @@ def test_cuda_phase2_batch24_vs_oracle():
     logs = tr.generator_update(real_bt, noise, update=True)
     scalar_check(logs["loss_gen"], o["loss_gen"], 2e-2, "loss_gen after one critic Adam step")
     scalar_check(logs["tv"], o["tv"], 1e-3, "tv")
+
+
+def test_lr_schedule_matches_multisteplr():
+    """phase2/train.py:88-89,179-180: MultiStepLR(milestones, gamma=0.8) stepped once per generator update.  Host-only:
+    the trainer's factor against torch's scheduler (milestones scaled down so that the loop is short)."""
+    from music2dance_b200.phase2 import Phase2Trainer
+
+    class T(Phase2Trainer):
+        LR_MILESTONES = (10, 35, 50)
+
+        def __init__(self):              # no device needed for the schedule
+            self.sched_steps = 0
+
+    t = T()
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.Adam([p], lr=2e-4)
+    sch = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[10, 35, 50], gamma=0.8)
+    for _ in range(60):
+        assert abs(2e-4 * t.lr_factor() - opt.param_groups[0]["lr"]) < 1e-12, t.sched_steps
+        opt.step()
+        sch.step()
+        t.sched_steps += 1
+    assert Phase2Trainer.LR_MILESTONES == (10000, 35000, 50000) and Phase2Trainer.LR_GAMMA == 0.8

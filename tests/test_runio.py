@@ -81,6 +81,19 @@ def test_scalar_tags_and_signs():
     assert w.rows[-1] == ("l1_loss_val", 1.0, 40)
 
 
+def test_scalars_from_trainer_logs_structure():
+    """`Phase3Trainer.logs()` returns {'critic': [nc dicts], 'gen': {...}} (trainer.LOG_CRITIC / LOG_GEN): the scalars
+    the reference writes at train.py:239-243 come from the LAST critic iteration and the generator update."""
+    from music2dance_b200.trainer import LOG_CRITIC, LOG_GEN
+    nc = 8
+    crit = [dict(zip(LOG_CRITIC, [-(i + 1.0), 0.1 * i, -0.5 * i, 1.0, 2.0])) for i in range(nc)]
+    gen = dict(zip(LOG_GEN, [12.0, 0.75, 0.0, 1.0, 2.0]))
+    w = _Writer()
+    runio.log_train_scalars(w, {"critic": crit, "gen": gen}, 8)
+    assert w.rows == [("loss_critic", 8.0, 8), ("loss_gen", 12.0, 8), ("gp", 0.1 * 7, 8), ("w_dist", 3.5, 8),
+                      ("l1_loss_train", 0.75, 8)]
+
+
 def test_checkpoint_files_round_trip_with_reference_keys(tmp_path):
     """Files written at the reference cadence hold the drop-in modules' state_dict (= the reference's keys, SURVEY
     Appendix A) and load back strictly."""
