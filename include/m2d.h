@@ -297,6 +297,37 @@ int m2d_slice_audio(const float* audio, float* out, int nseq, int A, int nwin, i
 int m2d_adam(float* p, const float* g, float* m, float* v, long long n, int* step,
              float lr, float beta1, float beta2, float eps, float gscale, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Optimiser step fused with the weight re-layouts.  ONE launch applies torch.optim.Adam (train.py:102-103,216,237;
+ * same arithmetic as m2d_adam) to every parameter a table covers AND rewrites the packed / pre-tiled copies of the
+ * convolution weights that m2d_rowconv reads (what m2d_pack_batch produces), reading the weight gradients in the
+ * tap-major layout m2d_wgrad(packed = 1) leaves them in — so "gradient unpack -> Adam -> re-layout" is one pass over
+ * the parameters instead of three dependent launches.
+ *
+ * The table (DEVICE memory, built once: all pointers are stable) has one item per tile of a weight tensor
+ * (Cout, Cin, k): rows [co0, co0+nco) x channels [ci0, ci0+nci) x taps [t0, t0+nt), nco <= 32, or per plain range of
+ * `flat_n` floats (biases, BatchNorm, GRU recurrent weights, ...).  Each thread block stages its tile in shared
+ * memory (nco * (nci * (nt | 1) | 1) floats <= `smem_floats`), so every global access — gradient (tap-major),
+ * p / m / v (parameter layout), each packed destination — is made in that array's own contiguous order.
+ * pk[i] = the re-layouts of the tile (kinds and destination layouts exactly as in m2d_pack_desc).
+ * counters[0] = Adam step count (device int, incremented by the launch: graph-replay safe), counters[1] = scratch (0).
+ * ---------------------------------------------------------------------- */
+typedef struct {
+    float* dst; float* dst_tiled;
+    int kind, stride, reserved, pad_;
+} m2d_adam_pack_out;
+typedef struct {
+    float* p; float* m; float* v; const float* g;    /* item base pointers: the LAYER's slices (flat: the range's) */
+    long long flat_n;                                 /* > 0: plain range, the fields below are ignored */
+    int Cout, Cin, k;
+    int g_packed;                                     /* 1: g is tap-major [co, t*Cin + ci]; 0: parameter layout */
+    int co0, nco, ci0, nci, t0, nt;
+    int n_pack, pad_;
+    m2d_adam_pack_out pk[3];
+} m2d_adam_item;
+int m2d_adam_pack(const m2d_adam_item* items, int n, int smem_floats, int* counters, float lr, float beta1,
+                  float beta2, float eps, float gscale, void* stream);
+
 /* Diagnostics (tools/step_timeline.py): *slot = %globaltimer (ns) when `stream` reaches this point; graph-capturable,
  * so the replayed train step can be cut into phases without a profiler attached. */
 int m2d_timestamp(unsigned long long* slot, void* stream);

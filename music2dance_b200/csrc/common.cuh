@@ -47,6 +47,30 @@ __host__ __device__ inline long long tiled_index(int n, int t, int ci, int T, in
     return blk * tiled_block_floats(R) + nl * 32 + ((((kk >> 2) ^ (nl & 7)) << 2) | (kk & 3));
 }
 
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+// hi / lo values of element `v` into the tiled block that holds float index `pidx` (the hi plane).  TF32X3: lo plane
+// = rna_tf32(v - hi) at pidx + R*32.  TF32_BF16 (`mixed`): the lo plane holds, per 128-byte row, the weight side of
+// the BF16 cross-term contraction [bf16(lo) x 32 | bf16(hi) x 32] in the same 16-byte-chunk swizzle.
+__device__ __forceinline__ void store_tiled_split(float* dst_tiled, long long pidx, int R, float v, bool mixed) {
+    const float h = rna_tf32(v);
+    dst_tiled[pidx] = h;
+    if (!mixed) {
+        dst_tiled[pidx + R * 32] = rna_tf32(v - h);
+        return;
+    }
+    const long long blk = pidx / (64LL * R);
+    const int f = (int)(pidx - blk * 64LL * R);                 // float index inside the hi plane
+    const int nl = f >> 5, j = ((f >> 2) & 7) ^ (nl & 7), kk = 4 * j + (f & 3);
+    __nv_bfloat16* plane = reinterpret_cast<__nv_bfloat16*>(dst_tiled + blk * 64LL * R + R * 32);
+    const int sw = nl & 7;
+    plane[nl * 64 + ((((kk >> 3) ^ sw) << 3) | (kk & 7))] = __float2bfloat16_rn(v - h);
+    plane[nl * 64 + (((((32 + kk) >> 3) ^ sw) << 3) | (kk & 7))] = __float2bfloat16_rn(h);
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == M2D_ACT_RELU) return v > 0.f ? v : 0.f;
     if (act == M2D_ACT_LEAKY) return v > 0.f ? v : 0.2f * v;

@@ -524,29 +524,6 @@ __global__ void pack_bwd_kernel(const float* __restrict__ w, float* __restrict__
 // the exact fp32 copy (dst), each entry may request the 3xTF32 operand split of the same matrix
 // (dst_tiled: pre-tiled in the tensor core's shared-memory image, see m2d_rowconv_args.w_tiled) consumed by
 // the tensor-core kernels.
-__device__ __forceinline__ float rna_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-// hi / lo values of element `v` into the tiled block that holds float index `pidx` (the hi plane).  TF32X3: lo plane
-// = rna_tf32(v - hi) at pidx + R*32.  TF32_BF16 (`mixed`): the lo plane holds, per 128-byte row, the weight side of
-// the BF16 cross-term contraction [bf16(lo) x 32 | bf16(hi) x 32] in the same 16-byte-chunk swizzle.
-__device__ __forceinline__ void store_tiled_split(float* dst_tiled, long long pidx, int R, float v, bool mixed) {
-    const float h = rna_tf32(v);
-    dst_tiled[pidx] = h;
-    if (!mixed) {
-        dst_tiled[pidx + R * 32] = rna_tf32(v - h);
-        return;
-    }
-    const long long blk = pidx / (64LL * R);
-    const int f = (int)(pidx - blk * 64LL * R);                 // float index inside the hi plane
-    const int nl = f >> 5, j = ((f >> 2) & 7) ^ (nl & 7), kk = 4 * j + (f & 3);
-    __nv_bfloat16* plane = reinterpret_cast<__nv_bfloat16*>(dst_tiled + blk * 64LL * R + R * 32);
-    const int sw = nl & 7;
-    plane[nl * 64 + ((((kk >> 3) ^ sw) << 3) | (kk & 7))] = __float2bfloat16_rn(v - h);
-    plane[nl * 64 + (((((32 + kk) >> 3) ^ sw) << 3) | (kk & 7))] = __float2bfloat16_rn(h);
-}
 __global__ void __launch_bounds__(256) pack_batch_kernel(const m2d_pack_desc* __restrict__ table, const bool mixed) {
     const m2d_pack_desc d = table[blockIdx.y];
     const float* __restrict__ w = d.w;

@@ -13,6 +13,14 @@ from .nets import CriticNet, GeneratorNet
 _DEAD = re.compile(r"decoder\.blocks\.\d+\.(fc1|bn1)\.(weight|bias)$")   # Q1: never receive a gradient
 
 
+class GradDict(OrderedDict):
+    """name -> gradient view in the parameter layout; `.packed[name]` -> the tap-major buffer of the same weight."""
+
+    def __init__(self):
+        super().__init__()
+        self.packed = {}
+
+
 class FlatParams:
     """Re-points every parameter of `module` into one flat fp32 buffer (live
     parameters first, the dead LinearBlock branch last) with a matching flat gradient
@@ -24,7 +32,13 @@ class FlatParams:
         assert named, "module has no parameters"
         dev = named[0][1].device
         assert dev.type == "cuda", "music2dance_b200 runs on CUDA devices only (no CPU fallback)"
-        live = [(n, p) for n, p in named if not _DEAD.search(n)]
+        # convolution weights whose gradient the weight-gradient GEMM leaves tap-major (nets.ConvLayer: k > 1 and
+        # Cin > 1) come last among the live parameters: [0, n_plain_padded) of the gradient buffer is then everything
+        # Adam / the all-reduce read in the parameter layout, and `gpk` (same sizes, same order) holds the rest tap-major
+        is_packed = lambda p: p.dim() == 3 and p.shape[1] > 1 and p.shape[2] > 1
+        live_all = [(n, p) for n, p in named if not _DEAD.search(n)]
+        live = [(n, p) for n, p in live_all if not is_packed(p)] + [(n, p) for n, p in live_all if is_packed(p)]
+        n_plain = sum(1 for _, p in live_all if not is_packed(p))
         dead = [(n, p) for n, p in named if _DEAD.search(n)]
         self.order = live + dead
         self.n_live = sum(p.numel() for _, p in live)
@@ -35,9 +49,11 @@ class FlatParams:
             offs.append(o)
             o += (p.numel() + 3) // 4 * 4
         self.n_live_padded = offs[len(live)] if dead else o
+        self.n_plain_padded = offs[n_plain] if n_plain < len(live) else self.n_live_padded
         self.flat = torch.zeros(o, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(o, dtype=torch.float32, device=dev)
-        self.P, self.G, self.params = OrderedDict(), OrderedDict(), OrderedDict()
+        self.gpk = torch.zeros(max(self.n_live_padded - self.n_plain_padded, 4), dtype=torch.float32, device=dev)
+        self.P, self.G, self.params = OrderedDict(), GradDict(), OrderedDict()
         with torch.no_grad():
             for (n, p), off in zip(self.order, offs):
                 view = self.flat[off:off + p.numel()].view(p.shape)
@@ -47,6 +63,9 @@ class FlatParams:
                 self.params[n] = p
                 if not _DEAD.search(n):
                     self.G[n] = self.grad[off:off + p.numel()].view(p.shape)
+                    if is_packed(p):
+                        q = off - self.n_plain_padded
+                        self.G.packed[n] = self.gpk[q:q + p.numel()]
         # BatchNorm step counters: views of one int64 buffer so that a forward bumps them all at once
         nbt = [(n, b) for n, b in module.named_buffers() if n.endswith("num_batches_tracked")]
         if nbt:
@@ -70,6 +89,108 @@ class FlatParams:
 
     def version(self):
         return sum(p._version for p in self.params.values())
+
+    def grad_buffers(self):
+        """What an optimiser step reads, as flat tensors (the data-parallel all-reduce runs over exactly these):
+        the parameter-layout gradients of everything but the tap-major convolution weights, and the tap-major arena."""
+        out = [self.grad[:self.n_plain_padded]]
+        if self.n_live_padded > self.n_plain_padded:
+            out.append(self.gpk[:self.n_live_padded - self.n_plain_padded])
+        return out
+
+
+class AdamPack:
+    """Device table of m2d_adam_pack items for (a subset of) a network's live parameters: convolution / linear weights
+    that have packed copies become tiles (gradient read tap-major where the weight-gradient GEMM wrote it that way,
+    re-layouts written from the same shared-memory tile); everything else is a plain range.  `m`, `v`: flat Adam moment
+    buffers laid out like `fp.flat`.  `only` / `exclude`: lists of ConvLayer objects selecting a subset of the weights
+    (plain ranges belong to the table built with only=None)."""
+
+    TILE = 800            # floats of one output row's slice held in shared memory (x 32 rows)
+    FLAT_CHUNK = 8192
+
+    def __init__(self, fp, net, m, v, only=None, exclude=None):
+        import numpy as np
+        dev = fp.device
+        convs = {c.w.data_ptr(): c for c in net.convs() if c.gw is not None}
+        sel = None if only is None else {id(c) for c in only}
+        exc = set() if exclude is None else {id(c) for c in exclude}
+        base = fp.flat.data_ptr()
+        out_dt = np.dtype([("dst", "<u8"), ("dst_tiled", "<u8"), ("kind", "<i4"), ("stride", "<i4"),
+                           ("reserved", "<i4"), ("pad_", "<i4")])
+        dt = np.dtype([("p", "<u8"), ("m", "<u8"), ("v", "<u8"), ("g", "<u8"), ("flat_n", "<i8"),
+                       ("Cout", "<i4"), ("Cin", "<i4"), ("k", "<i4"), ("g_packed", "<i4"),
+                       ("co0", "<i4"), ("nco", "<i4"), ("ci0", "<i4"), ("nci", "<i4"), ("t0", "<i4"), ("nt", "<i4"),
+                       ("n_pack", "<i4"), ("pad_", "<i4"), ("pk", out_dt, (3,))])
+        assert dt.itemsize == 8 * 5 + 4 * 12 + 3 * 32
+        items, flats = [], []
+        self.smem_floats = 0
+        ptr = lambda t: 0 if t is None else t.data_ptr()
+        n_live = fp.n_live_padded
+        for name, prm in fp.params.items():
+            off = (prm.data_ptr() - base) // 4
+            if off >= n_live:
+                continue                                          # dead LinearBlock branch (Q1): no gradient, no update
+            conv = convs.get(prm.data_ptr())
+            if conv is None or prm.dim() < 2:
+                if sel is None:
+                    flats.append((off, prm.numel()))
+                continue
+            if (sel is not None and id(conv) not in sel) or id(conv) in exc:
+                continue
+            Cout, Cin, k = conv.Cout, conv.Cin, conv.k
+            packs = conv.pack_entries()
+            assert len(packs) <= 3
+            g_packed = conv.gwp is not None
+            g_ptr = conv.gwp.data_ptr() if g_packed else fp.grad.data_ptr() + 4 * off
+            parts = -(-k // 25)
+            nt_full = -(-k // parts)
+            ntp = nt_full | 1
+            if Cin == 1:
+                nci_full = 1
+            else:
+                nci_full = min(Cin, max(32, (self.TILE // ntp) // 32 * 32))
+            for co0 in range(0, Cout, 32):
+                nco = min(32, Cout - co0)
+                for ci0 in range(0, Cin, nci_full):
+                    nci = min(nci_full, Cin - ci0)
+                    for t0 in range(0, k, nt_full):
+                        nt = min(nt_full, k - t0)
+                        it = np.zeros((), dtype=dt)
+                        it["p"], it["m"], it["v"] = prm.data_ptr(), m.data_ptr() + 4 * off, v.data_ptr() + 4 * off
+                        it["g"], it["flat_n"] = g_ptr, 0
+                        it["Cout"], it["Cin"], it["k"], it["g_packed"] = Cout, Cin, k, int(g_packed)
+                        it["co0"], it["nco"], it["ci0"], it["nci"], it["t0"], it["nt"] = co0, nco, ci0, nci, t0, nt
+                        it["n_pack"] = len(packs)
+                        for j, e in enumerate(packs):
+                            it["pk"][j] = (ptr(e[1]), ptr(e[2]), e[7], e[6], e[8] if len(e) > 8 else 0, 0)
+                        items.append(it)
+                        self.smem_floats = max(self.smem_floats, nco * ((nci * (nt | 1)) | 1))
+        # plain ranges: adjacent parameters (16-byte aligned slots, zero padding between them) merge into runs
+        flats.sort()
+        runs = []
+        for off, n in flats:
+            end = off + (n + 3) // 4 * 4
+            if runs and runs[-1][1] == off:
+                runs[-1][1] = end
+            else:
+                runs.append([off, end])
+        for lo, hi in runs:
+            for c0 in range(lo, hi, self.FLAT_CHUNK):
+                n = min(self.FLAT_CHUNK, hi - c0)
+                it = np.zeros((), dtype=dt)
+                it["p"], it["m"], it["v"] = base + 4 * c0, m.data_ptr() + 4 * c0, v.data_ptr() + 4 * c0
+                it["g"], it["flat_n"] = fp.grad.data_ptr() + 4 * c0, n
+                items.append(it)
+        self.n = len(items)
+        arr = np.array(items, dtype=dt) if items else np.zeros(0, dtype=dt)
+        self.table = torch.from_numpy(arr.view(np.uint8).reshape(-1).copy()).to(dev) if self.n else None
+        self.counters = torch.zeros(2, dtype=torch.int32, device=dev)      # [0] Adam step count, [1] finished blocks
+        self.keep = (m, v)
+
+    def step(self, lr, gscale=1.0):
+        if self.n:
+            ops.adam_pack(self.table, self.n, self.smem_floats, self.counters, float(lr), gscale=gscale)
 
 
 class Engine:

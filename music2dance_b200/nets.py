@@ -100,7 +100,7 @@ class ConvLayer:
     """Conv1d / Linear as row-convolution GEMMs.  `w` (Cout,Cin,k) or (Cout,Cin),
     `b` (Cout,), `gw`/`gb` same-shaped gradient tensors (views of a flat buffer)."""
 
-    def __init__(self, name, w, b, gw, gb, Cin, Cout, k=1, stride=1, pad=0, Lin=1, need_dgrad=True):
+    def __init__(self, name, w, b, gw, gb, Cin, Cout, k=1, stride=1, pad=0, Lin=1, need_dgrad=True, gwp=None):
         self.name, self.w, self.b, self.gw, self.gb = name, w, b, gw, gb
         self.Cin, self.Cout, self.k, self.s, self.p, self.Lin = Cin, Cout, k, stride, pad, Lin
         self.Lout = conv_out_len(Lin, k, stride, pad)
@@ -126,7 +126,9 @@ class ConvLayer:
             poff += tf(Cin, Trho, Cout) if Trho > 0 else 0
         # weight gradients of real convolutions are produced tap-major [co, t*Cin + ci] (coalesced stores) and
         # turned into the parameter layout by one batched kernel per network (unpack_entries)
-        self.gwp = z(n) if (gw is not None and k > 1 and Cin > 1) else None
+        # (`gwp` given: a slice of the network's tap-major gradient arena, engine.FlatParams.gpk)
+        self.gwp = (gwp if gwp is not None else z(n)) if (gw is not None and k > 1 and Cin > 1) else None
+        assert gwp is None or (self.gwp is gwp and gwp.numel() == n)
         if self.merged:
             self.cmax = (stride - 1 + pad) // stride
             self.Tm = max(-(-(k - (r + pad) % stride) // stride) + self.cmax - (r + pad) // stride for r in range(stride))
@@ -265,7 +267,8 @@ class BNLayer:
 
 def _conv_from(P, G, name, Cin, Cout, k, s, p, Lin, need_dgrad=True):
     return ConvLayer(name, P[name + ".weight"], P[name + ".bias"], G.get(name + ".weight"),
-                     G.get(name + ".bias"), Cin, Cout, k, s, p, Lin, need_dgrad)
+                     G.get(name + ".bias"), Cin, Cout, k, s, p, Lin, need_dgrad,
+                     gwp=getattr(G, "packed", {}).get(name + ".weight"))
 
 
 class ConvBNAct:
@@ -806,6 +809,16 @@ class CriticNet:
         self.s_pack.wait_stream(cur)
         with torch.cuda.stream(self.s_pack):
             ops.pack_batch(*tabs[1])
+        self._late_pack = True
+
+    def late_fork(self, fn):
+        """Run `fn` (the optimiser step of audio_d.l5 / l6) on the re-layout side stream, ordered after the current
+        stream; the next audio_fwd joins it right before l5 (same protocol as pack_late_fork)."""
+        self._split_tabs()
+        cur = torch.cuda.current_stream(self.dev)
+        self.s_pack.wait_stream(cur)
+        with torch.cuda.stream(self.s_pack):
+            fn()
         self._late_pack = True
 
     def unpack_grads(self):

@@ -22,6 +22,7 @@ import os
 import torch
 
 from . import dp, ops
+from .engine import AdamPack
 from .ops import Mat
 from .nets import ACT_ID
 from .wgan import (critic_backward_fused, critic_forward, critic_forward_fused, gradient_penalty_pass, rows,
@@ -67,8 +68,18 @@ class Phase3Trainer:
         nD, nG = self.de.fp.n_live_padded, self.ge.fp.n_live_padded
         self.mD, self.vD = torch.zeros(nD, **f), torch.zeros(nD, **f)
         self.mG, self.vG = torch.zeros(nG, **f), torch.zeros(nG, **f)
-        self.stepD = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.stepG = torch.zeros(1, dtype=torch.int32, device=dev)
+        # optimiser step fused with the weight re-layouts (m2d_adam_pack): one table per launch.  The critic's two
+        # big late layers (audio_d.l5 / l6, 68 % of its parameters) have their own table so that their update runs on
+        # a side stream next to the next iteration's first convolutions (CriticNet.pack_late_fork protocol)
+        with torch.cuda.device(dev):
+            self.apG = AdamPack(self.ge.fp, self.G, self.mG, self.vG)
+            if self.D.can_split_pack():
+                late = [self.D.a_layers[4], self.D.a_l6]
+                self.apD = AdamPack(self.de.fp, self.D, self.mD, self.vD, exclude=late)
+                self.apD_late = AdamPack(self.de.fp, self.D, self.mD, self.vD, only=late)
+            else:
+                self.apD = AdamPack(self.de.fp, self.D, self.mD, self.vD)
+                self.apD_late = None
         self.gp_buf = torch.zeros(1, **f)
         self.k0, self.k1 = torch.zeros(B, **f), torch.zeros(B, **f)
         self.use_graphs = use_graphs
@@ -83,20 +94,29 @@ class Phase3Trainer:
         self.fused_backward = os.environ.get("M2D_FUSED_BWD", "1") != "0"
 
     # ------------------------------------------------------------------ pieces
-    def _all_reduce(self, flat):
+    def _all_reduce(self, eng):
+        """Sum of the gradient buffers an optimiser step reads (engine.FlatParams.grad_buffers) over the ranks."""
         if self.world > 1:
-            dp.all_reduce_sum_(flat, self.pg)
+            for t in eng.fp.grad_buffers():
+                dp.all_reduce_sum_(t, self.pg)
 
-    def _adam(self, eng, m, v, step, lr):
-        n = eng.fp.n_live_padded
-        self._all_reduce(eng.fp.grad[:n])
-        ops.adam(eng.fp.flat, eng.fp.grad, m, v, n, step, float(lr), gscale=1.0 / self.world)
-        ops.mark("adam")
-        if eng is self.de and not self.per_iter and self.overlap and self.split_pack:
-            eng.net.pack(split=True)          # big late layers re-laid out next to the next iteration's first convolutions
-        else:
-            eng.net.pack()
-        ops.mark("pack")
+    def _adam(self, eng, lr, late_fork=None):
+        """Adam + re-layout of one network (gradients are read where the kernels left them: tap-major for the
+        convolution weights).  late_fork: run the critic's late table on the re-layout side stream (True), inline
+        (False), or decide from the step structure (None)."""
+        gs = 1.0 / self.world
+        if eng is self.ge:
+            self.apG.step(lr, gs)
+            ops.mark("adam_pack")
+            return
+        if self.apD_late is not None:
+            fork = (not self.per_iter and self.overlap and self.split_pack) if late_fork is None else late_fork
+            if fork:
+                self.D.late_fork(lambda: self.apD_late.step(lr, gs))
+            else:
+                self.apD_late.step(lr, gs)
+        self.apD.step(lr, gs)
+        ops.mark("adam_pack")
 
     def _gen_forward(self, i):
         """Generator forward of critic iteration i (train-mode BatchNorm, no graph kept)."""
@@ -134,10 +154,10 @@ class Phase3Trainer:
             ops.sum_(rows(d, 2 * B, n3), B, sums[1:2])
             critic_backward_fused(D, fw, B, audio, gamma, self.gp_buf, self.k0, self.k1)
             ops.wgan_scalars(sums, self.gp_buf, B, 1, 1, gamma, 0.0, 0, self.log_c[i])
-            D.unpack_grads()
-            ops.mark("unpack")
             if update:
-                self._adam(self.de, self.mD, self.vD, self.stepD, self.cfg["lr_critic"])
+                self._adam(self.de, self.cfg["lr_critic"])
+            elif not self.per_iter:
+                D.unpack_grads()              # caller wants the gradients in the parameter layout (tests, tools)
             return
         fw = critic_forward(D, X3, None if D.ablated else audio, n3, B, "c", groups=3)
         sums = wk.acc_slot(4)
@@ -151,9 +171,10 @@ class Phase3Trainer:
             wasserstein_backward(D, fw, B, 2 * B, (-1.0, 1.0), B, "c:w", beta=0.0)
         gradient_penalty_pass(D, fw, B, "c:gp", gamma, 1.0, self.gp_buf, self.k0, self.k1, before_wgrads=D.join_w)
         ops.wgan_scalars(sums, self.gp_buf, B, 1, 1, gamma, 0.0, 0, self.log_c[i])
-        D.unpack_grads()
         if update:
-            self._adam(self.de, self.mD, self.vD, self.stepD, self.cfg["lr_critic"])
+            self._adam(self.de, self.cfg["lr_critic"])
+        elif not self.per_iter:
+            D.unpack_grads()
 
     def generator_update(self, update=True, gen_inline=True):
         """train.py:222-237 on the last staged batch."""
@@ -183,13 +204,16 @@ class Phase3Trainer:
         ops.mark("gu:critic_done")
         G.backward(dfake.flat_rows())
         ops.mark("gu:gen_bwd")
-        G.unpack_grads()
         if update:
-            self._adam(self.ge, self.mG, self.vG, self.stepG, self.cfg["lr_gen"])
+            self._adam(self.ge, self.cfg["lr_gen"])
+        elif not self.per_iter:
+            G.unpack_grads()
 
     # ------------------------------------------------------------------ step
     def _state(self):
-        ts = [self.ge.fp.flat, self.de.fp.flat, self.mD, self.vD, self.mG, self.vG, self.stepD, self.stepG]
+        ts = [self.ge.fp.flat, self.de.fp.flat, self.mD, self.vD, self.mG, self.vG, self.apG.counters, self.apD.counters]
+        if self.apD_late is not None:
+            ts.append(self.apD_late.counters)
         ts += [b for _, b in self.gen.named_buffers()]
         return ts
 
@@ -228,7 +252,7 @@ class Phase3Trainer:
                     return
                 main = torch.cuda.current_stream()
                 if split and i > 0:
-                    self.D.pack_late_fork()
+                    late_fork()
                 self.s_gen.wait_stream(main)
                 with torch.cuda.stream(self.s_gen):
                     if i + 1 < self.nc:
@@ -238,18 +262,18 @@ class Phase3Trainer:
                 self.critic_iteration(i, update=False, gen_inline=False)
                 main.wait_stream(self.s_gen)
 
+            # the late critic table (audio_d.l5 / l6) is not part of the Adam graph: the NEXT graph that evaluates the
+            # critic forks it at its start, so it overlaps that graph's first convolutions
             def adam_d():
-                ops.adam(self.de.fp.flat, self.de.fp.grad, self.mD, self.vD, self.de.fp.n_live_padded,
-                         self.stepD, float(self.cfg["lr_critic"]), gscale=1.0 / self.world)
-                if split:
-                    self.D.pack_early()
-                else:
-                    self.de.net.pack()
+                self.apD.step(self.cfg["lr_critic"], 1.0 / self.world)
+                if not split and self.apD_late is not None:
+                    self.apD_late.step(self.cfg["lr_critic"], 1.0 / self.world)
 
             def adam_g():
-                ops.adam(self.ge.fp.flat, self.ge.fp.grad, self.mG, self.vG, self.ge.fp.n_live_padded,
-                         self.stepG, float(self.cfg["lr_gen"]), gscale=1.0 / self.world)
-                self.ge.net.pack()
+                self.apG.step(self.cfg["lr_gen"], 1.0 / self.world)
+
+            def late_fork():
+                self.D.late_fork(lambda: self.apD_late.step(self.cfg["lr_critic"], 1.0 / self.world))
 
             if self.overlap:
                 graphs.append(("p", cap(lambda: self._gen_forward(0))))
@@ -258,7 +282,7 @@ class Phase3Trainer:
                 graphs.append(("cu", cap(adam_d)))
             def gen_update():
                 if split:
-                    self.D.pack_late_fork()                  # weights of the last critic Adam step
+                    late_fork()                              # audio_d.l5 / l6 update of the last critic Adam step
                 self.generator_update(update=False, gen_inline=not self.overlap)
 
             graphs.append(("g", cap(gen_update)))
@@ -306,9 +330,33 @@ class Phase3Trainer:
         self.in_alpha.copy_(alpha.reshape(self.in_alpha.shape), non_blocking=non_blocking)
         self.in_noise_g.copy_(noise_g.reshape(self.in_noise_g.shape), non_blocking=non_blocking)
 
+    def _ensure_packed(self):
+        """Parameters changed behind the trainer's back (load_state_dict to resume, an external optimiser step):
+        refresh the packed weight copies the kernels read before the next step (host-side version check)."""
+        for eng in (self.ge, self.de):
+            v = eng.fp.version()
+            if v != eng.packed_version:
+                eng.net.pack()
+                eng.packed_version = v
+
+    def optimizer_state(self):
+        """Adam state for checkpoint / resume (moments laid out like the flat parameter buffers)."""
+        return {"mD": self.mD.clone(), "vD": self.vD.clone(), "mG": self.mG.clone(), "vG": self.vG.clone(),
+                "stepD": int(self.apD.counters[0]), "stepG": int(self.apG.counters[0])}
+
+    def load_optimizer_state(self, st):
+        with torch.no_grad():
+            for k in ("mD", "vD", "mG", "vG"):
+                getattr(self, k).copy_(st[k])
+            self.apD.counters[0] = int(st["stepD"])
+            if self.apD_late is not None:
+                self.apD_late.counters[0] = int(st["stepD"])
+            self.apG.counters[0] = int(st["stepG"])
+
     def train_step(self):
         """Run one train step on the staged inputs (asynchronous; read `logs()` to sync)."""
         with torch.cuda.device(self.dev):
+            self._ensure_packed()
             if not self.use_graphs:
                 self._run_eager()
                 return
@@ -317,9 +365,9 @@ class Phase3Trainer:
             for kind, g in self.graphs:
                 g.replay()
                 if kind == "c":
-                    self._all_reduce(self.de.fp.grad[:self.de.fp.n_live_padded])
+                    self._all_reduce(self.de)
                 elif kind == "g":
-                    self._all_reduce(self.ge.fp.grad[:self.ge.fp.n_live_padded])
+                    self._all_reduce(self.ge)
 
     def validate(self, real, audio, noise):
         """Validation pass of phase3/train.py:245-261: eval-mode generator (BatchNorm running statistics) on one

@@ -440,3 +440,65 @@ def test_adam_matches_torch(lib):
         lib.adam(p, (gr * 4).to(DEV), m, v, n, step, 2e-4, gscale=0.25)
         close(p, pt, tol=1e-6, what=f"adam step {it}")
     assert int(step.item()) == 5
+
+
+@pytest.mark.parametrize("which,variant", [("critic", "default"), ("critic", "ablated"), ("gen", "default"),
+                                           ("gen", "wavegan"), ("gen", "unet")])
+def test_adam_pack_matches_unpack_adam_pack(which, variant):
+    """m2d_adam_pack (Adam fused with the weight re-layouts, gradients read tap-major) against the three-launch chain
+    it replaces — gradient unpack, flat m2d_adam, m2d_pack_batch — on a whole network: parameters, both moments and
+    every packed / pre-tiled weight copy must be BIT-identical after two steps."""
+    from music2dance_b200.archis.default import (AblatedSequenceDiscriminator, SequenceDiscriminator,
+                                                 SequenceGenerator)
+    from music2dance_b200.engine import AdamPack
+    from oracle import phase3_oracle as O
+    from tests.parity import VARIANTS
+    cfg = O.make_cfg(**VARIANTS[variant])
+
+    def make():
+        torch.manual_seed(0)
+        if which == "gen":
+            m = SequenceGenerator(cfg["audio_feat_samples"], cfg["input_vector_size"], cfg["latent_vector_size"],
+                                  cfg["size"], cfg["output_size"], cfg["noise_size"], cfg["nblocks_gen"],
+                                  cfg["n_cells"], cfg["enc_type"], cfg["activ"], DEV)
+        else:
+            cls = AblatedSequenceDiscriminator if cfg["ablated"] else SequenceDiscriminator
+            m = cls(cfg["output_size"], cfg["channels"], cfg["code_size"], cfg["stick_length"],
+                    init_ker=cfg["init_kernel"], activ=cfg["activ"], device=DEV)
+        eng = m._engine()
+        eng.net.pack()
+        return m, eng
+
+    (ma, ea), (mb, eb) = make(), make()
+    n = ea.fp.n_live_padded
+    f = dict(dtype=torch.float32, device=DEV)
+    st = {k: (torch.zeros(n, **f), torch.zeros(n, **f)) for k in "ab"}
+    step_a = torch.zeros(1, dtype=torch.int32, device=DEV)
+    convs_a, convs_b = ea.net.convs(), eb.net.convs()
+    if which == "critic" and not cfg["ablated"]:
+        late = [eb.net.a_layers[4], eb.net.a_l6]
+        tabs = [AdamPack(eb.fp, eb.net, *st["b"], exclude=late), AdamPack(eb.fp, eb.net, *st["b"], only=late)]
+    else:
+        tabs = [AdamPack(eb.fp, eb.net, *st["b"])]
+    g = torch.Generator(device=DEV).manual_seed(5)
+    for it in range(2):
+        # same kernel-layout gradients on both sides: plain range + tap-major arena
+        for ta, tb in zip(ea.fp.grad_buffers(), eb.fp.grad_buffers()):
+            ta.normal_(generator=g)
+            ta.mul_(1e-2 * (1 + it))
+            tb.copy_(ta)
+        ea.net.unpack_grads()
+        ops.adam(ea.fp.flat, ea.fp.grad, *st["a"], n, step_a, 2e-4, gscale=0.5)
+        ea.net.pack()
+        for t in tabs:
+            t.step(2e-4, gscale=0.5)
+        torch.cuda.synchronize()
+        assert all(int(t.counters[0]) == it + 1 and int(t.counters[1]) == 0 for t in tabs)
+        assert torch.equal(ea.fp.flat, eb.fp.flat), f"{which}/{variant}: parameters differ after step {it}"
+        assert torch.equal(st["a"][0], st["b"][0]) and torch.equal(st["a"][1], st["b"][1]), "Adam moments differ"
+        for ca, cb in zip(convs_a, convs_b):
+            for name in ("wp", "wpt", "wd", "wdt", "wdm", "wdmt"):
+                xa, xb = getattr(ca, name, None), getattr(cb, name, None)
+                assert (xa is None) == (xb is None)
+                if xa is not None and cb.gw is not None:
+                    assert torch.equal(xa, xb), f"{ca.name}.{name} differs after step {it}"
