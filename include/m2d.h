@@ -214,6 +214,17 @@ int m2d_bn_bwd_apply(const float* dy, int lddy, const float* y, int ldy, const f
 int m2d_colsum(const float* x, int ld, long long M, int C, float* out, float scale, float beta,
                double* acc, void* stream);
 
+/* column sums of n matrices in one launch (+ one finalize launch): every bias gradient of a network after a
+ * backward sweep.  `table` lives in DEVICE memory; acc = fp64 scratch, acc_off = the entry's offset in it
+ * (entries must not overlap; the finalize kernel leaves their slots zero). */
+typedef struct {
+    const float* x; float* out;
+    long long M; long long acc_off;
+    int ld, C;
+    float scale, beta;
+} m2d_colsum_desc;
+int m2d_colsum_batch(const m2d_colsum_desc* table, int n, int max_C, double* acc, void* stream);
+
 /* ------------------------------------------------------------------------
  * element-wise / reductions
  * ---------------------------------------------------------------------- */
@@ -225,6 +236,10 @@ int m2d_scale_rows(const float* x, const float* s, float* y, int nb, long long p
 /* losses.py:15-20: xi[b,:] = alpha[b]*real[b,:] + (1-alpha[b])*fake[b,:] */
 int m2d_interp(const float* real, const float* fake, const float* alpha, float* xi,
                int nb, long long per, void* stream);
+/* the same plus the two copies a critic iteration stacks behind the interpolates (train.py:204-211 evaluates the
+ * critic on interpolates, real and fake poses): xi3 = [interpolates (nb); real (nb); fake (nb)] in one pass */
+int m2d_interp_stack3(const float* real, const float* fake, const float* alpha, float* xi3,
+                      int nb, long long per, void* stream);
 /* out[b] += sum x[b,:]^2  (fp64 accumulators) */
 int m2d_rows_sumsq(const float* x, int nb, long long per, double* out, void* stream);
 /* out[0] += sum x  (fp64) */
@@ -232,7 +247,7 @@ int m2d_sum(const float* x, long long n, double* out, void* stream);
 /* losses.py:55-60.  ss0/ss1 [B] sums of squares (ss1 NULL when ablated):
  * scal[0] = gp, kappa0[b] = dGP/d||.|| chain factor (2/B)(n-1)/n, same for kappa1 */
 int m2d_gp_finalize(const double* ss0, const double* ss1, int B, float* gp, float* kappa0,
-                    float* kappa1, void* stream);
+                    float* kappa1, float kscale /* kappa *= kscale (the trainer folds gamma in) */, void* stream);
 /* losses.py:47-50 (lp=True, the phase2 trainers): gp = mean(max(0, ||g|| - 1)^2), kappa0[b] = (2/B) max(0, n-1)/n */
 int m2d_gp_finalize_lp(const double* ss0, int B, float* gp, float* kappa0, void* stream);
 /* train.py:226,233 + losses.py:76-82 on channels-last poses [B,T,C]:
@@ -284,7 +299,10 @@ int m2d_transpose_bcl(const float* x, float* y, int nb, int R, int C, void* stre
  * sum D(fake), sum|real-fake|, sum|tv diffs|}.  mode 0: out = {err_fake-err_real+c0*gp, gp,
  * w_dist, err_real, err_fake};  mode 1: out = {err_real-err_fake+c0*l1+c1*tv, l1, tv, err_real, err_fake} */
 int m2d_wgan_scalars(const double* sums, const float* gp, int B, long long n_l1, long long n_tv,
-                     float c0, float c1, int mode, float* out, void* stream);
+                     float c0, float c1, int mode, float* out,
+                     const float* d_real, const float* d_fake /* optional: B critic scores each, summed here instead
+                                                                 of read from sums[0] / sums[1] */,
+                     void* stream);
 
 /* utils.py:329-353 (slice_audio_batch / slice_audio_sequence): out[seq,f,j] =
  * audio[seq, f*stride - pad_left + j], zero outside [0,A).  Pure indexing, bit-exact. */
@@ -307,7 +325,7 @@ int m2d_adam(float* p, const float* g, float* m, float* v, long long n, int* ste
  * The table (DEVICE memory, built once: all pointers are stable) has one item per tile of a weight tensor
  * (Cout, Cin, k): rows [co0, co0+nco) x channels [ci0, ci0+nci) x taps [t0, t0+nt), nco <= 32, or per plain range of
  * `flat_n` floats (biases, BatchNorm, GRU recurrent weights, ...).  Each thread block stages its tile in shared
- * memory (nco * (nci * (nt | 1) | 1) floats <= `smem_floats`), so every global access — gradient (tap-major),
+ * memory (nco * ((nci * nt) | 1) floats <= `smem_floats`; nt <= 32), so every global access — gradient (tap-major),
  * p / m / v (parameter layout), each packed destination — is made in that array's own contiguous order.
  * pk[i] = the re-layouts of the tile (kinds and destination layouts exactly as in m2d_pack_desc).
  * counters[0] = Adam step count (device int, incremented by the launch: graph-replay safe), counters[1] = scratch (0).
@@ -322,7 +340,9 @@ typedef struct {
     int Cout, Cin, k;
     int g_packed;                                     /* 1: g is tap-major [co, t*Cin + ci]; 0: parameter layout */
     int co0, nco, ci0, nci, t0, nt;
-    int n_pack, pad_;
+    int n_pack;
+    int pad_;                                         /* 1: Cout, Cin, co0, nco, ci0, nci are all multiples of 4 and every
+                                                         pointer is 16-byte aligned -> 16-byte accesses throughout */
     m2d_adam_pack_out pk[3];
 } m2d_adam_item;
 int m2d_adam_pack(const m2d_adam_item* items, int n, int smem_floats, int* counters, float lr, float beta1,

@@ -82,7 +82,9 @@ SIGNATURES = {
     "m2d_interp": [_P, _P, _P, _P, _I, _L, _P],
     "m2d_rows_sumsq": [_P, _I, _L, _P, _P],
     "m2d_sum": [_P, _L, _P, _P],
-    "m2d_gp_finalize": [_P, _P, _I, _P, _P, _P, _P],
+    "m2d_gp_finalize": [_P, _P, _I, _P, _P, _P, _F, _P],
+    "m2d_interp_stack3": [_P, _P, _P, _P, _I, _L, _P],
+    "m2d_colsum_batch": [_P, _I, _I, _P, _P],
     "m2d_gp_finalize_lp": [_P, _I, _P, _P, _P],
     "m2d_pose_losses": [_P, _P, _P, _I, _I, _I, _F, _F, _I, _P, _P],
     "m2d_jerkiness": [_P, _I, _I, _I, _P, _P],
@@ -97,7 +99,7 @@ SIGNATURES = {
     "m2d_embed_rows": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
     "m2d_embed_grad": [_P, _I, _P, _P, _I, _I, _I, _I, _F, _F, _P],
     "m2d_transpose_bcl": [_P, _P, _I, _I, _I, _P],
-    "m2d_wgan_scalars": [_P, _P, _I, _L, _L, _F, _F, _I, _P, _P],
+    "m2d_wgan_scalars": [_P, _P, _I, _L, _L, _F, _F, _I, _P, _P, _P, _P],
     "m2d_slice_audio": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "m2d_adam": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _P],
     "m2d_adam_pack": [_P, _I, _I, _P, _F, _F, _F, _F, _F, _P],

@@ -72,6 +72,47 @@ colsum_kernel(const float* __restrict__ x, int ld, long long M, int C, long long
     col_reduce<1>(M, C, rows_per, acc, [&](long long r, int c, float* v) { v[0] = x[r * ld + c]; });
 }
 
+// column sums of several matrices in ONE launch (the bias gradients of every layer of a network after a backward
+// sweep): blockIdx.y = table entry, blockIdx.x = (row chunk, 32-column block).  fp64 partials -> acc[entry.acc_off + c]
+__global__ void __launch_bounds__(256)
+colsum_batch_kernel(const m2d_colsum_desc* __restrict__ table, double* acc) {
+    const m2d_colsum_desc d = table[blockIdx.y];
+    const int ncb = (d.C + 31) >> 5;
+    const int nrc = (int)gridDim.x / ncb;                  // row chunks (>= 1: the host sizes gridDim.x >= max ncb)
+    if (nrc == 0 || (int)blockIdx.x >= nrc * ncb) return;
+    const int cb = blockIdx.x % ncb, rc = blockIdx.x / ncb;
+    const int c = cb * 32 + (threadIdx.x & 31), ry = threadIdx.x >> 5;
+    const long long rows_per = (d.M + nrc - 1) / nrc;
+    const long long r0 = rc * rows_per, r1 = r0 + rows_per < d.M ? r0 + rows_per : d.M;
+    double s0 = 0.0, s1 = 0.0;
+    if (c < d.C) {
+        long long r = r0 + ry;
+        for (; r + 8 < r1; r += 16) {                      // two independent loads in flight
+            s0 += (double)d.x[r * d.ld + c];
+            s1 += (double)d.x[(r + 8) * d.ld + c];
+        }
+        if (r < r1) s0 += (double)d.x[r * d.ld + c];
+    }
+    __shared__ double sh[8][33];
+    sh[ry][threadIdx.x & 31] = s0 + s1;
+    __syncthreads();
+    if (ry == 0 && c < d.C && r0 < r1) {
+        double t = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += sh[j][threadIdx.x];
+        atomicAdd(acc + d.acc_off + c, t);
+    }
+}
+__global__ void colsum_batch_finalize_kernel(const m2d_colsum_desc* __restrict__ table, double* acc) {
+    const m2d_colsum_desc d = table[blockIdx.y];
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < d.C) {
+        const float v = (float)(acc[d.acc_off + c] * (double)d.scale);
+        d.out[c] = d.beta != 0.f ? d.beta * d.out[c] + v : v;
+        acc[d.acc_off + c] = 0.0;                          // ready for the next launch (graph replay)
+    }
+}
+
 __global__ void colsum_finalize_kernel(const double* acc, int C, float* out, float scale, float beta) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < C) {
@@ -195,6 +236,20 @@ __global__ void interp_kernel(const float* __restrict__ real, const float* __res
         xi[base + i] = a * real[base + i] + (1.f - a) * fake[base + i];
 }
 
+// xi3 = [interpolates; real; fake] (3 x nb entries): the stacked pose input of one critic iteration in one pass
+__global__ void interp_stack3_kernel(const float* __restrict__ real, const float* __restrict__ fake,
+                                     const float* __restrict__ alpha, float* xi3, int nb, long long per) {
+    const float a = alpha[blockIdx.y];
+    const long long base = blockIdx.y * per, all = (long long)nb * per;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float r = real[base + i], f = fake[base + i];
+        xi3[base + i] = a * r + (1.f - a) * f;
+        xi3[all + base + i] = r;
+        xi3[2 * all + base + i] = f;
+    }
+}
+
 __device__ __forceinline__ void block_atomic_add(double v, double* out) {
     __shared__ double sh[32];
     v = warp_sum(v);
@@ -228,19 +283,19 @@ __global__ void sum_kernel(const float* __restrict__ x, long long n, double* out
 }
 
 __global__ void gp_finalize_kernel(const double* ss0, const double* ss1, int B, float* gp, float* k0,
-                                   float* k1) {
+                                   float* k1, float kscale) {
     // single block; B is a minibatch (<= a few thousand)
     double acc = 0.0;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         float n0 = sqrtf((float)ss0[b] + 1e-12f);
         float d0 = n0 - 1.f;
         acc += (double)(d0 * d0);
-        k0[b] = (2.f / (float)B) * d0 / n0;
+        k0[b] = kscale * ((2.f / (float)B) * d0 / n0);
         if (ss1) {
             float n1 = sqrtf((float)ss1[b] + 1e-12f);
             float d1 = n1 - 1.f;
             acc += (double)(d1 * d1);
-            k1[b] = (2.f / (float)B) * d1 / n1;
+            k1[b] = kscale * ((2.f / (float)B) * d1 / n1);
         }
     }
     __shared__ double total;
@@ -493,9 +548,20 @@ __global__ void transpose_kernel(const float* __restrict__ x, float* y, int R, i
 
 // train.py:207-214,226-235: scalar losses of one critic iteration / generator update
 __global__ void wgan_scalars_kernel(const double* sums, const float* gp, int B, long long n_l1, long long n_tv,
-                                    float c0, float c1, int mode, float* out) {
+                                    float c0, float c1, int mode, float* out, const float* d_real,
+                                    const float* d_fake) {
+    // one warp; d_real / d_fake (B critic scores each) replace sums[0] / sums[1] when given
+    double sr = 0.0, sf = 0.0;
+    if (d_real) {
+        for (int b = threadIdx.x; b < B; b += 32) { sr += (double)d_real[b]; sf += (double)d_fake[b]; }
+        sr = warp_sum(sr);
+        sf = warp_sum(sf);
+    } else {
+        sr = sums[0];
+        sf = sums[1];
+    }
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const float er = (float)(sums[0] / (double)B), ef = (float)(sums[1] / (double)B);
+    const float er = (float)(sr / (double)B), ef = (float)(sf / (double)B);
     if (mode == 0) {            // critic: err_fake - err_real + gamma*gp
         const float g = gp[0];
         out[0] = ef - er + c0 * g; out[1] = g; out[2] = ef - er; out[3] = er; out[4] = ef;
@@ -634,6 +700,17 @@ extern "C" int m2d_colsum(const float* x, int ld, long long M, int C, float* out
     return check_launch("colsum");
 }
 
+extern "C" int m2d_colsum_batch(const m2d_colsum_desc* table, int n, int max_C, double* acc, void* stream) {
+    M2D_REQUIRE(table && acc && n > 0 && max_C > 0, "colsum_batch: bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ncb = (max_C + 31) / 32;
+    dim3 grid((unsigned)(ncb > 64 ? ncb : 64), (unsigned)n);
+    colsum_batch_kernel<<<grid, 256, 0, st>>>(table, acc);
+    dim3 g2((unsigned)((max_C + 255) / 256), (unsigned)n);
+    colsum_batch_finalize_kernel<<<g2, 256, 0, st>>>(table, acc);
+    return check_launch("colsum_batch");
+}
+
 extern "C" int m2d_axpby(const float* x, const float* z, float* y, long long n, float a, float b,
                          void* stream) {
     M2D_REQUIRE(x && y && n > 0, "axpby: bad args");
@@ -663,6 +740,14 @@ extern "C" int m2d_interp(const float* real, const float* fake, const float* alp
     return check_launch("interp");
 }
 
+extern "C" int m2d_interp_stack3(const float* real, const float* fake, const float* alpha, float* xi3, int nb,
+                                 long long per, void* stream) {
+    M2D_REQUIRE(real && fake && alpha && xi3 && nb > 0 && per > 0, "interp_stack3: bad args");
+    dim3 grid((unsigned)grid1d(per, 256, 2), (unsigned)nb);
+    interp_stack3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(real, fake, alpha, xi3, nb, per);
+    return check_launch("interp_stack3");
+}
+
 extern "C" int m2d_rows_sumsq(const float* x, int nb, long long per, double* out, void* stream) {
     M2D_REQUIRE(x && out && nb > 0 && per > 0, "rows_sumsq: bad args");
     dim3 grid((unsigned)grid1d(per, 256, 1), (unsigned)nb);
@@ -677,9 +762,9 @@ extern "C" int m2d_sum(const float* x, long long n, double* out, void* stream) {
 }
 
 extern "C" int m2d_gp_finalize(const double* ss0, const double* ss1, int B, float* gp, float* kappa0,
-                               float* kappa1, void* stream) {
+                               float* kappa1, float kscale, void* stream) {
     M2D_REQUIRE(ss0 && gp && kappa0 && B > 0 && (!ss1 || kappa1), "gp_finalize: bad args");
-    gp_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(ss0, ss1, B, gp, kappa0, kappa1);
+    gp_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(ss0, ss1, B, gp, kappa0, kappa1, kscale);
     return check_launch("gp_finalize");
 }
 
@@ -785,9 +870,11 @@ extern "C" int m2d_transpose_bcl(const float* x, float* y, int nb, int R, int C,
 }
 
 extern "C" int m2d_wgan_scalars(const double* sums, const float* gp, int B, long long n_l1, long long n_tv,
-                                float c0, float c1, int mode, float* out, void* stream) {
-    M2D_REQUIRE(sums && out && B > 0 && (mode == 1 || gp), "wgan_scalars: bad args");
-    wgan_scalars_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, gp, B, n_l1, n_tv, c0, c1, mode, out);
+                                float c0, float c1, int mode, float* out, const float* d_real, const float* d_fake,
+                                void* stream) {
+    M2D_REQUIRE(out && B > 0 && (mode == 1 || gp) && (sums || (d_real && mode == 0)) && (!d_real == !d_fake),
+                "wgan_scalars: bad args");
+    wgan_scalars_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, gp, B, n_l1, n_tv, c0, c1, mode, out, d_real, d_fake);
     return check_launch("wgan_scalars");
 }
 

@@ -107,7 +107,7 @@ class AdamPack:
     (plain ranges belong to the table built with only=None)."""
 
     TILE = 800            # floats of one output row's slice held in shared memory (x 32 rows)
-    FLAT_CHUNK = 8192
+    FLAT_CHUNK = 4096
 
     def __init__(self, fp, net, m, v, only=None, exclude=None):
         import numpy as np
@@ -143,13 +143,11 @@ class AdamPack:
             assert len(packs) <= 3
             g_packed = conv.gwp is not None
             g_ptr = conv.gwp.data_ptr() if g_packed else fp.grad.data_ptr() + 4 * off
-            parts = -(-k // 25)
-            nt_full = -(-k // parts)
-            ntp = nt_full | 1
+            nt_full = min(k, 25)                                  # taps per tile (odd when split: conflict-free transposes)
             if Cin == 1:
                 nci_full = 1
             else:
-                nci_full = min(Cin, max(32, (self.TILE // ntp) // 32 * 32))
+                nci_full = min(Cin, max(32, (self.TILE // nt_full) // 32 * 32))
             for co0 in range(0, Cout, 32):
                 nco = min(32, Cout - co0)
                 for ci0 in range(0, Cin, nci_full):
@@ -162,10 +160,11 @@ class AdamPack:
                         it["Cout"], it["Cin"], it["k"], it["g_packed"] = Cout, Cin, k, int(g_packed)
                         it["co0"], it["nco"], it["ci0"], it["nci"], it["t0"], it["nt"] = co0, nco, ci0, nci, t0, nt
                         it["n_pack"] = len(packs)
+                        it["pad_"] = int(all(x % 4 == 0 for x in (Cout, Cin, co0, nco, ci0, nci)))
                         for j, e in enumerate(packs):
                             it["pk"][j] = (ptr(e[1]), ptr(e[2]), e[7], e[6], e[8] if len(e) > 8 else 0, 0)
                         items.append(it)
-                        self.smem_floats = max(self.smem_floats, nco * ((nci * (nt | 1)) | 1))
+                        self.smem_floats = max(self.smem_floats, nco * ((nci * nt) | 1))
         # plain ranges: adjacent parameters (16-byte aligned slots, zero padding between them) merge into runs
         flats.sort()
         runs = []

@@ -261,9 +261,35 @@ def sum_(x, n, out):
     call("m2d_sum", _p(x), n, _p(out), _stream())
 
 
-def gp_finalize(ss0, ss1, B, gp, k0, k1):
+def gp_finalize(ss0, ss1, B, gp, k0, k1, kscale=1.0):
     LAUNCHES[0] += 1
-    call("m2d_gp_finalize", _p(ss0), _p(ss1), B, _p(gp), _p(k0), _p(k1), _stream())
+    call("m2d_gp_finalize", _p(ss0), _p(ss1), B, _p(gp), _p(k0), _p(k1), kscale, _stream())
+
+
+def interp_stack3(real, fake, alpha, xi3, nb, per):
+    """xi3 = [alpha*real + (1-alpha)*fake; real; fake]: the 3*nb stacked pose entries of a critic iteration."""
+    LAUNCHES[0] += 1
+    call("m2d_interp_stack3", _p(real), _p(fake), _p(alpha), _p(xi3), nb, per, _stream())
+
+
+def colsum_table(entries, acc_doubles, device):
+    """entries: (x Mat [1, M, C], out tensor, scale, beta) -> (device table, n, max C, fp64 scratch)."""
+    import numpy as np
+    dt = np.dtype([("x", "<u8"), ("out", "<u8"), ("M", "<i8"), ("acc_off", "<i8"), ("ld", "<i4"), ("C", "<i4"),
+                   ("scale", "<f4"), ("beta", "<f4")])
+    arr = np.zeros(len(entries), dtype=dt)
+    off = 0
+    for i, (x, out, scale, beta) in enumerate(entries):
+        arr[i] = (x.ptr, out.data_ptr(), x.M, off, x.ld, x.cols, scale, beta)
+        off += x.cols
+    acc = torch.zeros(max(off, 1), dtype=torch.float64, device=device)
+    t = torch.from_numpy(arr.view(np.uint8).copy()).to(device)
+    return t, len(entries), max(e[0].cols for e in entries), acc
+
+
+def colsum_batch(tab):
+    LAUNCHES[0] += 2
+    call("m2d_colsum_batch", _p(tab[0]), tab[1], tab[2], _p(tab[3]), _stream())
 
 
 def gp_finalize_lp(ss0, B, gp, k0):
@@ -340,9 +366,9 @@ def transpose_bcl(x, y, nb, R, Cn):
     call("m2d_transpose_bcl", _p(x), _p(y), nb, R, Cn, _stream())
 
 
-def wgan_scalars(sums, gp, B, n_l1, n_tv, c0, c1, mode, out):
+def wgan_scalars(sums, gp, B, n_l1, n_tv, c0, c1, mode, out, d_real=None, d_fake=None):
     LAUNCHES[0] += 1
-    call("m2d_wgan_scalars", _p(sums), _p(gp), B, n_l1, n_tv, c0, c1, mode, _p(out), _stream())
+    call("m2d_wgan_scalars", _p(sums), _p(gp), B, n_l1, n_tv, c0, c1, mode, _p(out), _p(d_real), _p(d_fake), _stream())
 
 
 def slice_audio(audio, out, nseq, A, nwin, W, stride, pad_left):

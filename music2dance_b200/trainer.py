@@ -57,7 +57,10 @@ class Phase3Trainer:
         f = dict(dtype=torch.float32, device=dev)
         # staged inputs of one train step (device resident)
         self.in_real = torch.zeros(nc, B, T, O, **f)
-        self.in_audio = torch.zeros(nc, B, A, **f)
+        # audio staged as the first half of a [2B, A] block per iteration: the second half receives the penalty's
+        # direction v1, which makes the block the stacked input operand of audio_d.l1's weight gradient (no copy)
+        self.in_audio2 = torch.zeros(nc, 2 * B, A, **f)
+        self.in_audio = self.in_audio2[:, :B]
         self.in_noise = torch.zeros(nc, B, T, Nz, **f)
         self.in_alpha = torch.zeros(nc, B, **f)
         self.in_noise_g = torch.zeros(B, T, Nz, **f)
@@ -141,19 +144,16 @@ class Phase3Trainer:
         n3 = 3 * B
         X3 = wk.mat("c:X3", n3, T, O)
         per = T * O
-        ops.interp(real, fake_c, self.in_alpha[i], X3, B, per)
-        ops.axpby(real, None, rows(X3, B, 2 * B), B * per, 1.0, 0.0)
-        ops.axpby(fake_c, None, rows(X3, 2 * B, n3), B * per, 1.0, 0.0)
+        ops.interp_stack3(real, fake_c, self.in_alpha[i], X3, B, per)      # [interpolates; real; fake]
         gamma = float(self.cfg["gamma"])
         if self.fused_backward and D.act == ACT_ID:
             # one backward sweep for the Wasserstein terms and the penalty (wgan.critic_backward_fused)
             fw = critic_forward_fused(D, X3, None if D.ablated else audio, B, "c")
-            sums = wk.acc_slot(4)
             d = fw["d"]
-            ops.sum_(rows(d, B, 2 * B), B, sums[0:1])
-            ops.sum_(rows(d, 2 * B, n3), B, sums[1:2])
-            critic_backward_fused(D, fw, B, audio, gamma, self.gp_buf, self.k0, self.k1)
-            ops.wgan_scalars(sums, self.gp_buf, B, 1, 1, gamma, 0.0, 0, self.log_c[i])
+            aud2 = None if D.ablated else Mat(self.in_audio2[i], 2 * B, self.A, 1)
+            critic_backward_fused(D, fw, B, audio, gamma, self.gp_buf, self.k0, self.k1, aud2=aud2)
+            ops.wgan_scalars(None, self.gp_buf, B, 1, 1, gamma, 0.0, 0, self.log_c[i],
+                             d_real=rows(d, B, 2 * B), d_fake=rows(d, 2 * B, n3))
             if update:
                 self._adam(self.de, self.cfg["lr_critic"])
             elif not self.per_iter:

@@ -155,7 +155,7 @@ def critic_forward_fused(D, X3, audio, B, tag):
     return dict(svp=svp, sva=sva, sa=sa, u=u, d=d)
 
 
-def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f"):
+def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f", aud2=None):
     """Critic gradients of  err_fake - err_real + gamma * gp  (phase3/train.py:204-215) in ONE backward sweep.
 
     Rows of the forward state: [0,B) interpolates, [B,2B) real, [2B,3B) fake.  The Wasserstein terms and the
@@ -174,10 +174,13 @@ def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f"):
     wk, T, O, code = D.wk, D.T, D.O, D.code
     n3 = 3 * B
     A1 = lambda c: wk.acc_slot(c)
-    dd = wk.vec(f"{tag}:dd", n3)
-    ops.fill(dd[:B], B, 1.0)
-    ops.fill(dd[B:2 * B], B, -1.0 / B)
-    ops.fill(dd[2 * B:], B, 1.0 / B)
+    dd = wk.vec(f"{tag}:dd", n3)                                  # upstream of the scores: a constant, written once
+    consts = D.__dict__.setdefault("_consts", set())
+    if (tag, "dd", B) not in consts:
+        ops.fill(dd[:B], B, 1.0)
+        ops.fill(dd[B:2 * B], B, -1.0 / B)
+        ops.fill(dd[2 * B:], B, 1.0 / B)
+        consts.add((tag, "dd", B))
     ddm = Mat(dd, 1, n3, 1)
     u, sa = fw["u"], fw["sa"]
     dh, dsa = D.fusion_bwd(ddm, u, n3, tag)                       # the branches' upstreams first: they start at once
@@ -187,7 +190,7 @@ def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f"):
     if not D.ablated:
         Alen = D.cfg["audio_length"]
         ss1 = wk.acc_slot(B)
-        g1 = wk.mat(f"{tag}:aud2", 2 * B, Alen, 1)                 # [audio; v1]: stacked input operand of l1
+        g1 = aud2 if aud2 is not None else wk.mat(f"{tag}:aud2", 2 * B, Alen, 1)   # [audio; v1]: stacked input of l1
         with D.fork():
             d_a2 = wk.mat(f"{tag}:d_a2", 1, 2 * B, code)
             ops.copy2d(rows(dsa, B, 2 * B).cols_slice(code, D.F), rows(d_a2, 0, B))
@@ -199,25 +202,26 @@ def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f"):
             D.l1_dgrad(dla[0].batch_slice(B, 2 * B), gv, B)
             ops.mark(f"{tag}:aud_bwd_l1")
             ops.rows_sumsq(gv, B, Alen, ss1)
-            ops.copy2d(Mat.of(audio.reshape(-1), 1, B, Alen) if not isinstance(audio, Mat) else audio.flat_rows(),
-                       Mat(g1.t, 1, B, Alen, Alen))
+            if aud2 is None:
+                ops.copy2d(Mat.of(audio.reshape(-1), 1, B, Alen) if not isinstance(audio, Mat) else audio.flat_rows(),
+                           Mat(g1.t, 1, B, Alen, Alen))
     d_s3 = wk.mat(f"{tag}:d_s3", 1, n3, code)
     ops.copy2d(dsa.cols_slice(0, code), d_s3)
     svp = fw["svp"]
     dlp = D.pose_bwd(svp, d_s3, n3, tag, wgrads=False, dX=None)
-    D.fc2.wgrad(rows(ddm, B, n3), rows(u, B, n3), wk.scratch, beta=0.0, bbeta=0.0, acc=A1(1))
-    D.fc1.wgrad(rows(dh, B, n3), rows(sa, B, n3), wk.scratch, beta=0.0, bbeta=0.0, acc=A1(128))
+    D.fc2.wgrad(rows(ddm, B, n3), rows(u, B, n3), wk.scratch, beta=0.0, bias=False)
+    D.fc1.wgrad(rows(dh, B, n3), rows(sa, B, n3), wk.scratch, beta=0.0, bias=False)
     X3 = svp["X"]
     g0 = wk.mat(f"{tag}:g0", B, T, O)
     D.s_conv1.dgrad(rows(dlp["conv1"], 0, B), g0, ws=wk.scratch)
     ss0 = wk.acc_slot(B)
     ops.rows_sumsq(g0, B, T * O, ss0)
     D.join()
-    ops.gp_finalize(ss0, ss1, B, gp_out, k0, k1)
-    ops.mark(f"{tag}:gp")
-    # v = gamma * kappa * g, written where the layer-1 weight gradients read their input
+    # kappa scaled by gamma in the same launch: v = gamma * kappa * g is written where the layer-1 weight gradients
+    # read their input
     kg = wk.vec(f"{tag}:kg", 2 * B)
-    ops.axpby(k0, None, kg[:B], B, gamma, 0.0)
+    ops.gp_finalize(ss0, ss1, B, gp_out, kg[:B], kg[B:], kscale=gamma)
+    ops.mark(f"{tag}:gp")
     t_sa = wk.mat(f"{tag}:t_sa", 1, B, D.F)
     main = torch.cuda.current_stream(D.dev)
     par = D.par
@@ -234,7 +238,6 @@ def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f"):
         return ev
 
     if not D.ablated:
-        ops.axpby(k1, None, kg[B:], B, gamma, 0.0)
         if par:
             s_ta.wait_stream(main)
             s_wa.wait_stream(main)
@@ -258,13 +261,11 @@ def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f"):
             x = g1
             ws_a = wk.scratch                                      # per-stream scratch (Workspace.scratch)
             for i, l in enumerate(D.a_layers):
-                ops.colsum(dla[i].batch_slice(0, B).flat_rows(), l.gb, A1(l.Cout), scale=1.0, beta=0.0)
                 if par:
                     s_wa.wait_event(evs[i])
                 l.wgrad(dla[i], x, ws_a, scale=1.0, beta=0.0, bias=False)
                 ops.mark(f"{tag}:aud_wg_l{i + 1}")
                 x = sva["q2"][i]
-            ops.colsum(rows(d_a2, 0, B), D.a_l6.gb, A1(D.a_l6.Cout), scale=1.0, beta=0.0)
             if par:
                 s_wa.wait_event(evs[len(D.a_layers)])
             D.a_l6.wgrad(d_a2.as_rows(2 * B, 1), x, ws_a, scale=1.0, beta=0.0, bias=False)
@@ -302,9 +303,21 @@ def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f"):
     ops.mark(f"{tag}:pose_tan_end")
     with torch.cuda.stream(s_wp):
         ws_p = wk.scratch
+        # every bias gradient of the iteration (Wasserstein rows only, Q5) in one batched column-sum launch: the deltas
+        # of both branches are complete (the main stream joined the audio branch before the penalty was finalised)
+        tabs = D.__dict__.setdefault("_bias_tabs", {})
+        key = (tag, B, tuple(dl.ptr for _, dl, _, _ in pending))
+        if key not in tabs:
+            ent = [(rows(ddm, B, n3), D.fc2.gb, 1.0, 0.0), (rows(dh, B, n3), D.fc1.gb, 1.0, 0.0)]
+            for conv, dl, _, _ in pending:
+                ent.append((rows(d_s3, B, n3) if conv is D.s_fconv else rows(dl, B, n3).flat_rows(), conv.gb, 1.0, 0.0))
+            if not D.ablated:
+                for i, l in enumerate(D.a_layers):
+                    ent.append((dla[i].batch_slice(0, B).flat_rows(), l.gb, 1.0, 0.0))
+                ent.append((rows(d_a2, 0, B), D.a_l6.gb, 1.0, 0.0))
+            tabs[key] = ops.colsum_table(ent, None, D.dev)
+        ops.colsum_batch(tabs[key])
         for conv, dl, x_in, ev in pending:
-            dlr = dl if conv is D.s_fconv else rows(dl, B, n3).flat_rows()
-            ops.colsum(rows(d_s3, B, n3) if conv is D.s_fconv else dlr, conv.gb, A1(conv.Cout), scale=1.0, beta=0.0)
             if par:
                 s_wp.wait_event(ev)
             conv.wgrad(dl, x_in, ws_p, scale=1.0, beta=0.0, bias=False)

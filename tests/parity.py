@@ -6,7 +6,10 @@ import torch
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 VARIANTS = {"default": {}, "wavegan": {"enc_type": "wavegan"}, "unet": {"enc_type": "unet"},
-            "ablated": {"ablated": True}, "tanh": {"activ": "tanh"}}
+            "ablated": {"ablated": True}, "tanh": {"activ": "tanh"},
+            # phase3/configs/tv.yaml (eta = 50), noise_enhanced.yaml (noise 100 -> audio GRU hidden 150, noise GRU 100),
+            # activ = 'relu' (default.py:73-74,100-101,254)
+            "tv": {"eta": 50.0}, "noise_enhanced": {"noise_size": 100}, "relu": {"activ": "relu"}}
 B_GOLD, ALPHA_SEED, DATA_SEED = 2, 77, 1234
 
 # tolerance stated by BASELINE.json's north_star: 1e-3 relative on losses and GP terms.

@@ -450,6 +450,7 @@ def test_adam_pack_matches_unpack_adam_pack(which, variant):
     every packed / pre-tiled weight copy must be BIT-identical after two steps."""
     from music2dance_b200.archis.default import (AblatedSequenceDiscriminator, SequenceDiscriminator,
                                                  SequenceGenerator)
+    from music2dance_b200 import ops
     from music2dance_b200.engine import AdamPack
     from oracle import phase3_oracle as O
     from tests.parity import VARIANTS

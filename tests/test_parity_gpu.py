@@ -233,6 +233,71 @@ def test_fused_trainer_vs_oracle(variant, B, nc, graphs):
                 assert float(d.mean()) < TOL_DRIFT_LR * lr * steps + 1e-6 * float(P[k].abs().max()), (k, float(d.mean()))
 
 
+def _sync_trainer_from_oracle(tr, gen, critic, G, D, ad, ag):
+    """Copy the oracle's state (parameters, BatchNorm buffers, Adam moments and step counts) into the trainer: after
+    this both sides start the next iteration from IDENTICAL state, so every iteration is a single-iteration
+    comparison (the protocol of oracle/validate_vs_reference.py:93-101)."""
+    torch.cuda.synchronize()
+    gen.load_state_dict({k: v.clone() for k, v in G.items()}, strict=True)
+    critic.load_state_dict({k: v.clone() for k, v in D.items()}, strict=True)
+    for eng, st, m, v, tabs in ((tr.de, ad, tr.mD, tr.vD, [tr.apD, tr.apD_late]), (tr.ge, ag, tr.mG, tr.vG, [tr.apG])):
+        base = eng.fp.flat.data_ptr()
+        for name, prm in eng.fp.params.items():
+            if name not in st.m:
+                continue
+            off = (prm.data_ptr() - base) // 4
+            m[off:off + prm.numel()].copy_(st.m[name].reshape(-1))
+            v[off:off + prm.numel()].copy_(st.v[name].reshape(-1))
+        t = max(st.t.values()) if st.t else 0
+        for tab in tabs:
+            if tab is not None:
+                tab.counters[0] = t
+    tr._ensure_packed()
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("variant,B,nc", [("default", 7, 8), ("tv", 2, 2), ("noise_enhanced", 2, 2), ("unet", 2, 2),
+                                          ("wavegan", 2, 2), ("ablated", 3, 3), ("tanh", 2, 2), ("relu", 2, 2)])
+def test_trainer_every_iteration_vs_oracle_resynced(variant, B, nc):
+    """North-star tolerance (1e-3 relative on losses and gradient-penalty terms) on EVERY critic iteration and on the
+    generator update of a train step — including the BASELINE configuration itself (default.yaml: batch 7,
+    n_critic 8), tv.yaml, noise_enhanced.yaml, the U-Net / WaveGAN encoders and the three code activations.  After
+    each comparison the oracle's post-update state is copied into the trainer, so chained Adam steps cannot amplify a
+    ReLU / L1 kink flip into the next comparison (tests/parity.py: TOL_CHAINED is what the un-synced test needs)."""
+    from music2dance_b200.trainer import Phase3Trainer
+    cfg = O.make_cfg(n_critic_steps=nc, **VARIANTS[variant])
+    gen, critic = build(cfg)
+    G, D = oracle_params(gen), oracle_params(critic)
+    tr = Phase3Trainer(gen, critic, cfg, B, use_graphs=False)
+    ad, ag = O.AdamState(D, cfg["lr_critic"]), O.AdamState(G, cfg["lr_gen"])
+    T, Oo = cfg["stick_length"], cfg["output_size"]
+    for step in range(2 if nc < 8 else 1):
+        batches = [O.synthetic_batch(cfg, B, 5000 + step * nc + i) for i in range(nc)]
+        tr.load_batches(torch.stack([b[0] for b in batches]), torch.stack([b[1] for b in batches]),
+                        torch.stack([b[2] for b in batches]), torch.stack([b[3] for b in batches]),
+                        batches[-1][4])
+        for i, b in enumerate(batches):
+            with torch.cuda.device(tr.dev):
+                tr.critic_iteration(i)                            # generator forward, critic backward, Adam, re-layout
+            torch.cuda.synchronize()
+            got = dict(zip(("loss_critic", "gp", "w_dist"), tr.log_c[i, :3].tolist()))
+            o = O.critic_iteration(G, D, cfg, b[0], b[1], b[2], b[3], ad)
+            for k in ("loss_critic", "gp", "w_dist"):
+                scalar_check(got[k], o[k], TOL_NORTH_STAR, f"{variant} step{step} it{i} {k}")
+            f = tr.fake_c[i].view(B, T, Oo).permute(0, 2, 1).cpu()
+            assert float((f - o["fake"]).abs().max() / o["fake"].abs().max()) < TOL_NORTH_STAR, f"it{i} generated poses"
+            _sync_trainer_from_oracle(tr, gen, critic, G, D, ad, ag)
+        b = batches[-1]
+        with torch.cuda.device(tr.dev):
+            tr.generator_update()
+        torch.cuda.synchronize()
+        got = dict(zip(("loss_gen", "l1", "tv"), tr.log_g[:3].tolist()))
+        o = O.generator_update(G, D, cfg, b[0], b[1], b[4], ag)
+        for k in ("loss_gen", "l1", "tv"):
+            scalar_check(got[k], o[k], TOL_NORTH_STAR, f"{variant} step{step} gen {k}")
+        _sync_trainer_from_oracle(tr, gen, critic, G, D, ad, ag)
+
+
 def test_per_iteration_graphs_match_single_graph():
     """The multi-GPU step structure (one CUDA graph per critic iteration, optimiser / re-layout graphs in between,
     generator forwards pipelined one iteration ahead, audio_d.l5 / l6 re-layout forked into the next graph) run on ONE
