@@ -1,6 +1,6 @@
 """Generate golden fixtures from the UNMODIFIED reference modules.
 
-    python tests/golden/make_golden.py          (build container only: needs /root/reference)
+    python tests/golden/make_golden.py [variant ...]    (build container only: needs /root/reference)
 
 For every variant the reference's own SequenceGenerator / SequenceDiscriminator /
 losses.gradient_penalty / utils.slice_audio_batch are executed on CPU (torch fp32)
@@ -24,7 +24,9 @@ from oracle import phase3_oracle as O          # noqa: E402
 from oracle import reference_harness as R      # noqa: E402
 
 VARIANTS = {"default": {}, "wavegan": {"enc_type": "wavegan"}, "unet": {"enc_type": "unet"},
-            "ablated": {"ablated": True}, "tanh": {"activ": "tanh"}}
+            "ablated": {"ablated": True}, "tanh": {"activ": "tanh"},
+            # round 2: phase3/configs/tv.yaml, noise_enhanced.yaml, activ = 'relu' (same dict as tests/parity.py)
+            "tv": {"eta": 50.0}, "noise_enhanced": {"noise_size": 100}, "relu": {"activ": "relu"}}
 B = 2
 ALPHA_SEED = 77
 DATA_SEED = 1234
@@ -149,7 +151,10 @@ def windowing(out):
 if __name__ == "__main__":
     torch.set_num_threads(8)
     here = os.path.dirname(os.path.abspath(__file__))
+    only = sys.argv[1:]                       # python tests/golden/make_golden.py [variant ...]
     for name, over in VARIANTS.items():
+        if only and name not in only:
+            continue
         cfg = O.make_cfg(**over)
         out = {}
         for state in ("init", "perturbed"):
