@@ -68,6 +68,9 @@ def parse():
     ap.add_argument("--no-throughput-regime", action="store_true",
                     help="skip the throughput_regime sub-record (a second, short run at --regime-batch per GPU)")
     ap.add_argument("--regime-batch", type=int, default=64)
+    ap.add_argument("--collective", default=None, choices=["nvl", "nccl"],
+                    help="N > 1: gradient all-reduce by the hand-written NVLink peer-memory kernel inside ONE step graph "
+                         "(nvl) or by NCCL between per-iteration graphs (nccl); default: nvl when available")
     ap.add_argument("--sub", action="store_true", help=argparse.SUPPRESS)      # child run: no nested legs
     return ap.parse_args()
 
@@ -359,7 +362,7 @@ def run_b200(args):
                             cfg["n_cells"], cfg["enc_type"], cfg["activ"], dev)
     critic = SequenceDiscriminator(cfg["output_size"], cfg["channels"], cfg["code_size"], cfg["stick_length"],
                                    init_ker=cfg["init_kernel"], activ=cfg["activ"], device=dev)
-    tr = Phase3Trainer(gen, critic, cfg, B, use_graphs=not args.no_graphs)
+    tr = Phase3Trainer(gen, critic, cfg, B, use_graphs=not args.no_graphs, collective=args.collective)
 
     # synthetic inputs of the reference shape: NSETS distinct step-input sets, pinned on the host and
     # mirrored in HBM; every rank draws its own shard (weak scaling)
@@ -590,6 +593,13 @@ def run_b200(args):
                 "data": "synthetic",
                 "config": {"workload": workload_name(args, cfg), "global_batch": B * world, "gemm": args.gemm,
                            "sequences_per_step": (nc) * B * world, "parallelism": f"dp{world}",
+                           "collective": (None if world == 1 else
+                                          ("m2d_nvl_allreduce: NVLink peer-memory two-shot all-reduce kernel inside the step "
+                                           "graph (" + ("multimem.ld_reduce / multimem.st, NVLink SHARP" if tr.nvl.multicast
+                                                        else "peer loads / stores, no multicast mapping") + ")")
+                                          if tr.nvl is not None else
+                                          "NCCL all-reduce (torch.distributed) between per-iteration graphs" +
+                                          (f"; peer-memory path unavailable: {tr.nvl_error}" if getattr(tr, "nvl_error", None) else "")),
                            "cuda_graphs": not args.no_graphs,
                            "graph_structure": ("eager" if args.no_graphs else "one graph per critic iteration, NCCL "
                                                "all-reduce between graphs" if tr.per_iter else
@@ -622,6 +632,9 @@ def run_b200(args):
             line["throughput_regime"] = regime
         print(json.dumps(line), flush=True)
     if world > 1:
+        if tr.nvl is not None:
+            tr.nvl.check()
+        torch.cuda.synchronize(dev)
         dist.barrier()
         dist.destroy_process_group()
 

@@ -348,6 +348,21 @@ typedef struct {
 int m2d_adam_pack(const m2d_adam_item* items, int n, int smem_floats, int* counters, float lr, float beta1,
                   float beta2, float eps, float gscale, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Gradient all-reduce over NVLink / NVSwitch peer memory (the data-parallel step of SURVEY 8e; the reference has no
+ * multi-GPU path).  In-place sum of floats [off, off+n) of a buffer that every GPU of the node has mapped:
+ *   bufs[r]        rank r's mapping of the buffer as seen from THIS process (bufs[rank] = the local pointer)
+ *   mc             multicast address of the buffer (NVLink SHARP: multimem.ld_reduce / multimem.st), or NULL: the
+ *                  reduction is done with peer loads in rank order (deterministic) and peer stores
+ *   signal_pads[r] rank r's flag array (unsigned, zero-initialised, >= slot0 + blocks*world entries): block-wise
+ *                  release / acquire handshakes before and after the reduction; the flags return to zero
+ * ONE kernel of `blocks` thread blocks (two-shot: rank r reduces slice r and broadcasts it); every rank must launch
+ * the same sequence of calls.  A peer that does not show up within 2 s sets *status (device int) to 1 instead of
+ * hanging the GPU.  Caller contract: producers of the local buffer precede the call on `stream`.
+ * ---------------------------------------------------------------------- */
+int m2d_nvl_allreduce(float* const* bufs, float* mc, unsigned int* const* signal_pads, int rank, int world,
+                      long long off, long long n, int blocks, int slot0, int* status, void* stream);
+
 /* Diagnostics (tools/step_timeline.py): *slot = %globaltimer (ns) when `stream` reaches this point; graph-capturable,
  * so the replayed train step can be cut into phases without a profiler attached. */
 int m2d_timestamp(unsigned long long* slot, void* stream);

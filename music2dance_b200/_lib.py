@@ -103,6 +103,7 @@ SIGNATURES = {
     "m2d_slice_audio": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "m2d_adam": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _P],
     "m2d_adam_pack": [_P, _I, _I, _P, _F, _F, _F, _F, _F, _P],
+    "m2d_nvl_allreduce": [_P, _P, _P, _I, _I, _L, _L, _I, _I, _P, _P],
     "m2d_timestamp": [_P, _P],
 }
 _RESTYPE = {"m2d_wgrad_min_ws": i64, "m2d_halo_launch_count": i64}

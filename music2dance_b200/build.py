@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libm2d_b200.so")
-SOURCES = ["api.cu", "rowconv.cu", "rowconv_tc.cu", "conv_c1.cu", "gru.cu", "elem.cu", "adam_pack.cu"]
+SOURCES = ["api.cu", "rowconv.cu", "rowconv_tc.cu", "conv_c1.cu", "gru.cu", "elem.cu", "adam_pack.cu", "nvl_allreduce.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-shared", "-Xcompiler", "-fPIC"]
 

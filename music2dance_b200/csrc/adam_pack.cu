@@ -63,19 +63,6 @@ __device__ __forceinline__ void pack_index(const PackGeom& g, int co, int ci, in
     }
 }
 
-struct AdamConst {
-    float step_size, bc2_sqrt, b1, b2, eps, gscale;
-};
-__device__ __forceinline__ float adam_update(float p, float g, float& m, float& v, const AdamConst& c) {
-    const float gi = g * c.gscale;
-    const float mi = m + (gi - m) * (1.f - c.b1);
-    const float vi = v * c.b2 + (1.f - c.b2) * gi * gi;
-    m = mi;
-    v = vi;
-    const float denom = sqrtf(vi) / c.bc2_sqrt + c.eps;
-    return p - c.step_size * (mi / denom);
-}
-
 // ---- fast index helpers (tile-local ranges: j < 2^16, divisors < 2^10 -> the float reciprocal is exact) ----------
 __device__ __forceinline__ int fdiv(int j, float inv) { return (int)(((float)j + 0.5f) * inv); }
 __device__ __forceinline__ long long tiled_fast(int n, int t, int ci, int T, int cch, int lgR) {
@@ -113,14 +100,7 @@ adam_pack_kernel(const m2d_adam_item* __restrict__ items, int* counters, float l
     __shared__ TapInfo taps[3][AP_MAXT];
     const m2d_adam_item& it = items[blockIdx.x];
     const int t_step = counters[0] + 1;
-    AdamConst c;
-    {
-        const double bc1 = 1.0 - pow((double)b1, (double)t_step);
-        const double bc2 = 1.0 - pow((double)b2, (double)t_step);
-        c.step_size = (float)((double)lr / bc1);
-        c.bc2_sqrt = (float)sqrt(bc2);
-        c.b1 = b1; c.b2 = b2; c.eps = eps; c.gscale = gscale;
-    }
+    const AdamConst c = adam_const(t_step, lr, b1, b2, eps, gscale);
     const int tid = threadIdx.x;
     if (it.flat_n > 0) {
         // plain range: 16-byte vectors, two vectors per thread in flight

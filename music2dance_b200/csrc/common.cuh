@@ -85,6 +85,30 @@ __device__ __forceinline__ float act_deriv(float y, int mode) {
     return 1.f;
 }
 
+struct AdamConst {
+    float step_size, bc2_sqrt, b1, b2, eps, gscale;
+};
+// torch.optim.Adam element update.  Every rounding is pinned with intrinsics (no compiler-chosen FMA contraction), so
+// the flat kernel (m2d_adam) and every path of the fused kernel (m2d_adam_pack) produce bit-identical p / m / v.
+__device__ __forceinline__ float adam_update(float p, float g, float& m, float& v, const AdamConst& c) {
+    const float gi = __fmul_rn(g, c.gscale);
+    const float mi = __fmaf_rn(__fsub_rn(gi, m), 1.f - c.b1, m);
+    const float vi = __fmaf_rn(__fmul_rn(1.f - c.b2, gi), gi, __fmul_rn(v, c.b2));
+    m = mi;
+    v = vi;
+    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), c.bc2_sqrt), c.eps);
+    return __fsub_rn(p, __fmul_rn(c.step_size, __fdiv_rn(mi, denom)));
+}
+__device__ __forceinline__ AdamConst adam_const(int t_step, float lr, float b1, float b2, float eps, float gscale) {
+    AdamConst c;
+    const double bc1 = 1.0 - pow((double)b1, (double)t_step);
+    const double bc2 = 1.0 - pow((double)b2, (double)t_step);
+    c.step_size = (float)((double)lr / bc1);
+    c.bc2_sqrt = (float)sqrt(bc2);
+    c.b1 = b1; c.b2 = b2; c.eps = eps; c.gscale = gscale;
+    return c;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -610,20 +610,13 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
                             float* __restrict__ v, long long n, const int* step, float lr, float b1,
                             float b2, float eps, float gscale) {
     // step counter was already incremented for this update
-    const int t = *step;
-    const double bc1 = 1.0 - pow((double)b1, (double)t);
-    const double bc2 = 1.0 - pow((double)b2, (double)t);
-    const float step_size = (float)((double)lr / bc1);
-    const float bc2_sqrt = (float)sqrt(bc2);
+    const AdamConst c = adam_const(*step, lr, b1, b2, eps, gscale);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x) {
-        float gi = g[i] * gscale;
-        float mi = m[i] + (gi - m[i]) * (1.f - b1);
-        float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+        float mi = m[i], vi = v[i];
+        p[i] = adam_update(p[i], g[i], mi, vi, c);
         m[i] = mi;
         v[i] = vi;
-        float denom = sqrtf(vi) / bc2_sqrt + eps;
-        p[i] = p[i] - step_size * (mi / denom);
     }
 }
 __global__ void tick_kernel(int* step) { *step += 1; }

@@ -1,0 +1,120 @@
+// In-place sum all-reduce of a float buffer over the GPUs of one NVSwitch domain, written against peer memory: no
+// NCCL call, one kernel, graph-capturable like any other launch (m2d_nvl_allreduce, include/m2d.h).
+//
+// Two-shot: rank r owns slice r of the buffer.  Every thread block first meets its same-index blocks on all peers
+// (release / acquire flags in the peers' signal pads: "my gradients are complete"), then reduces its part of the
+// rank's slice over all GPUs — with NVLink SHARP when a multicast mapping exists (multimem.ld_reduce: the switch
+// adds the eight copies, one 16-byte load per 4 results) or by peer loads in rank order otherwise — and broadcasts
+// the sums to every GPU (multimem.st / peer stores), then meets the peers again ("every slice is written").
+// Bytes over NVLink per GPU: 2 * (W-1)/W * n * 4, the all-reduce minimum.
+#include "common.cuh"
+
+namespace m2d {
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ uint32_t cas_release_sys(uint32_t* addr, uint32_t cmp, uint32_t val) {
+    uint32_t old;
+    asm volatile("atom.global.release.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(addr), "r"(cmp), "r"(val) : "memory");
+    return old;
+}
+__device__ __forceinline__ uint32_t cas_acquire_sys(uint32_t* addr, uint32_t cmp, uint32_t val) {
+    uint32_t old;
+    asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(addr), "r"(cmp), "r"(val) : "memory");
+    return old;
+}
+// Meet block `blockIdx.x` of every peer.  Slot (block, sender) of a GPU's signal pad is raised 0 -> 1 by the sender and
+// lowered 1 -> 0 by the owner, so the pads need no epoch and return to zero.  A peer that never arrives (a bug or a
+// dead rank) must not hang the GPU: after `timeout_ns` the block records the failure in *status and moves on.
+__device__ __forceinline__ void meet_peers(uint32_t* const* pads, int rank, int world, int slot0, int* status,
+                                           unsigned long long timeout_ns) {
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        const int peer = threadIdx.x;
+        uint32_t* put = pads[peer] + slot0 + (int)blockIdx.x * world + rank;
+        uint32_t* wait = pads[rank] + slot0 + (int)blockIdx.x * world + peer;
+        const unsigned long long t0 = gtimer();
+        bool ok = true;
+        while (cas_release_sys(put, 0u, 1u) != 0u)
+            if (gtimer() - t0 > timeout_ns) { ok = false; break; }
+        while (ok && cas_acquire_sys(wait, 1u, 0u) != 1u)
+            if (gtimer() - t0 > timeout_ns) { ok = false; break; }
+        if (!ok) atomicExch(status, 1);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float4 mc_ld_reduce(const float* mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st(float* mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+constexpr int NVL_THREADS = 512;
+constexpr int NVL_MAX_WORLD = 16;
+
+struct NvlPtrs {
+    float* buf[NVL_MAX_WORLD];
+    uint32_t* pad[NVL_MAX_WORLD];
+};
+
+__global__ void __launch_bounds__(NVL_THREADS)
+nvl_allreduce_kernel(const NvlPtrs P, float* mc, const int rank, const int world, const long long off,
+                     const long long n4 /* 16-byte vectors */, const int slot0, int* status,
+                     const unsigned long long timeout_ns) {
+    meet_peers(P.pad, rank, world, slot0, status, timeout_ns);
+    // slice of this rank, then this block's share of it
+    const long long per_rank = (n4 + world - 1) / world;
+    const long long r0 = rank * per_rank, r1 = r0 + per_rank < n4 ? r0 + per_rank : n4;
+    const long long base4 = off >> 2;
+    if (mc) {
+        float4* m4 = reinterpret_cast<float4*>(mc) + base4;
+        for (long long i = r0 + (long long)blockIdx.x * NVL_THREADS + threadIdx.x; i < r1;
+             i += (long long)gridDim.x * NVL_THREADS) {
+            const float4 v = mc_ld_reduce(reinterpret_cast<const float*>(m4 + i));
+            mc_st(reinterpret_cast<float*>(m4 + i), v);
+        }
+    } else {
+        for (long long i = r0 + (long long)blockIdx.x * NVL_THREADS + threadIdx.x; i < r1;
+             i += (long long)gridDim.x * NVL_THREADS) {
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int p = 0; p < world; ++p) {                    // fixed order: identical sums on every rank
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(P.buf[p]) + base4 + i);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+            for (int p = 0; p < world; ++p) __stcg(reinterpret_cast<float4*>(P.buf[p]) + base4 + i, s);
+        }
+    }
+    __threadfence_system();
+    meet_peers(P.pad, rank, world, slot0, status, timeout_ns);
+}
+
+}  // namespace m2d
+
+using namespace m2d;
+
+extern "C" int m2d_nvl_allreduce(float* const* bufs, float* mc, unsigned int* const* signal_pads, int rank, int world,
+                                 long long off, long long n, int blocks, int slot0, int* status, void* stream) {
+    M2D_REQUIRE(bufs && signal_pads && status && world >= 2 && world <= NVL_MAX_WORLD && rank >= 0 && rank < world,
+                "nvl_allreduce: bad args");
+    M2D_REQUIRE(n > 0 && (n & 3) == 0 && (off & 3) == 0 && blocks > 0 && blocks <= 64 && slot0 >= 0,
+                "nvl_allreduce: n and off must be multiples of 4 floats, 1 <= blocks <= 64");
+    NvlPtrs P;
+    for (int r = 0; r < world; ++r) {
+        M2D_REQUIRE(bufs[r] && signal_pads[r] && aligned16(bufs[r]), "nvl_allreduce: null / unaligned peer pointer");
+        P.buf[r] = bufs[r];
+        P.pad[r] = signal_pads[r];
+    }
+    M2D_REQUIRE(!mc || aligned16(mc), "nvl_allreduce: unaligned multicast pointer");
+    nvl_allreduce_kernel<<<blocks, NVL_THREADS, 0, (cudaStream_t)stream>>>(P, mc, rank, world, off, n >> 2, slot0, status,
+                                                                          2000000000ull /* 2 s */);
+    return check_launch("nvl_allreduce");
+}

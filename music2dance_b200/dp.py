@@ -50,3 +50,66 @@ def flatten_grads(named_grads, out=None):
         offsets[n] = (o, s)
         o += (s + 3) // 4 * 4
     return out, offsets
+
+
+class NvlAllReduce:
+    """Gradient all-reduce over NVLink / NVSwitch peer memory: hand-written kernel `m2d_nvl_allreduce` (two-shot,
+    NVLink-SHARP multimem.ld_reduce / multimem.st when the buffers have a multicast mapping, peer loads / stores
+    otherwise) on buffers allocated from torch's symmetric-memory allocator.  It is an ordinary kernel launch on the
+    caller's stream, so it is captured into the train step's CUDA graph like everything else — no NCCL call, no
+    graph split at the collective.  One instance per process; `alloc` must be called in the same order on every rank."""
+
+    def __init__(self, group=None, device=None, blocks=32, pad_bytes=16384):
+        import ctypes as C
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self._C, self._symm = C, symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.blocks = blocks
+        if symm.get_signal_pad_size() < pad_bytes:
+            symm.set_signal_pad_size(pad_bytes)
+        self.pad_slots = symm.get_signal_pad_size() // 4
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.regs = []                     # (tensor, handle, peer pointer array, pad pointer array, multicast pointer)
+        self.multicast = None
+
+    def alloc(self, n):
+        """Zeroed symmetric float buffer of n floats, mapped on every rank (collective call)."""
+        C = self._C
+        t = self._symm.empty(n, dtype=torch.float32, device=self.device)
+        hdl = self._symm.rendezvous(t, self.group)
+        t.zero_()
+        ptrs = (C.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
+        pads = (C.c_void_p * self.world)(*[int(p) for p in hdl.signal_pad_ptrs])
+        mc = int(hdl.multicast_ptr) if getattr(hdl, "has_multicast_support", False) and hdl.multicast_ptr else 0
+        assert int(ptrs[self.rank]) == t.data_ptr(), "symmetric-memory handle does not map the local tensor at offset 0"
+        self.regs.append((t, hdl, ptrs, pads, mc))
+        self.multicast = bool(mc) if self.multicast is None else (self.multicast and bool(mc))
+        return t
+
+    def _reg_of(self, t):
+        p = t.data_ptr()
+        for r in self.regs:
+            base = r[0].data_ptr()
+            if base <= p < base + 4 * r[0].numel():
+                return r, (p - base) // 4
+        raise ValueError("tensor is not a view of a buffer from NvlAllReduce.alloc")
+
+    def all_reduce_sum_(self, t, slot=0, blocks=None):
+        """In-place sum over the ranks of the flat float view `t` (numel and offset multiples of 4).  `slot`: distinct
+        per call site that may be in flight concurrently with another one on the same buffer (flag-array region)."""
+        from . import ops
+        (buf, _, ptrs, pads, mc), off = self._reg_of(t)
+        nb = blocks or self.blocks
+        slot0 = slot * self.blocks * self.world
+        assert slot0 + nb * self.world <= self.pad_slots, "signal pad too small for this many concurrent call sites"
+        n = t.numel()
+        assert n % 4 == 0 and off % 4 == 0 and t.is_contiguous()
+        ops.nvl_allreduce(ptrs, mc, pads, self.rank, self.world, off, n, nb, slot0, self.status)
+
+    def check(self):
+        """Raise if any launch so far timed out waiting for a peer (synchronises)."""
+        if int(self.status.item()) != 0:
+            raise RuntimeError("m2d_nvl_allreduce: a peer did not reach the collective within 2 s")

@@ -10,6 +10,11 @@ import torch
 from . import ops
 from .nets import CriticNet, GeneratorNet
 
+# allocator of the gradient buffers (n floats -> zeroed flat tensor).  The data-parallel trainer swaps in the
+# symmetric-memory allocator of dp.NvlAllReduce while it builds its engines, so that the kernels write their gradients
+# straight into buffers every GPU of the node has mapped.
+GRAD_ALLOC = [None]
+
 _DEAD = re.compile(r"decoder\.blocks\.\d+\.(fc1|bn1)\.(weight|bias)$")   # Q1: never receive a gradient
 
 
@@ -51,8 +56,9 @@ class FlatParams:
         self.n_live_padded = offs[len(live)] if dead else o
         self.n_plain_padded = offs[n_plain] if n_plain < len(live) else self.n_live_padded
         self.flat = torch.zeros(o, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(o, dtype=torch.float32, device=dev)
-        self.gpk = torch.zeros(max(self.n_live_padded - self.n_plain_padded, 4), dtype=torch.float32, device=dev)
+        galloc = GRAD_ALLOC[0] or (lambda n: torch.zeros(n, dtype=torch.float32, device=dev))
+        self.grad = galloc(o)
+        self.gpk = galloc(max(self.n_live_padded - self.n_plain_padded, 4))
         self.P, self.G, self.params = OrderedDict(), GradDict(), OrderedDict()
         with torch.no_grad():
             for (n, p), off in zip(self.order, offs):

@@ -393,6 +393,13 @@ def adam_pack(table, n, smem_floats, counters, lr, b1=0.9, b2=0.999, eps=1e-8, g
     call("m2d_adam_pack", _p(table), n, smem_floats, _p(counters), lr, b1, b2, eps, gscale, _stream())
 
 
+def nvl_allreduce(ptrs, mc, pads, rank, world, off, n, blocks, slot0, status):
+    """ptrs / pads: ctypes arrays of `world` device pointers (this process's mappings of every rank's buffer / flags)."""
+    LAUNCHES[0] += 1
+    call("m2d_nvl_allreduce", ptrs, C.c_void_p(mc) if mc else None, pads, rank, world, off, n, blocks, slot0,
+         _p(status), _stream())
+
+
 GEMM_MODES = {"fp32": 0, "tf32": 1, "tf32bf16": 2, "tf32x3": 3}
 
 

@@ -33,7 +33,11 @@ LOG_GEN = ("loss_gen", "l1", "tv", "err_real", "err_fake")
 
 
 class Phase3Trainer:
-    def __init__(self, gen, critic, cfg, batch_size, use_graphs=True, process_group=None, per_iteration_graphs=False):
+    def __init__(self, gen, critic, cfg, batch_size, use_graphs=True, process_group=None, per_iteration_graphs=False,
+                 collective=None):
+        """collective (world_size > 1): "nvl" = gradient all-reduce by the hand-written NVLink peer-memory kernel
+        (dp.NvlAllReduce; the whole step stays ONE CUDA graph), "nccl" = torch.distributed all-reduce between
+        per-iteration graphs, None = "nvl" when symmetric memory is available on every rank, else "nccl"."""
         dev = next(gen.parameters()).device
         assert dev.type == "cuda", "Phase3Trainer needs the modules on a CUDA device"
         self.dev, self.cfg, self.B = dev, cfg, batch_size
@@ -42,17 +46,33 @@ class Phase3Trainer:
         gen.cutting_stride, gen.pad_samples = cfg["cutting_stride"], cfg["pad_samples"]
         gen.__dict__.pop("_m2d_engine", None)
         self.gen, self.critic = gen, critic
+        self.pg = process_group
+        self.world = dp.world_size(process_group)
+        self.nvl = self._make_nvl(collective, dev) if self.world > 1 else None
+        from . import engine as _engine_mod
         with torch.cuda.device(dev):
-            self.ge, self.de = gen._engine(), critic._engine()
+            if self.nvl is not None:                     # gradients are written straight into node-mapped buffers
+                critic.__dict__.pop("_m2d_engine", None)
+                _engine_mod.GRAD_ALLOC[0] = self.nvl.alloc
+            try:
+                self.ge, self.de = gen._engine(), critic._engine()
+            finally:
+                _engine_mod.GRAD_ALLOC[0] = None
             self.G, self.D = self.ge.net, self.de.net
+            if self.world > 1:
+                # every replica starts from rank 0's parameters and BatchNorm buffers (identical seeds make this a
+                # no-op; a resumed or re-seeded rank must not silently diverge)
+                import torch.distributed as dist
+                with torch.no_grad():
+                    for t in [self.ge.fp.flat, self.de.fp.flat] + [b for _, b in gen.named_buffers()]:
+                        dist.broadcast(t, 0, group=process_group)
             self.ge.net.pack()
             self.de.net.pack()
         self.ge.packed_version, self.de.packed_version = self.ge.fp.version(), self.de.fp.version()
-        self.pg = process_group
-        self.world = dp.world_size(process_group)
-        # multi-GPU runs replay one graph per critic iteration (the all-reduce sits between graphs); the flag selects
-        # that structure on a single GPU too (tests exercise it without a second device)
-        self.per_iter = per_iteration_graphs or self.world > 1
+        # NCCL runs replay one graph per critic iteration (the all-reduce sits between graphs); the flag selects that
+        # structure on a single GPU too (tests exercise it without a second device).  With the peer-memory kernel the
+        # collective is just another launch, so the multi-GPU step is ONE graph like the single-GPU one.
+        self.per_iter = per_iteration_graphs or (self.world > 1 and self.nvl is None)
         B, T, O, A, Nz, nc = self.B, self.T, self.O, self.A, self.Nz, self.nc
         f = dict(dtype=torch.float32, device=dev)
         # staged inputs of one train step (device resident)
@@ -80,6 +100,10 @@ class Phase3Trainer:
                 late = [self.D.a_layers[4], self.D.a_l6]
                 self.apD = AdamPack(self.de.fp, self.D, self.mD, self.vD, exclude=late)
                 self.apD_late = AdamPack(self.de.fp, self.D, self.mD, self.vD, only=late)
+                # audio_d.l5 / l6 are the last two tap-major weights of the arena: their gradients are one contiguous tail
+                self._late_off = (late[0].gwp.data_ptr() - self.de.fp.gpk.data_ptr()) // 4
+                assert late[1].gwp.data_ptr() == late[0].gwp.data_ptr() + 4 * ((late[0].gwp.numel() + 3) // 4 * 4)
+                assert self._late_off % 4 == 0
             else:
                 self.apD = AdamPack(self.de.fp, self.D, self.mD, self.vD)
                 self.apD_late = None
@@ -97,9 +121,55 @@ class Phase3Trainer:
         self.fused_backward = os.environ.get("M2D_FUSED_BWD", "1") != "0"
 
     # ------------------------------------------------------------------ pieces
+    def _make_nvl(self, collective, dev):
+        """dp.NvlAllReduce if requested / available on EVERY rank (agreed on through one NCCL all-reduce), else None."""
+        import torch.distributed as dist
+        if collective == "nccl":
+            return None
+        nvl, err = None, None
+        try:
+            with torch.cuda.device(dev):
+                nvl = dp.NvlAllReduce(self.pg, dev)
+                probe = nvl.alloc(1024)                      # exercises allocation + rendezvous on every rank
+                probe.fill_(1.0)
+                torch.cuda.synchronize(dev)
+                dist.barrier(group=self.pg)
+                nvl.all_reduce_sum_(probe, slot=0, blocks=2)
+                torch.cuda.synchronize(dev)
+                nvl.check()
+                if abs(float(probe.sum().item()) - 1024.0 * self.world) > 1e-3:
+                    raise RuntimeError(f"peer-memory all-reduce probe returned {float(probe.sum().item())}")
+        except Exception as e:                                # noqa: BLE001
+            nvl, err = None, e
+        ok = torch.tensor([1 if nvl is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.pg)
+        if int(ok.item()) == 0:
+            if collective == "nvl":
+                raise RuntimeError(f"collective='nvl' requested but the peer-memory path is unavailable: {err!r}")
+            self.nvl_error = repr(err)
+            return None
+        return nvl
+
+    def _nvl_reduce(self, eng, part):
+        """Peer-memory all-reduce of one network's gradient buffers.  part: "all", or for the critic with split
+        tables "early" (everything but audio_d.l5 / l6) / "late"."""
+        plain, *rest = eng.fp.grad_buffers()
+        base = 0 if eng is self.de else 3
+        if part in ("all", "early") and plain.numel():
+            self.nvl.all_reduce_sum_(plain, slot=base, blocks=4)
+        if not rest:
+            return
+        gpk = rest[0]
+        cut = self._late_off if (eng is self.de and self.apD_late is not None) else gpk.numel()
+        if part in ("all", "early") and cut > 0:
+            self.nvl.all_reduce_sum_(gpk[:cut], slot=base + 1)
+        if part in ("all", "late") and cut < gpk.numel():
+            self.nvl.all_reduce_sum_(gpk[cut:], slot=base + 2)
+
     def _all_reduce(self, eng):
-        """Sum of the gradient buffers an optimiser step reads (engine.FlatParams.grad_buffers) over the ranks."""
-        if self.world > 1:
+        """NCCL path: sum of the gradient buffers an optimiser step reads (engine.FlatParams.grad_buffers) over the
+        ranks, issued between the per-iteration graphs."""
+        if self.world > 1 and self.nvl is None:
             for t in eng.fp.grad_buffers():
                 dp.all_reduce_sum_(t, self.pg)
 
@@ -108,16 +178,25 @@ class Phase3Trainer:
         convolution weights).  late_fork: run the critic's late table on the re-layout side stream (True), inline
         (False), or decide from the step structure (None)."""
         gs = 1.0 / self.world
+        nvl = self.nvl is not None
         if eng is self.ge:
+            if nvl:
+                self._nvl_reduce(eng, "all")
             self.apG.step(lr, gs)
             ops.mark("adam_pack")
             return
         if self.apD_late is not None:
+            def late():
+                if nvl:
+                    self._nvl_reduce(eng, "late")
+                self.apD_late.step(lr, gs)
             fork = (not self.per_iter and self.overlap and self.split_pack) if late_fork is None else late_fork
             if fork:
-                self.D.late_fork(lambda: self.apD_late.step(lr, gs))
+                self.D.late_fork(late)
             else:
-                self.apD_late.step(lr, gs)
+                late()
+        if nvl:
+            self._nvl_reduce(eng, "early" if self.apD_late is not None else "all")
         self.apD.step(lr, gs)
         ops.mark("adam_pack")
 

@@ -495,7 +495,14 @@ def test_adam_pack_matches_unpack_adam_pack(which, variant):
             t.step(2e-4, gscale=0.5)
         torch.cuda.synchronize()
         assert all(int(t.counters[0]) == it + 1 and int(t.counters[1]) == 0 for t in tabs)
-        assert torch.equal(ea.fp.flat, eb.fp.flat), f"{which}/{variant}: parameters differ after step {it}"
+        if not torch.equal(ea.fp.flat, eb.fp.flat):
+            bad = []
+            for (na, pa), (_, pb) in zip(ea.fp.params.items(), eb.fp.params.items()):
+                if not torch.equal(pa, pb):
+                    d = (pa - pb).abs()
+                    bad.append((na, tuple(pa.shape), int((d > 0).sum()), float(d.max()),
+                                (d > 0).nonzero()[:3].tolist()))
+            raise AssertionError(f"{which}/{variant}: parameters differ after step {it}: {bad[:6]}")
         assert torch.equal(st["a"][0], st["b"][0]) and torch.equal(st["a"][1], st["b"][1]), "Adam moments differ"
         for ca, cb in zip(convs_a, convs_b):
             for name in ("wp", "wpt", "wd", "wdt", "wdm", "wdmt"):
