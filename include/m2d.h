@@ -60,6 +60,9 @@ int m2d_check_device(int dev);
 enum { M2D_GEMM_FP32 = 0, M2D_GEMM_TF32 = 1, M2D_GEMM_TF32_BF16 = 2, M2D_GEMM_TF32X3 = 3 };
 /* number of m2d_rowconv calls served by the TMA halo-tile kernel so far (diagnostics / tests) */
 long long m2d_halo_launch_count(void);
+/* ... of which by its persistent variant (one CTA per SM over a static tile list, double-buffered TMEM accumulators,
+ * epilogue overlapped with the next tile's MMAs): launches with >= 148 tiles and no split-K */
+long long m2d_halo_persist_launch_count(void);
 int m2d_set_gemm_mode(int mode);
 int m2d_get_gemm_mode(void);
 
@@ -362,6 +365,11 @@ int m2d_adam_pack(const m2d_adam_item* items, int n, int smem_floats, int* count
  * ---------------------------------------------------------------------- */
 int m2d_nvl_allreduce(float* const* bufs, float* mc, unsigned int* const* signal_pads, int rank, int world,
                       long long off, long long n, int blocks, int slot0, int* status, void* stream);
+/* the same over TWO ranges (of possibly different mapped buffers) between one pair of handshakes: the small
+ * parameter-layout gradients and the tap-major arena of a network in one launch; the flags of the first buffer */
+int m2d_nvl_allreduce2(float* const* bufs, float* mc, long long off, long long n, float* const* bufs2, float* mc2,
+                       long long off2, long long n2, unsigned int* const* signal_pads, int rank, int world, int blocks,
+                       int slot0, int* status, void* stream);
 
 /* Diagnostics (tools/step_timeline.py): *slot = %globaltimer (ns) when `stream` reaches this point; graph-capturable,
  * so the replayed train step can be cut into phases without a profiler attached. */

@@ -60,6 +60,7 @@ SIGNATURES = {
     "m2d_set_gemm_mode": [_I],
     "m2d_get_gemm_mode": [],
     "m2d_halo_launch_count": [],
+    "m2d_halo_persist_launch_count": [],
     "m2d_rowconv": [C.POINTER(RowConvArgs), _P],
     "m2d_wgrad": [C.POINTER(WgradArgs), _P],
     "m2d_wgrad_min_ws": [_I, _I, _I],
@@ -104,10 +105,12 @@ SIGNATURES = {
     "m2d_adam": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _P],
     "m2d_adam_pack": [_P, _I, _I, _P, _F, _F, _F, _F, _F, _P],
     "m2d_nvl_allreduce": [_P, _P, _P, _I, _I, _L, _L, _I, _I, _P, _P],
+    "m2d_nvl_allreduce2": [_P, _P, _L, _L, _P, _P, _L, _L, _P, _I, _I, _I, _I, _P, _P],
     "m2d_timestamp": [_P, _P],
 }
-_RESTYPE = {"m2d_wgrad_min_ws": i64, "m2d_halo_launch_count": i64}
-_NOCHECK = {"m2d_wgrad_min_ws", "m2d_version", "m2d_get_gemm_mode", "m2d_halo_launch_count"}     # return a value, not a status
+_RESTYPE = {"m2d_wgrad_min_ws": i64, "m2d_halo_launch_count": i64, "m2d_halo_persist_launch_count": i64}
+_NOCHECK = {"m2d_wgrad_min_ws", "m2d_version", "m2d_get_gemm_mode", "m2d_halo_launch_count",
+            "m2d_halo_persist_launch_count"}     # return a value, not a status
 
 _lib = None
 

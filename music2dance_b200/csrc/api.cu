@@ -36,8 +36,9 @@ extern "C" int m2d_get_gemm_mode(void) { return m2d::g_gemm_mode; }
 
 extern "C" const char* m2d_last_error(void) { return m2d::g_err; }
 extern "C" int m2d_version(void) { return 100; }
-namespace m2d { long long halo_launch_count(); }
+namespace m2d { long long halo_launch_count(); long long halo_persist_launch_count(); }
 extern "C" long long m2d_halo_launch_count(void) { return m2d::halo_launch_count(); }
+extern "C" long long m2d_halo_persist_launch_count(void) { return m2d::halo_persist_launch_count(); }
 
 extern "C" int m2d_check_device(int dev) {
     cudaDeviceProp p;

@@ -62,16 +62,13 @@ constexpr int NVL_THREADS = 512;
 constexpr int NVL_MAX_WORLD = 16;
 
 struct NvlPtrs {
-    float* buf[NVL_MAX_WORLD];
+    float* buf[NVL_MAX_WORLD];           // segment 0: every rank's mapping of the buffer
+    float* buf2[NVL_MAX_WORLD];          // optional segment 1 (another symmetric buffer), same handshakes
     uint32_t* pad[NVL_MAX_WORLD];
 };
 
-__global__ void __launch_bounds__(NVL_THREADS)
-nvl_allreduce_kernel(const NvlPtrs P, float* mc, const int rank, const int world, const long long off,
-                     const long long n4 /* 16-byte vectors */, const int slot0, int* status,
-                     const unsigned long long timeout_ns) {
-    meet_peers(P.pad, rank, world, slot0, status, timeout_ns);
-    // slice of this rank, then this block's share of it
+// reduce + broadcast this block's share of rank `rank`'s slice of one segment
+__device__ __forceinline__ void nvl_segment(float* const* buf, float* mc, int rank, int world, long long off, long long n4) {
     const long long per_rank = (n4 + world - 1) / world;
     const long long r0 = rank * per_rank, r1 = r0 + per_rank < n4 ? r0 + per_rank : n4;
     const long long base4 = off >> 2;
@@ -87,12 +84,21 @@ nvl_allreduce_kernel(const NvlPtrs P, float* mc, const int rank, const int world
              i += (long long)gridDim.x * NVL_THREADS) {
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int p = 0; p < world; ++p) {                    // fixed order: identical sums on every rank
-                const float4 v = __ldcg(reinterpret_cast<const float4*>(P.buf[p]) + base4 + i);
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(buf[p]) + base4 + i);
                 s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
             }
-            for (int p = 0; p < world; ++p) __stcg(reinterpret_cast<float4*>(P.buf[p]) + base4 + i, s);
+            for (int p = 0; p < world; ++p) __stcg(reinterpret_cast<float4*>(buf[p]) + base4 + i, s);
         }
     }
+}
+
+__global__ void __launch_bounds__(NVL_THREADS)
+nvl_allreduce_kernel(const NvlPtrs P, float* mc, const int rank, const int world, const long long off,
+                     const long long n4 /* 16-byte vectors */, float* mc2, const long long off2, const long long n4_2,
+                     const int slot0, int* status, const unsigned long long timeout_ns) {
+    meet_peers(P.pad, rank, world, slot0, status, timeout_ns);
+    nvl_segment(P.buf, mc, rank, world, off, n4);
+    if (n4_2 > 0) nvl_segment(P.buf2, mc2, rank, world, off2, n4_2);
     __threadfence_system();
     meet_peers(P.pad, rank, world, slot0, status, timeout_ns);
 }
@@ -101,20 +107,35 @@ nvl_allreduce_kernel(const NvlPtrs P, float* mc, const int rank, const int world
 
 using namespace m2d;
 
-extern "C" int m2d_nvl_allreduce(float* const* bufs, float* mc, unsigned int* const* signal_pads, int rank, int world,
-                                 long long off, long long n, int blocks, int slot0, int* status, void* stream) {
+static int nvl_launch(float* const* bufs, float* mc, long long off, long long n, float* const* bufs2, float* mc2,
+                      long long off2, long long n2, unsigned int* const* signal_pads, int rank, int world, int blocks,
+                      int slot0, int* status, void* stream) {
     M2D_REQUIRE(bufs && signal_pads && status && world >= 2 && world <= NVL_MAX_WORLD && rank >= 0 && rank < world,
                 "nvl_allreduce: bad args");
     M2D_REQUIRE(n > 0 && (n & 3) == 0 && (off & 3) == 0 && blocks > 0 && blocks <= 64 && slot0 >= 0,
                 "nvl_allreduce: n and off must be multiples of 4 floats, 1 <= blocks <= 64");
+    M2D_REQUIRE(n2 == 0 || (bufs2 && n2 > 0 && (n2 & 3) == 0 && (off2 & 3) == 0), "nvl_allreduce: bad second segment");
     NvlPtrs P;
     for (int r = 0; r < world; ++r) {
         M2D_REQUIRE(bufs[r] && signal_pads[r] && aligned16(bufs[r]), "nvl_allreduce: null / unaligned peer pointer");
         P.buf[r] = bufs[r];
+        P.buf2[r] = n2 ? bufs2[r] : nullptr;
+        M2D_REQUIRE(!n2 || (bufs2[r] && aligned16(bufs2[r])), "nvl_allreduce: null / unaligned peer pointer (segment 1)");
         P.pad[r] = signal_pads[r];
     }
-    M2D_REQUIRE(!mc || aligned16(mc), "nvl_allreduce: unaligned multicast pointer");
-    nvl_allreduce_kernel<<<blocks, NVL_THREADS, 0, (cudaStream_t)stream>>>(P, mc, rank, world, off, n >> 2, slot0, status,
-                                                                          2000000000ull /* 2 s */);
+    M2D_REQUIRE((!mc || aligned16(mc)) && (!mc2 || aligned16(mc2)), "nvl_allreduce: unaligned multicast pointer");
+    nvl_allreduce_kernel<<<blocks, NVL_THREADS, 0, (cudaStream_t)stream>>>(P, mc, rank, world, off, n >> 2, mc2, off2,
+                                                                          n2 >> 2, slot0, status, 2000000000ull /* 2 s */);
     return check_launch("nvl_allreduce");
+}
+
+extern "C" int m2d_nvl_allreduce(float* const* bufs, float* mc, unsigned int* const* signal_pads, int rank, int world,
+                                 long long off, long long n, int blocks, int slot0, int* status, void* stream) {
+    return nvl_launch(bufs, mc, off, n, nullptr, nullptr, 0, 0, signal_pads, rank, world, blocks, slot0, status, stream);
+}
+
+extern "C" int m2d_nvl_allreduce2(float* const* bufs, float* mc, long long off, long long n, float* const* bufs2,
+                                  float* mc2, long long off2, long long n2, unsigned int* const* signal_pads, int rank,
+                                  int world, int blocks, int slot0, int* status, void* stream) {
+    return nvl_launch(bufs, mc, off, n, bufs2, mc2, off2, n2, signal_pads, rank, world, blocks, slot0, status, stream);
 }

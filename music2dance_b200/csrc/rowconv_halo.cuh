@@ -471,7 +471,10 @@ static int launch_halo(const m2d_rowconv_args& a, const HaloPlan& plan, int tpb,
     return launch_clustered("rowconv_halo", kern, grid, smem, Z, st, HL_THREADS, a, plan, tpb, NA, NB, brows, trace, *mx);
 }
 
+#include "rowconv_halo_persist.cuh"
+
 static long long g_halo_launches = 0;
+static long long g_halo_persist_launches = 0;
 
 // Returns 1 when the shape is not served by the halo kernel (caller continues with rowconv_tc_kernel).
 static int rowconv_halo_dispatch(const m2d_rowconv_args& a, int M, int mode, cudaStream_t st) {
@@ -509,6 +512,16 @@ static int rowconv_halo_dispatch(const m2d_rowconv_args& a, int M, int mode, cud
     }
     ++g_halo_launches;
     static const int trace_on = halo_env("M2D_HALO_TRACE", 0);
+    // at least one full wave of tiles and no split-K: persistent CTAs with double-buffered accumulators (the epilogue
+    // of a tile overlaps the next tile's MMAs); M2D_HALO_PERSIST=0 keeps the one-tile-per-CTA kernel
+    static const int persist_on = halo_env("M2D_HALO_PERSIST", 1);
+    static const int persist_min = halo_env("M2D_HALO_PERSIST_MIN", kNumSMs);
+    if (persist_on && !trace_on && splits == 1 && tiles >= persist_min) {
+        ++g_halo_persist_launches;
+        if (mode == M2D_GEMM_TF32_BF16) return launch_halo_persist<2>(a, plan, tpb, st, NA, NB, brows, mx);
+        return mode == 3 ? launch_halo_persist<3>(a, plan, tpb, st, NA, NB, brows, mx)
+                         : launch_halo_persist<1>(a, plan, tpb, st, NA, NB, brows, mx);
+    }
     if (mode == M2D_GEMM_TF32_BF16) return launch_halo<2, false>(a, plan, tpb, splits, st, NA, NB, brows, mx);
     if (trace_on)
         return mode == 3 ? launch_halo<3, true>(a, plan, tpb, splits, st, NA, NB, brows, mx)

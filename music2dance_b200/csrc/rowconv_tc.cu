@@ -523,6 +523,7 @@ static int launch_tc_shape(const m2d_rowconv_args& a, int M, int nsteps, int cch
 #include "rowconv_halo.cuh"
 
 long long halo_launch_count() { return g_halo_launches; }
+long long halo_persist_launch_count() { return g_halo_persist_launches; }
 
 // Called by m2d_rowconv when the tensor-core path is selected.  Returns 1 if the shape is
 // not worth a tensor-core launch (caller falls through to the SIMT kernel), <= 0 otherwise.

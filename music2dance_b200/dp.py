@@ -109,6 +109,19 @@ class NvlAllReduce:
         assert n % 4 == 0 and off % 4 == 0 and t.is_contiguous()
         ops.nvl_allreduce(ptrs, mc, pads, self.rank, self.world, off, n, nb, slot0, self.status)
 
+    def all_reduce_sum2_(self, t, t2, slot=0, blocks=None):
+        """Both flat views in ONE launch (one pair of handshakes); the flag array of `t`'s buffer is used."""
+        from . import ops
+        (_, _, ptrs, pads, mc), off = self._reg_of(t)
+        (_, _, ptrs2, _, mc2), off2 = self._reg_of(t2)
+        nb = blocks or self.blocks
+        slot0 = slot * self.blocks * self.world
+        assert slot0 + nb * self.world <= self.pad_slots
+        for x, o in ((t, off), (t2, off2)):
+            assert x.numel() % 4 == 0 and o % 4 == 0 and x.is_contiguous()
+        ops.nvl_allreduce2(ptrs, mc, off, t.numel(), ptrs2, mc2, off2, t2.numel(), pads, self.rank, self.world, nb,
+                           slot0, self.status)
+
     def check(self):
         """Raise if any launch so far timed out waiting for a peer (synchronises)."""
         if int(self.status.item()) != 0:

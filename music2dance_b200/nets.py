@@ -811,6 +811,12 @@ class CriticNet:
             ops.pack_batch(*tabs[1])
         self._late_pack = True
 
+    def comm_stream(self):
+        """Stream of the data-parallel early-bucket all-reduce (next to the last weight-gradient GEMMs)."""
+        if getattr(self, "s_comm", None) is None:
+            self.s_comm = torch.cuda.Stream(device=self.dev)
+        return self.s_comm
+
     def late_fork(self, fn):
         """Run `fn` (the optimiser step of audio_d.l5 / l6) on the re-layout side stream, ordered after the current
         stream; the next audio_fwd joins it right before l5 (same protocol as pack_late_fork)."""

@@ -400,6 +400,12 @@ def nvl_allreduce(ptrs, mc, pads, rank, world, off, n, blocks, slot0, status):
          _p(status), _stream())
 
 
+def nvl_allreduce2(ptrs, mc, off, n, ptrs2, mc2, off2, n2, pads, rank, world, blocks, slot0, status):
+    LAUNCHES[0] += 1
+    call("m2d_nvl_allreduce2", ptrs, C.c_void_p(mc) if mc else None, off, n, ptrs2, C.c_void_p(mc2) if mc2 else None,
+         off2, n2, pads, rank, world, blocks, slot0, _p(status), _stream())
+
+
 GEMM_MODES = {"fp32": 0, "tf32": 1, "tf32bf16": 2, "tf32x3": 3}
 
 

@@ -151,20 +151,24 @@ class Phase3Trainer:
         return nvl
 
     def _nvl_reduce(self, eng, part):
-        """Peer-memory all-reduce of one network's gradient buffers.  part: "all", or for the critic with split
-        tables "early" (everything but audio_d.l5 / l6) / "late"."""
+        """Peer-memory all-reduce of one network's gradient buffers.  part: "all"; for the critic with split tables
+        "plain" (parameter-layout gradients: biases, audio_d.l1, fusion MLP), "early" (tap-major arena without
+        audio_d.l5 / l6), "plain+early" (both in one launch), "late" (audio_d.l5 / l6)."""
         plain, *rest = eng.fp.grad_buffers()
-        base = 0 if eng is self.de else 3
-        if part in ("all", "early") and plain.numel():
+        base = 0 if eng is self.de else 4
+        gpk = rest[0] if rest else None
+        cut = self._late_off if (eng is self.de and self.apD_late is not None) else (gpk.numel() if rest else 0)
+        if part == "plain":
             self.nvl.all_reduce_sum_(plain, slot=base, blocks=4)
-        if not rest:
-            return
-        gpk = rest[0]
-        cut = self._late_off if (eng is self.de and self.apD_late is not None) else gpk.numel()
-        if part in ("all", "early") and cut > 0:
+        elif part == "early":
             self.nvl.all_reduce_sum_(gpk[:cut], slot=base + 1)
-        if part in ("all", "late") and cut < gpk.numel():
+        elif part == "late":
             self.nvl.all_reduce_sum_(gpk[cut:], slot=base + 2)
+        elif part == "plain+early" or (part == "all" and rest):
+            hi = cut if part == "plain+early" else gpk.numel()
+            self.nvl.all_reduce_sum2_(gpk[:hi], plain, slot=base + 3)
+        else:
+            self.nvl.all_reduce_sum_(plain, slot=base, blocks=4)
 
     def _all_reduce(self, eng):
         """NCCL path: sum of the gradient buffers an optimiser step reads (engine.FlatParams.grad_buffers) over the
@@ -173,7 +177,7 @@ class Phase3Trainer:
             for t in eng.fp.grad_buffers():
                 dp.all_reduce_sum_(t, self.pg)
 
-    def _adam(self, eng, lr, late_fork=None):
+    def _adam(self, eng, lr, late_fork=None, early_reduced=False):
         """Adam + re-layout of one network (gradients are read where the kernels left them: tap-major for the
         convolution weights).  late_fork: run the critic's late table on the re-layout side stream (True), inline
         (False), or decide from the step structure (None)."""
@@ -196,7 +200,10 @@ class Phase3Trainer:
             else:
                 late()
         if nvl:
-            self._nvl_reduce(eng, "early" if self.apD_late is not None else "all")
+            if self.apD_late is None:
+                self._nvl_reduce(eng, "all")
+            else:
+                self._nvl_reduce(eng, "plain" if early_reduced else "plain+early")
         self.apD.step(lr, gs)
         ops.mark("adam_pack")
 
@@ -230,11 +237,15 @@ class Phase3Trainer:
             fw = critic_forward_fused(D, X3, None if D.ablated else audio, B, "c")
             d = fw["d"]
             aud2 = None if D.ablated else Mat(self.in_audio2[i], 2 * B, self.A, 1)
-            critic_backward_fused(D, fw, B, audio, gamma, self.gp_buf, self.k0, self.k1, aud2=aud2)
+            hook = None
+            if update and self.nvl is not None and self.apD_late is not None:
+                hook = lambda: self._nvl_reduce(self.de, "early")
+            early = critic_backward_fused(D, fw, B, audio, gamma, self.gp_buf, self.k0, self.k1, aud2=aud2,
+                                          early_reduce=hook)
             ops.wgan_scalars(None, self.gp_buf, B, 1, 1, gamma, 0.0, 0, self.log_c[i],
                              d_real=rows(d, B, 2 * B), d_fake=rows(d, 2 * B, n3))
             if update:
-                self._adam(self.de, self.cfg["lr_critic"])
+                self._adam(self.de, self.cfg["lr_critic"], early_reduced=bool(early))
             elif not self.per_iter:
                 D.unpack_grads()              # caller wants the gradients in the parameter layout (tests, tools)
             return

@@ -155,7 +155,7 @@ def critic_forward_fused(D, X3, audio, B, tag):
     return dict(svp=svp, sva=sva, sa=sa, u=u, d=d)
 
 
-def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f", aud2=None):
+def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f", aud2=None, early_reduce=None):
     """Critic gradients of  err_fake - err_real + gamma * gp  (phase3/train.py:204-215) in ONE backward sweep.
 
     Rows of the forward state: [0,B) interpolates, [B,2B) real, [2B,3B) fake.  The Wasserstein terms and the
@@ -260,12 +260,15 @@ def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f", aud2=
             # one weight-gradient GEMM per audio layer over the 2B stacked entries; biases from the Wasserstein half
             x = g1
             ws_a = wk.scratch                                      # per-stream scratch (Workspace.scratch)
+            ev_wa_early = None
             for i, l in enumerate(D.a_layers):
                 if par:
                     s_wa.wait_event(evs[i])
                 l.wgrad(dla[i], x, ws_a, scale=1.0, beta=0.0, bias=False)
                 ops.mark(f"{tag}:aud_wg_l{i + 1}")
                 x = sva["q2"][i]
+                if i == len(D.a_layers) - 2 and early_reduce is not None and par:
+                    ev_wa_early = after(s_wa)                     # audio_d.l1 .. l4 weight gradients done
             if par:
                 s_wa.wait_event(evs[len(D.a_layers)])
             D.a_l6.wgrad(d_a2.as_rows(2 * B, 1), x, ws_a, scale=1.0, beta=0.0, bias=False)
@@ -322,6 +325,15 @@ def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f", aud2=
                 s_wp.wait_event(ev)
             conv.wgrad(dl, x_in, ws_p, scale=1.0, beta=0.0, bias=False)
         ops.mark(f"{tag}:pose_wg_end")
+    early_done = False
+    if early_reduce is not None and par and not D.ablated and ev_wa_early is not None:
+        s_comm = D.comm_stream()
+        s_comm.wait_stream(s_wp)
+        s_comm.wait_event(ev_wa_early)
+        with torch.cuda.stream(s_comm):
+            early_reduce()
+            ops.mark(f"{tag}:early_reduce")
+        early_done = True
     if par and not D.ablated:
         main.wait_stream(s_ta)
     # fusion MLP: penalty part through the tangent of the codes
@@ -333,7 +345,10 @@ def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f", aud2=
         if not D.ablated:
             main.wait_stream(s_wa)
         main.wait_stream(s_wp)
+        if early_done:
+            main.wait_stream(s_comm)
     ops.mark(f"{tag}:bwd_end")
+    return early_done
 
 
 def wasserstein_backward(D, fw, r0, nR, signs, B, tag, beta, dX_rows=None, dX=None, param_grads=True):

@@ -510,3 +510,58 @@ def test_adam_pack_matches_unpack_adam_pack(which, variant):
                 assert (xa is None) == (xb is None)
                 if xa is not None and cb.gw is not None:
                     assert torch.equal(xa, xb), f"{ca.name}.{name} differs after step {it}"
+
+
+PERSIST_CASES = [
+    # Cin, Cout, k, s, p, L, B : at least one wave (148) of 128-row tiles without split-K
+    (32, 64, 25, 4, 11, 19200, 7),     # audio_d.l2 forward at the reference batch: 266 tiles, K = 800
+    (64, 128, 25, 4, 11, 4800, 16),    # audio_d.l3: 160 tiles
+    (128, 100, 7, 1, 3, 1000, 24),     # N = 100 (ragged column tile), 192 tiles
+    (32, 300, 3, 1, 1, 640, 16),       # three N tiles (128 + 128 + 44): weight blocks switch between tiles
+]
+
+
+@pytest.mark.parametrize("case", PERSIST_CASES)
+def test_persistent_halo_kernel(lib, case):
+    """rowconv_halo_persist_kernel (persistent CTAs, double-buffered TMEM accumulators, epilogue straight from tensor
+    memory): forward with bias + ReLU + second output, merged backward-data with mask + residual add, in-place masked
+    tangent pass — against torch fp32, and the launch must really take the persistent path."""
+    from music2dance_b200 import _lib
+    from music2dance_b200.ops import Mat
+    if CUR["mode"] == "fp32":
+        pytest.skip("tensor-core kernel")
+    Cin, Cout, k, s, p, L, B = case
+    lay, w, b = make_layer(Cin, Cout, k, s, p, L)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, Cin, L, generator=g)
+    xr = x.clone().requires_grad_(True)
+    pre = F.conv1d(xr, w, b, stride=s, padding=p)
+    y_ref = F.relu(pre)
+    Lout = y_ref.shape[-1]
+    scratch = torch.empty(1 << 22, device=DEV)
+    X = Mat.of(cl(x), B, L, Cin)
+    Y = Mat.of(torch.empty(B, Lout, Cout, device=DEV), B, Lout, Cout)
+    Y2 = Mat.of(torch.empty(B, Lout, Cout, device=DEV), B, Lout, Cout)
+    n0 = _lib.load().m2d_halo_persist_launch_count()
+    lay.fwd(X, Y, act=1, ws=scratch, y2=Y2)
+    assert _lib.load().m2d_halo_persist_launch_count() == n0 + 1, "shape did not take the persistent kernel"
+    close(ncl(Y, B, Lout, Cout), y_ref, what="persist fwd")
+    close(ncl(Y2, B, Lout, Cout), y_ref, what="persist fwd y2")
+    # in-place masked tangent: t = (conv(v) without bias) * relu'(y), written over the mask buffer itself
+    v = torch.randn(B, Cin, L, generator=g)
+    t_ref = F.conv1d(v, w, None, stride=s, padding=p) * (y_ref > 0).float()
+    lay.fwd(Mat.of(cl(v), B, L, Cin), Y2, bias=False, ws=scratch, mask=Y2, mask_mode=1)
+    close(ncl(Y2, B, Lout, Cout), t_ref, what="persist in-place tangent")
+    # backward-data with ReLU mask and residual add (add_before_mask both ways)
+    dy = torch.randn(B, Cout, Lout, generator=g)
+    pre.backward(dy)
+    msk, add = torch.randn(B, Cin, L, generator=g), torch.randn(B, Cin, L, generator=g)
+    D = Mat.of(cl(dy), B, Lout, Cout)
+    DX = Mat.of(torch.empty(B, L, Cin, device=DEV), B, L, Cin)
+    E2 = Mat.of(torch.empty(B, L, Cin, device=DEV), B, L, Cin)
+    lay.dgrad(D, DX, ws=scratch, mask=Mat.of(cl(msk), B, L, Cin), mask_mode=1, add=Mat.of(cl(add), B, L, Cin),
+              add_before_mask=True, y2=E2)
+    close(ncl(E2, B, L, Cin), xr.grad + add, what="persist dgrad y2")
+    close(ncl(DX, B, L, Cin), (xr.grad + add) * (msk > 0), what="persist dgrad add-before-mask")
+    lay.dgrad(D, DX, ws=scratch, mask=Mat.of(cl(msk), B, L, Cin), mask_mode=1, add=Mat.of(cl(add), B, L, Cin))
+    close(ncl(DX, B, L, Cin), xr.grad * (msk > 0) + add, what="persist dgrad add-after-mask")
