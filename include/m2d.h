@@ -181,6 +181,10 @@ int m2d_conv_dgrad_c1(const float* dy, int nb, int Lout, int Cout, const float* 
  * reductions, h pushed to the cluster with st.async + mbarrier transaction counts (one mbarrier wait per
  * step); 1 = weights in shared memory, cluster barrier per step (any H up to the smem limit). */
 int m2d_set_gru_impl(int impl);
+/* Sequences served by one thread-block cluster of the forward recurrence (impl 2): 0 = automatic (one sequence per
+ * cluster up to batch 18: lowest latency), 1..8 = that many (fewer SMs busy for slightly longer steps — what the fused
+ * trainer asks for, because its generator forwards run on a side stream next to the critic iterations). */
+int m2d_set_gru_forward_batch_group(int bg);
 int m2d_gru_forward(const float* gi, const float* w_hh, const float* b_hh,
                     float* h_out, int ldh, float* save, int B, int T, int H, void* stream);
 /* BPTT: dh_out[b,t,:H] (row stride ldd) upstream gradient; writes dgi, dgh [B,T,3H]. */

@@ -69,6 +69,7 @@ SIGNATURES = {
     "m2d_pack_batch": [_P, _I, _P],
     "m2d_conv_dgrad_c1": [_P, _I, _I, _I, _P, _I, _I, _I, _P, _I, _P],
     "m2d_set_gru_impl": [_I],
+    "m2d_set_gru_forward_batch_group": [_I],
     "m2d_gru_forward": [_P, _P, _P, _P, _I, _P, _I, _I, _I, _P],
     "m2d_gru_backward": [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _P],
     "m2d_colstats": [_P, _I, _L, _I, _P, _P],

@@ -570,14 +570,23 @@ static int launch_gru2_bwd(const float* dh_out, int ldd, const float* h_out, int
                           dgi, dgh, B, T, H, p.nu, p.BG);
 }
 
-namespace m2d { int g_gru_impl = 2; }
+namespace m2d { int g_gru_impl = 2; int g_gru_fwd_bg = 0; }
 extern "C" int m2d_set_gru_impl(int v) { m2d::g_gru_impl = v; return M2D_OK; }
+extern "C" int m2d_set_gru_forward_batch_group(int bg) {
+    if (bg < 0 || bg > GRU2_BGMAX) {
+        m2d::set_error("set_gru_forward_batch_group: 0 (automatic) .. %d", GRU2_BGMAX);
+        return M2D_ERR_BAD_ARG;
+    }
+    m2d::g_gru_fwd_bg = bg;
+    return M2D_OK;
+}
 
 extern "C" int m2d_gru_forward(const float* gi, const float* w_hh, const float* b_hh, float* h_out,
                                int ldh, float* save, int B, int T, int H, void* stream) {
     M2D_REQUIRE(gi && w_hh && b_hh && h_out && B > 0 && T > 0 && H > 0 && ldh >= H, "gru_forward: bad args");
     if (m2d::g_gru_impl == 2 && H <= 256) {
-        const Gru2Plan p = gru2_plan(B, H);
+        Gru2Plan p = gru2_plan(B, H);
+        if (m2d::g_gru_fwd_bg > 0) p.BG = m2d::g_gru_fwd_bg < B ? m2d::g_gru_fwd_bg : B;
         cudaStream_t st = (cudaStream_t)stream;
         switch (p.KC) {
             case 1: return launch_gru2<1>(gi, w_hh, b_hh, h_out, ldh, save, B, T, H, p, st);

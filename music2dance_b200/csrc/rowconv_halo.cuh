@@ -512,10 +512,11 @@ static int rowconv_halo_dispatch(const m2d_rowconv_args& a, int M, int mode, cud
     }
     ++g_halo_launches;
     static const int trace_on = halo_env("M2D_HALO_TRACE", 0);
-    // at least one full wave of tiles and no split-K: persistent CTAs with double-buffered accumulators (the epilogue
+    // several waves of tiles and no split-K: persistent CTAs with double-buffered accumulators (the epilogue
     // of a tile overlaps the next tile's MMAs); M2D_HALO_PERSIST=0 keeps the one-tile-per-CTA kernel
     static const int persist_on = halo_env("M2D_HALO_PERSIST", 1);
-    static const int persist_min = halo_env("M2D_HALO_PERSIST_MIN", kNumSMs);
+    // (measured on B200: with only two tiles per CTA the un-overlapped last epilogue eats the gain; three waves and more win)
+    static const int persist_min = halo_env("M2D_HALO_PERSIST_MIN", 3 * kNumSMs);
     if (persist_on && !trace_on && splits == 1 && tiles >= persist_min) {
         ++g_halo_persist_launches;
         if (mode == M2D_GEMM_TF32_BF16) return launch_halo_persist<2>(a, plan, tpb, st, NA, NB, brows, mx);

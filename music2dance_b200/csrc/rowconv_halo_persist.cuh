@@ -11,11 +11,13 @@
 // boundaries.  The epilogue reads its 128 x BN tile straight from tensor memory — thread = output row, 16 columns per
 // tcgen05.ld — and writes 64-byte row segments, so no shared-memory staging tile competes with the operand rings.
 //
-// Warp roles (512 threads): 0-7 converters, 8 MMA issuer, 9 weight loader, 10 activation loader, 11 idle,
-// 12-15 epilogue (warp w owns TMEM lanes 32*(w%4).. as tcgen05.ld requires).
+// Warp roles (640 threads): 0-7 converters, 8 MMA issuer, 9 weight loader, 10 activation loader, 11 idle,
+// 12-19 epilogue (warp w owns TMEM lanes 32*(w%4).. as tcgen05.ld requires; the two warps of a lane quarter
+// take alternate 16-column chunks).
 
-constexpr int HP_THREADS = 512;
+constexpr int HP_THREADS = 640;
 constexpr int HP_EPI0 = 12;                     // first epilogue warp
+constexpr int HP_EPI_WARPS = 8;
 constexpr int HP_TMEM_COLS = 256;               // two 128-column accumulators
 
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
@@ -65,7 +67,7 @@ rowconv_halo_persist_kernel(const m2d_rowconv_args a, const HaloPlan plan, const
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(t_full + 8 * s, 1);
-            mbar_init(t_empty + 8 * s, 4);              // one arrival per epilogue warp
+            mbar_init(t_empty + 8 * s, HP_EPI_WARPS);   // one arrival per epilogue warp
         }
         fence_barrier_init();
     }
@@ -208,7 +210,7 @@ rowconv_halo_persist_kernel(const m2d_rowconv_args a, const HaloPlan plan, const
         }
     } else if (warp >= HP_EPI0) {
         // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
-        const int q = warp & 3;
+        const int q = warp & 3, half = (warp - HP_EPI0) >> 2;
         const int row = 32 * q + lane;
         const bool vecN = (a.N & 3) == 0;
         const bool vy = vecN && (a.y_ld & 3) == 0 && (a.y_bs & 3) == 0 && aligned16d(a.y) &&
@@ -232,7 +234,7 @@ rowconv_halo_persist_kernel(const m2d_rowconv_args a, const HaloPlan plan, const
             const long long mo = a.mask_mode ? b * a.m_bs + (long long)i * a.m_ld + n0 : 0;
             const long long ao = a.add ? b * a.a_bs + (long long)i * a.a_ld + n0 : 0;
             const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * 128);
-            for (int ch = 0; ch < bn / 16; ++ch) {
+            for (int ch = half; ch < bn / 16; ch += HP_EPI_WARPS / 4) {
                 uint32_t r[16];
                 tmem_ld16_nowait(taddr + (uint32_t)(16 * ch), r);
                 // operands of the fused epilogue are fetched while the tensor-memory load is in flight

@@ -454,6 +454,10 @@ def mark(name):
         tr.mark(name)
 
 
+def set_gru_forward_batch_group(bg):
+    call("m2d_set_gru_forward_batch_group", int(bg))
+
+
 def check_device(dev=0):
     call("m2d_check_device", dev)
     return _lib.load().m2d_version()

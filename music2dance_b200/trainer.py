@@ -116,6 +116,7 @@ class Phase3Trainer:
         # running statistics advance sequentially) run on a side stream and overlap the critic work.
         self.overlap = os.environ.get("M2D_OVERLAP", "1") != "0"
         self.s_gen = torch.cuda.Stream(device=dev)
+        self.gru_bg = int(os.environ.get("M2D_GRU_BG", "8"))
         self.split_pack = True          # critic re-layout of the late layers on a side stream (CriticNet.pack)
         # one backward sweep per critic iteration (wgan.critic_backward_fused); M2D_FUSED_BWD=0: two chains
         self.fused_backward = os.environ.get("M2D_FUSED_BWD", "1") != "0"
@@ -207,15 +208,26 @@ class Phase3Trainer:
         self.apD.step(lr, gs)
         ops.mark("adam_pack")
 
+    def _gru_side(self, on):
+        """The generator forwards run on a side stream next to the critic iterations: their GRU recurrences are off
+        the critical path, so they serve up to 8 sequences per thread-block cluster (8 SMs busy instead of 8 per
+        sequence) and leave the SMs to the critic's kernels.  M2D_GRU_BG overrides (0 = the latency-optimal plan)."""
+        if self.overlap:
+            ops.set_gru_forward_batch_group(self.gru_bg if on else 0)
+
     def _gen_forward(self, i):
         """Generator forward of critic iteration i (train-mode BatchNorm, no graph kept)."""
+        self._gru_side(True)
         self.G.forward(self.in_audio[i], self.in_noise[i], self.B, self.T, train=True,
                        out=Mat.of(self.fake_c[i], 1, self.B * self.T, self.O))
+        self._gru_side(False)
 
     def _gen_forward_update(self):
         """Generator forward of the generator update (its activations feed G.backward)."""
+        self._gru_side(True)
         self.G.forward(self.in_audio[self.nc - 1], self.in_noise_g, self.B, self.T, train=True,
                        out=Mat.of(self.fake_g, 1, self.B * self.T, self.O))
+        self._gru_side(False)
 
     def critic_iteration(self, i, update=True, gen_inline=True):
         """train.py:187-216 on staged batch i."""

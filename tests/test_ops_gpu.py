@@ -513,11 +513,11 @@ def test_adam_pack_matches_unpack_adam_pack(which, variant):
 
 
 PERSIST_CASES = [
-    # Cin, Cout, k, s, p, L, B : at least one wave (148) of 128-row tiles without split-K
-    (32, 64, 25, 4, 11, 19200, 7),     # audio_d.l2 forward at the reference batch: 266 tiles, K = 800
-    (64, 128, 25, 4, 11, 4800, 16),    # audio_d.l3: 160 tiles
-    (128, 100, 7, 1, 3, 1000, 24),     # N = 100 (ragged column tile), 192 tiles
-    (32, 300, 3, 1, 1, 640, 16),       # three N tiles (128 + 128 + 44): weight blocks switch between tiles
+    # Cin, Cout, k, s, p, L, B : at least three waves (444) of 128-row tiles without split-K
+    (32, 64, 25, 4, 11, 19200, 12),    # audio_d.l2 forward: 456 tiles, K = 800
+    (64, 128, 25, 4, 11, 4800, 48),    # audio_d.l3: 480 tiles
+    (128, 100, 7, 1, 3, 1000, 56),     # N = 100 (ragged column tile), 448 tiles
+    (32, 300, 3, 1, 1, 640, 32),       # three N tiles (128 + 128 + 44): weight blocks switch between tiles; 480 tiles
 ]
 
 
@@ -547,9 +547,11 @@ def test_persistent_halo_kernel(lib, case):
     assert _lib.load().m2d_halo_persist_launch_count() == n0 + 1, "shape did not take the persistent kernel"
     close(ncl(Y, B, Lout, Cout), y_ref, what="persist fwd")
     close(ncl(Y2, B, Lout, Cout), y_ref, what="persist fwd y2")
-    # in-place masked tangent: t = (conv(v) without bias) * relu'(y), written over the mask buffer itself
+    # in-place masked tangent: t = (conv(v) without bias) * relu'(y), written over the mask buffer itself.  The mask of
+    # the expected value is the DEVICE's own forward output: a pre-activation within rounding noise of zero lands on
+    # either side of the ReLU kink in two fp32 evaluations (1-8 of ~2e6 elements here), which is not a kernel property
     v = torch.randn(B, Cin, L, generator=g)
-    t_ref = F.conv1d(v, w, None, stride=s, padding=p) * (y_ref > 0).float()
+    t_ref = F.conv1d(v, w, None, stride=s, padding=p) * (ncl(Y2, B, Lout, Cout) > 0).float()
     lay.fwd(Mat.of(cl(v), B, L, Cin), Y2, bias=False, ws=scratch, mask=Y2, mask_mode=1)
     close(ncl(Y2, B, Lout, Cout), t_ref, what="persist in-place tangent")
     # backward-data with ReLU mask and residual add (add_before_mask both ways)
