@@ -90,10 +90,12 @@ __device__ __forceinline__ long long tiled_blk(int n, int t, int c, int T, int c
     return (((long long)(n >> lgR) * T + t) * cch + c) * (64LL << lgR);
 }
 
-constexpr int AP_THREADS = 512;
 constexpr int AP_MAXT = 32;       // taps per tile
 
-__global__ void __launch_bounds__(AP_THREADS, 2)
+// AP_THREADS = 512 with tiles of up to ~100 KiB (2 CTAs / SM) or 256 with tiles of up to ~50 KiB (4 CTAs / SM: same
+// number of warps per SM, finer-grained work items)
+template <int AP_THREADS>
+__global__ void __launch_bounds__(AP_THREADS, 1024 / AP_THREADS)
 adam_pack_kernel(const m2d_adam_item* __restrict__ items, int* counters, float lr, float b1, float b2, float eps,
                  float gscale, const bool mixed) {
     extern __shared__ float tile[];
@@ -407,16 +409,21 @@ extern "C" int m2d_adam_pack(const m2d_adam_item* items, int n, int smem_floats,
     M2D_REQUIRE(items && counters && n > 0 && smem_floats >= 0, "adam_pack: bad args");
     const size_t smem = (size_t)smem_floats * sizeof(float);
     M2D_REQUIRE(smem <= 200 * 1024, "adam_pack: tile too large for shared memory");
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(adam_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool small = smem <= 52 * 1024;
+    static size_t configured[2] = {0, 0};
+    if (smem > configured[small]) {
+        cudaError_t e = small ? cudaFuncSetAttribute(adam_pack_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                              : cudaFuncSetAttribute(adam_pack_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("adam_pack: %s", cudaGetErrorString(e));
             return M2D_ERR_CUDA;
         }
-        configured = smem;
+        configured[small] = smem;
     }
-    adam_pack_kernel<<<n, AP_THREADS, smem, (cudaStream_t)stream>>>(items, counters, lr, beta1, beta2, eps, gscale,
-                                                            gemm_mode() == M2D_GEMM_TF32_BF16);
+    const bool mixed = gemm_mode() == M2D_GEMM_TF32_BF16;
+    if (small)
+        adam_pack_kernel<256><<<n, 256, smem, (cudaStream_t)stream>>>(items, counters, lr, beta1, beta2, eps, gscale, mixed);
+    else
+        adam_pack_kernel<512><<<n, 512, smem, (cudaStream_t)stream>>>(items, counters, lr, beta1, beta2, eps, gscale, mixed);
     return check_launch("adam_pack");
 }

@@ -2,6 +2,7 @@
 modules (archis/default.py, losses.py) and the fused trainer (trainer.py)."""
 from __future__ import annotations
 
+import os
 import re
 from collections import OrderedDict
 
@@ -112,7 +113,10 @@ class AdamPack:
     buffers laid out like `fp.flat`.  `only` / `exclude`: lists of ConvLayer objects selecting a subset of the weights
     (plain ranges belong to the table built with only=None)."""
 
-    TILE = 800            # floats of one output row's slice held in shared memory (x 32 rows)
+    # floats of one output row's slice held in shared memory (x 32 rows): 800 -> 100 KiB tiles, 512-thread blocks,
+    # 2 per SM; 400 -> 50 KiB tiles, 256-thread blocks, 4 per SM (M2D_AP_TILE)
+    TILE = int(os.environ.get("M2D_AP_TILE", "800"))
+    ROWS = int(os.environ.get("M2D_AP_ROWS", "32"))       # output rows per tile (multiple of 4, <= 32)
     FLAT_CHUNK = 4096
 
     def __init__(self, fp, net, m, v, only=None, exclude=None):
@@ -154,8 +158,8 @@ class AdamPack:
                 nci_full = 1
             else:
                 nci_full = min(Cin, max(32, (self.TILE // nt_full) // 32 * 32))
-            for co0 in range(0, Cout, 32):
-                nco = min(32, Cout - co0)
+            for co0 in range(0, Cout, self.ROWS):
+                nco = min(self.ROWS, Cout - co0)
                 for ci0 in range(0, Cin, nci_full):
                     nci = min(nci_full, Cin - ci0)
                     for t0 in range(0, k, nt_full):

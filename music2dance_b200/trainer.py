@@ -116,7 +116,9 @@ class Phase3Trainer:
         # running statistics advance sequentially) run on a side stream and overlap the critic work.
         self.overlap = os.environ.get("M2D_OVERLAP", "1") != "0"
         self.s_gen = torch.cuda.Stream(device=dev)
-        self.gru_bg = int(os.environ.get("M2D_GRU_BG", "8"))
+        # measured on B200 at batch 7: 0 -> 57.0, 4 -> 55.8, 8 -> 50.3 train steps/s: under contention a generator
+        # forward takes about as long as a critic iteration, so its latency matters as much as its SM footprint
+        self.gru_bg = int(os.environ.get("M2D_GRU_BG", "0"))
         self.split_pack = True          # critic re-layout of the late layers on a side stream (CriticNet.pack)
         # one backward sweep per critic iteration (wgan.critic_backward_fused); M2D_FUSED_BWD=0: two chains
         self.fused_backward = os.environ.get("M2D_FUSED_BWD", "1") != "0"
@@ -209,10 +211,10 @@ class Phase3Trainer:
         ops.mark("adam_pack")
 
     def _gru_side(self, on):
-        """The generator forwards run on a side stream next to the critic iterations: their GRU recurrences are off
-        the critical path, so they serve up to 8 sequences per thread-block cluster (8 SMs busy instead of 8 per
-        sequence) and leave the SMs to the critic's kernels.  M2D_GRU_BG overrides (0 = the latency-optimal plan)."""
-        if self.overlap:
+        """The generator forwards run on a side stream next to the critic iterations; M2D_GRU_BG = 1..8 lets their GRU
+        recurrences serve that many sequences per thread-block cluster (fewer SMs busy, longer steps).  Default 0 = the
+        latency-optimal plan (see __init__)."""
+        if self.overlap and self.gru_bg:
             ops.set_gru_forward_batch_group(self.gru_bg if on else 0)
 
     def _gen_forward(self, i):

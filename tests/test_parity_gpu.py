@@ -246,6 +246,8 @@ def _sync_trainer_from_oracle(tr, gen, critic, G, D, ad, ag):
             if name not in st.m:
                 continue
             off = (prm.data_ptr() - base) // 4
+            if off >= m.numel():
+                continue                                      # dead LinearBlock branch (Q1): never updated
             m[off:off + prm.numel()].copy_(st.m[name].reshape(-1))
             v[off:off + prm.numel()].copy_(st.v[name].reshape(-1))
         t = max(st.t.values()) if st.t else 0
