@@ -194,6 +194,13 @@ class _CriticFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dd):
+        if torch.is_grad_enabled():
+            # autograd.grad(..., create_graph=True): the stock losses.gradient_penalty (losses.py:40-44) asks for a
+            # differentiable backward.  The kernels evaluate the penalty's double backward as a tangent pass instead.
+            raise RuntimeError(
+                "music2dance_b200 critic: backward with create_graph=True (double backward through the critic) is not "
+                "routed through autograd — use music2dance_b200.losses.gradient_penalty (same signature as the "
+                "reference's losses.gradient_penalty), which returns the penalty with its weight gradients attached")
         eng = ctx.owner._engine()
         if eng.slot_gen.get(ctx.slot) != ctx.gen:
             raise RuntimeError("critic: saved activations were overwritten (more than 6 live critic graphs)")

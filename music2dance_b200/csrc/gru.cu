@@ -250,6 +250,16 @@ __device__ __forceinline__ void gru_st_async4(uint32_t raddr, float4 v, uint32_t
                  "r"(__float_as_uint(v.w)), "r"(rbar)
                  : "memory");
 }
+// The same message inside a ONE-block "cluster" (hidden sizes <= 32: the noise GRU): an ordinary shared-memory store
+// followed by the transaction-count update of the CTA's own mbarrier.  st.async is specified for the shared memory of a
+// peer CTA of a real cluster; compute-sanitizer's memcheck rejects it in a 1-block launch.
+__device__ __forceinline__ void gru_st_local4(uint32_t addr, float4 v, uint32_t bar) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(__float_as_uint(v.x)),
+                 "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w))
+                 : "memory");
+    asm volatile("fence.acq_rel.cta;" ::: "memory");
+    asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], 16;" ::"r"(bar) : "memory");
+}
 
 // Layout shared by the forward and backward recurrences.  A vector of length V (V = H forward,
 // 3H backward) lives in shared memory as V floats padded to 32*KC; thread (unit ul = tid/8,
@@ -372,8 +382,10 @@ gru_fwd2_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, co
         h4.w = __shfl_sync(0xffffffffu, h, (lane & 7) + 24);
         if (sender && t + 1 < T) {
             const uint32_t off = (uint32_t)((((cur ^ 1) * GRU2_BGMAX + lane) * VP + u0 + 4 * (tid >> 5)) * 4);
-            for (int rk = 0; rk < NC; ++rk)
-                gru_st_async4(gru_mapa(hs_addr + off, (uint32_t)rk), h4, gru_mapa(bar0 + 8 * (cur ^ 1), (uint32_t)rk));
+            if (NC == 1) gru_st_local4(hs_addr + off, h4, bar0 + 8 * (cur ^ 1));
+            else
+                for (int rk = 0; rk < NC; ++rk)
+                    gru_st_async4(gru_mapa(hs_addr + off, (uint32_t)rk), h4, gru_mapa(bar0 + 8 * (cur ^ 1), (uint32_t)rk));
         }
     }
     cluster.sync();      // no CTA leaves while a peer could still address its shared memory
@@ -474,6 +486,11 @@ gru_bwd2_kernel(const float* __restrict__ dh_out, int ldd, const float* __restri
         m2.z = __shfl_sync(0xffffffffu, dghn, src + 16); m2.w = __shfl_sync(0xffffffffu, dghn, src + 24);
         if (sender) {
             const uint32_t off = (uint32_t)((((cur * BG + lane) * 3) * VP + u0 + 4 * (tid >> 5)) * 4);
+            if (NC == 1) {
+                gru_st_local4(ds_addr + off, m0, bar0 + 8 * cur);
+                gru_st_local4(ds_addr + off + 4 * VP, m1, bar0 + 8 * cur);
+                gru_st_local4(ds_addr + off + 8 * VP, m2, bar0 + 8 * cur);
+            } else
             for (int rk = 0; rk < NC; ++rk) {
                 const uint32_t ra = gru_mapa(ds_addr + off, (uint32_t)rk), rb = gru_mapa(bar0 + 8 * cur, (uint32_t)rk);
                 gru_st_async4(ra, m0, rb);

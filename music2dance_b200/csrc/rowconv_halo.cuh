@@ -252,6 +252,10 @@ rowconv_halo_kernel(const m2d_rowconv_args a, const HaloPlan plan, const int tpb
             mbar_wait(bar_acc, 0);
             if (TRACE && tr && tid == 0) tr[4] = clock64() - t_start;
             tc_fence_after();
+            // The staging tile reuses the activation stages.  Their last writers (these same 256 threads, as converters)
+            // are ordered before this point through a_full -> tcgen05.mma -> tcgen05.commit -> bar_acc; a plain barrier
+            // among the 256 states the same order in a form compute-sanitizer's racecheck can follow.
+            epi_bar();
             const int q = warp & 3, part = warp >> 2;
             const int row = 32 * q + lane;
             for (int ch = part; ch < bn / 16; ch += HL_CW / 4) {

@@ -233,6 +233,20 @@ def test_fused_trainer_vs_oracle(variant, B, nc, graphs):
                 assert float(d.mean()) < TOL_DRIFT_LR * lr * steps + 1e-6 * float(P[k].abs().max()), (k, float(d.mean()))
 
 
+def test_stock_gradient_penalty_fails_with_clear_message():
+    """SURVEY §8(b) autograd contract: double backward through the drop-in critic is bypassed by the fused
+    gradient_penalty; asking autograd for it (the reference's own losses.py:40-44 recipe) must say so."""
+    cfg = O.make_cfg(ablated=True)
+    _, critic = build(cfg)
+    x = torch.rand(2, cfg["output_size"], cfg["stick_length"], device=DEV, requires_grad=True)
+    out = critic(x)
+    with pytest.raises(RuntimeError, match="music2dance_b200.losses.gradient_penalty"):
+        torch.autograd.grad(outputs=out, inputs=x, grad_outputs=torch.ones_like(out), create_graph=True,
+                            retain_graph=True, only_inputs=True)
+    g, = torch.autograd.grad(outputs=critic(x), inputs=x, grad_outputs=torch.ones_like(out))   # first order still works
+    assert g.shape == x.shape and bool(torch.isfinite(g).all())
+
+
 def _sync_trainer_from_oracle(tr, gen, critic, G, D, ad, ag):
     """Copy the oracle's state (parameters, BatchNorm buffers, Adam moments and step counts) into the trainer: after
     this both sides start the next iteration from IDENTICAL state, so every iteration is a single-iteration
