@@ -15,6 +15,18 @@ from . import ops
 from .ops import Mat
 
 ACT_ID, ACT_RELU, ACT_LEAKY, ACT_TANH = 0, 1, 2, 3
+
+# CUDA stream priorities of the fused step (lower = served first when SMs free up; kernels capture their stream's
+# priority into the graph).  The dependent chain of a critic iteration — pose branch / fusion on the capture stream,
+# audio branch on its side stream — outranks the generator forwards (needed one iteration later), which outrank the
+# weight-gradient GEMMs and re-layouts (leaves of the dependency graph: big grids that would otherwise take every SM
+# while a 20-microsecond link of the chain waits).  M2D_PRIO=0: every stream at the default priority.
+_PRIO_ON = os.environ.get("M2D_PRIO", "1") != "0"
+PRIO_CHAIN, PRIO_LATE, PRIO_GEN, PRIO_LEAF = (-3, -2, -1, 0) if _PRIO_ON else (0, 0, 0, 0)
+
+
+def make_stream(device, priority):
+    return torch.cuda.Stream(device=device, priority=priority)
 ACT_CODE = {"id": ACT_ID, "relu": ACT_RELU, "tanh": ACT_TANH, "leaky": ACT_LEAKY}
 
 
@@ -591,7 +603,7 @@ class GeneratorNet:
         self.nbt = [v for k, v in P.items() if k.endswith("num_batches_tracked")]
         self.nbt_flat = P.get("__nbt_flat__")
         self.par = os.environ.get("M2D_OVERLAP", "1") != "0"
-        self.s_noise = torch.cuda.Stream(device=self.dev) if self.par else None
+        self.s_noise = make_stream(self.dev, PRIO_GEN) if self.par else None
 
     def convs(self):
         c = self.enc.convs() + self.rnn.convs() + self.nrnn.convs() + [self.fc1, self.last]
@@ -743,10 +755,10 @@ class CriticNet:
         # the audio branch is independent of the pose branch between the inputs and the fusion MLP:
         # it runs on a side stream (fork / join below; CUDA-graph capture turns that into parallel branches)
         self.par = os.environ.get("M2D_OVERLAP", "1") != "0"
-        mk = lambda: torch.cuda.Stream(device=self.dev)
         # s_aud: audio branch next to the pose branch; s_w / s_wa: the Wasserstein backward (pose / audio)
-        # next to the gradient-penalty passes
-        self.s_aud, self.s_w, self.s_wa = (mk(), mk(), mk()) if self.par else (None, None, None)
+        # next to the gradient-penalty passes — in the fused backward: the weight-gradient GEMMs
+        self.s_aud, self.s_w, self.s_wa = ((make_stream(self.dev, PRIO_CHAIN), make_stream(self.dev, PRIO_LEAF),
+                                            make_stream(self.dev, PRIO_LEAF)) if self.par else (None, None, None))
 
     def _side(self):
         cur = torch.cuda.current_stream(self.dev)
@@ -794,7 +806,7 @@ class CriticNet:
             early = [c for c in self.convs() if c not in late]
             mk = lambda cs: ops.pack_table([e for c in cs for e in c.pack_entries()], self.dev)
             self._pack_tabs = (mk(early), mk(late))
-            self.s_pack = torch.cuda.Stream(device=self.dev)
+            self.s_pack = make_stream(self.dev, PRIO_LATE)
         return self._pack_tabs
 
     def pack_early(self):
@@ -814,7 +826,7 @@ class CriticNet:
     def comm_stream(self):
         """Stream of the data-parallel early-bucket all-reduce (next to the last weight-gradient GEMMs)."""
         if getattr(self, "s_comm", None) is None:
-            self.s_comm = torch.cuda.Stream(device=self.dev)
+            self.s_comm = make_stream(self.dev, PRIO_LATE)
         return self.s_comm
 
     def late_fork(self, fn):

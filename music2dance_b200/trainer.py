@@ -24,7 +24,7 @@ import torch
 from . import dp, ops
 from .engine import AdamPack
 from .ops import Mat
-from .nets import ACT_ID
+from .nets import ACT_ID, PRIO_CHAIN, PRIO_GEN, make_stream
 from .wgan import (critic_backward_fused, critic_forward, critic_forward_fused, gradient_penalty_pass, rows,
                    wasserstein_backward)
 
@@ -115,7 +115,8 @@ class Phase3Trainer:
         # (one per iteration + the one of the generator update, in the reference's order: BatchNorm
         # running statistics advance sequentially) run on a side stream and overlap the critic work.
         self.overlap = os.environ.get("M2D_OVERLAP", "1") != "0"
-        self.s_gen = torch.cuda.Stream(device=dev)
+        self.s_gen = make_stream(dev, PRIO_GEN)
+        self.s_main = make_stream(dev, PRIO_CHAIN)          # capture stream of the step graph(s)
         # measured on B200 at batch 7: 0 -> 57.0, 4 -> 55.8, 8 -> 50.3 train steps/s: under contention a generator
         # forward takes about as long as a critic iteration, so its latency matters as much as its SM footprint
         self.gru_bg = int(os.environ.get("M2D_GRU_BG", "0"))
@@ -333,7 +334,7 @@ class Phase3Trainer:
         graphs = []
         if not self.per_iter:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=self.s_main):
                 self._run_eager()
             graphs.append(("all", g))
         else:
@@ -342,7 +343,7 @@ class Phase3Trainer:
             # (or the generator update's) on the side stream next to critic iteration i.
             def cap(fn):
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, stream=self.s_main):
                     fn()
                 return g
 
