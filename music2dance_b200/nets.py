@@ -20,8 +20,11 @@ ACT_ID, ACT_RELU, ACT_LEAKY, ACT_TANH = 0, 1, 2, 3
 # priority into the graph).  The dependent chain of a critic iteration — pose branch / fusion on the capture stream,
 # audio branch on its side stream — outranks the generator forwards (needed one iteration later), which outrank the
 # weight-gradient GEMMs and re-layouts (leaves of the dependency graph: big grids that would otherwise take every SM
-# while a 20-microsecond link of the chain waits).  M2D_PRIO=0: every stream at the default priority.
-_PRIO_ON = os.environ.get("M2D_PRIO", "1") != "0"
+# while a 20-microsecond link of the chain waits).  Measured on B200 at batch 7 (profiles/r02_*): the chain does finish
+# 30 % earlier (tangent pass done at 1.12 ms instead of 1.60 ms of an iteration), but the weight gradients then pile up
+# behind it and the iteration ends at the same time — the step is bound by total SM time, not by the chain: 56.3 vs
+# 57.0 train steps/s.  Hence opt-in (M2D_PRIO=1); default: every stream at the default priority.
+_PRIO_ON = os.environ.get("M2D_PRIO", "0") != "0"
 PRIO_CHAIN, PRIO_LATE, PRIO_GEN, PRIO_LEAF = (-3, -2, -1, 0) if _PRIO_ON else (0, 0, 0, 0)
 
 
@@ -304,13 +307,16 @@ class ConvBNAct:
         self.x, self.c, self.a = x, c, a
         return a
 
-    def bwd(self, e_a, wk, win=None, e_x=None, **dg):
+    def bwd(self, e_a, wk, win=None, e_x=None, leaf=lambda fn: fn(), **dg):
         """e_a: gradient w.r.t. the post-activation output.  Writes parameter grads;
-        if e_x is given, the gradient w.r.t. the input (fused epilogue options in dg)."""
+        if e_x is given, the gradient w.r.t. the input (fused epilogue options in dg).
+        leaf: runs a launch sequence that nothing in the backward chain depends on (weight / bias gradients) —
+        GeneratorNet passes a side-stream runner, the default runs it inline."""
         cv = self.conv
         dc = wk.mat(self.tag + ":dc", self.c.nb, cv.Lout, cv.Cout)
         self.bn.bwd(e_a, self.a, self.c, dc, self.act, wk)
-        cv.wgrad(dc, self.x, wk.scratch, win=win, acc=wk.acc_slot(cv.Cout))
+        acc = wk.acc_slot(cv.Cout)
+        leaf(lambda: cv.wgrad(dc, self.x, wk.scratch, win=win, acc=acc))      # nothing downstream reads it
         if e_x is not None:
             cv.dgrad(dc, e_x, ws=wk.scratch, **dg)
 
@@ -376,21 +382,22 @@ class DefaultEncoder(_Encoder):
         self.head.fwd(x, out, act=self.act, ws=wk.scratch)
         self.hx, self.out = x, out
 
-    def bwd(self, e_out, audio, nb, win, wk):
+    def bwd(self, e_out, audio, nb, win, wk, leaf=lambda fn: fn()):
         """e_out: gradient w.r.t. the encoder output [nb,1,out] (modified in place)."""
         if self.act != ACT_ID:
             ops.act_bwd(e_out, self.out, nb * self.head.Cout, self.act)
-        self.head.wgrad(e_out, self.hx, wk.scratch, acc=wk.acc_slot(self.head.Cout))
+        acc = wk.acc_slot(self.head.Cout)
+        leaf(lambda: self.head.wgrad(e_out, self.hx, wk.scratch, acc=acc))
         e = wk.mat("enc:e_head", nb, self.head.Lin, self.head.Cin)
         self.head.dgrad(e_out, e, ws=wk.scratch)
         for i in range(len(self.blocks) - 1, -1, -1):
             blk = self.blocks[i]
             if i > 0:
                 e_x = wk.mat(f"enc:e{i}", nb, blk.conv.Lin, blk.conv.Cin)
-                blk.bwd(e, wk, e_x=e_x)
+                blk.bwd(e, wk, e_x=e_x, leaf=leaf)
                 e = e_x
             else:
-                blk.bwd(e, wk, win=win)
+                blk.bwd(e, wk, win=win, leaf=leaf)
 
 
 class WaveGANEncoder(_Encoder):
@@ -473,7 +480,7 @@ class UNetEncoder(_Encoder):
         self.sv = (x, x1, x2, x3, x4, y3, y2, y1, d1, d2, d3)
         self.out = out
 
-    def bwd(self, e_out, audio, nb, win, wk):
+    def bwd(self, e_out, audio, nb, win, wk, leaf=None):
         C, Ls, cb = self.C, self.Ls, self.cb
         x, x1, x2, x3, x4, y3, y2, y1, d1, d2, d3 = self.sv
         if self.act != ACT_ID:
@@ -553,8 +560,10 @@ class GRUStack:
             self.saves.append(sv)
             x = h
 
-    def bwd(self, e_out, B, T, wk, e_x=None):
-        """e_out: Mat gradient w.r.t. the top layer output; e_x: Mat for d/d(input) or None."""
+    def bwd(self, e_out, B, T, wk, e_x=None, leaf=lambda fn: fn()):
+        """e_out: Mat gradient w.r.t. the top layer output; e_x: Mat for d/d(input) or None.
+        The chain is BPTT kernel -> backward-data of the input projection -> next layer's BPTT kernel; the four
+        parameter gradients of a layer are leaves (`leaf`, see ConvBNAct.bwd)."""
         H = self.H
         e = e_out
         for l in range(self.n - 1, -1, -1):
@@ -566,15 +575,19 @@ class GRUStack:
             # dW_hh = sum dgh (x) h_{t-1}: rows shifted by one step inside each sequence
             hB = Mat(h.t, B, T, H, h.ld, T * h.ld)
             hB.ptr = h.ptr
-            ops.wgrad(dgh.as_rows(B, T), hB, gw_hh, Cout=3 * H, T=1, Cc=H, sr=1, roff0=-1, droff=1,
-                      ws=wk.scratch)
-            ops.colsum(dgh, gb_hh, wk.acc_slot(3 * H))
-            self.ih[l].wgrad(dgi, self.xs[l], wk.scratch, acc=wk.acc_slot(3 * H))
+            acc1, acc2 = wk.acc_slot(3 * H), wk.acc_slot(3 * H)
+
+            def grads(l=l, dgi=dgi, dgh=dgh, hB=hB, gw_hh=gw_hh, gb_hh=gb_hh, acc1=acc1, acc2=acc2):
+                ops.wgrad(dgh.as_rows(B, T), hB, gw_hh, Cout=3 * H, T=1, Cc=H, sr=1, roff0=-1, droff=1,
+                          ws=wk.scratch)
+                ops.colsum(dgh, gb_hh, acc1)
+                self.ih[l].wgrad(dgi, self.xs[l], wk.scratch, acc=acc2)
             if l > 0:
                 e = wk.mat(f"{self.name}:e{l}", 1, B * T, H)
                 self.ih[l].dgrad(dgi, e, ws=wk.scratch)
             elif e_x is not None:
                 self.ih[l].dgrad(dgi, e_x, ws=wk.scratch)
+            leaf(grads)
 
 
 class GeneratorNet:
@@ -604,6 +617,7 @@ class GeneratorNet:
         self.nbt_flat = P.get("__nbt_flat__")
         self.par = os.environ.get("M2D_OVERLAP", "1") != "0"
         self.s_noise = make_stream(self.dev, PRIO_GEN) if self.par else None
+        self.s_leaf = make_stream(self.dev, PRIO_LEAF) if self.par else None      # parameter gradients of the backward
 
     def convs(self):
         c = self.enc.convs() + self.rnn.convs() + self.nrnn.convs() + [self.fc1, self.last]
@@ -687,6 +701,20 @@ class GeneratorNet:
         wk, B, T = self.wk, self.B, self.T
         nb = B * T
         wk.acc_reset()
+        cur = torch.cuda.current_stream(self.dev)
+        side = self.s_leaf if self.par else None
+
+        def leaf(fn):
+            """Parameter-gradient launches run on a side stream behind the point of the chain that produced their
+            operands; the chain (backward-data, BatchNorm backward, BPTT) continues at once."""
+            if side is None:
+                fn()
+                return
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                fn()
+        if side is not None:
+            side.wait_stream(cur)            # the arena reset above precedes every accumulation on the side stream
         self.last.wgrad(dfake, self.d_last, wk.scratch, acc=wk.acc_slot(self.O))
         e = wk.mat("g:e_d", 1, nb, self.S)
         self.last.dgrad(dfake, e, ws=wk.scratch)
@@ -706,12 +734,14 @@ class GeneratorNet:
         e_z = wk.mat("g:e_z", 1, nb, self.Lat)
         self.fc1.dgrad(dc, e_z, ws=wk.scratch)
         ops.mark("gb:dec")
-        self.nrnn.bwd(e_z.cols_slice(self.H, self.Lat), B, T, wk)
+        self.nrnn.bwd(e_z.cols_slice(self.H, self.Lat), B, T, wk, leaf=leaf)
         e_enc = wk.mat("g:e_enc", 1, nb, self.I)
-        self.rnn.bwd(e_z.cols_slice(0, self.H), B, T, wk, e_x=e_enc)
+        self.rnn.bwd(e_z.cols_slice(0, self.H), B, T, wk, e_x=e_enc, leaf=leaf)
         ops.mark("gb:rnn")
-        self.enc.bwd(e_enc.as_rows(nb, 1), self.src, nb, self.win, wk)
+        self.enc.bwd(e_enc.as_rows(nb, 1), self.src, nb, self.win, wk, leaf=leaf)
         ops.mark("gb:enc")
+        if side is not None:
+            cur.wait_stream(side)
 
 
 # ===========================================================================
