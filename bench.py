@@ -67,7 +67,9 @@ def parse():
     ap.add_argument("--no-eager-gpu", action="store_true", help="skip the torch_eager_gpu leg (reference modules on cuda:0)")
     ap.add_argument("--no-throughput-regime", action="store_true",
                     help="skip the throughput_regime sub-record (a second, short run at --regime-batch per GPU)")
-    ap.add_argument("--regime-batch", type=int, default=64)
+    ap.add_argument("--regime-batch", type=int, default=512,
+                    help="per-GPU batch of the throughput_regime sub-record (SURVEY 8d: the reference batch 7 is far too "
+                         "small to load a B200; 512 is its throughput configuration)")
     ap.add_argument("--collective", default=None, choices=["nvl", "nccl"],
                     help="N > 1: gradient all-reduce by the hand-written NVLink peer-memory kernel inside ONE step graph "
                          "(nvl) or by NCCL between per-iteration graphs (nccl); default: nvl when available")
@@ -568,7 +570,7 @@ def run_b200(args):
                            "last_step_logs": ln.get("detail", {}).get("logs")} if "value" in ln else ln)
     regime = None
     if rank == 0 and world == 1 and not args.sub and not args.no_throughput_regime and args.regime_batch != B:
-        ln = child_line(["--batch", str(args.regime_batch), "--enc", args.enc, "--gemm", args.gemm, "--steps", "5",
+        ln = child_line(["--batch", str(args.regime_batch), "--enc", args.enc, "--gemm", args.gemm, "--steps", "4",
                          "--warmup", "3", "--sub", "--no-cpu-baseline", "--no-device-dataset"], 400)
         if "value" in ln:
             regime = {"batch_per_gpu": args.regime_batch, "value": ln["value"], "unit": UNIT,

@@ -111,7 +111,8 @@ class AdamPack:
     that have packed copies become tiles (gradient read tap-major where the weight-gradient GEMM wrote it that way,
     re-layouts written from the same shared-memory tile); everything else is a plain range.  `m`, `v`: flat Adam moment
     buffers laid out like `fp.flat`.  `only` / `exclude`: lists of ConvLayer objects selecting a subset of the weights
-    (plain ranges belong to the table built with only=None)."""
+    (plain ranges belong to the table built with only=None unless `flat_range` = (lo, hi) float offsets into the
+    flat buffers selects the ones this table owns)."""
 
     # floats of one output row's slice held in shared memory (x 32 rows): 800 -> 100 KiB tiles, 512-thread blocks,
     # 2 per SM; 400 -> 50 KiB tiles, 256-thread blocks, 4 per SM (M2D_AP_TILE)
@@ -119,7 +120,7 @@ class AdamPack:
     ROWS = int(os.environ.get("M2D_AP_ROWS", "32"))       # output rows per tile (multiple of 4, <= 32)
     FLAT_CHUNK = 4096
 
-    def __init__(self, fp, net, m, v, only=None, exclude=None):
+    def __init__(self, fp, net, m, v, only=None, exclude=None, flat_range=None):
         import numpy as np
         dev = fp.device
         convs = {c.w.data_ptr(): c for c in net.convs() if c.gw is not None}
@@ -143,7 +144,7 @@ class AdamPack:
                 continue                                          # dead LinearBlock branch (Q1): no gradient, no update
             conv = convs.get(prm.data_ptr())
             if conv is None or prm.dim() < 2:
-                if sel is None:
+                if (sel is None and flat_range is None) or (flat_range is not None and flat_range[0] <= off < flat_range[1]):
                     flats.append((off, prm.numel()))
                 continue
             if (sel is not None and id(conv) not in sel) or id(conv) in exc:

@@ -97,11 +97,21 @@ class Phase3Trainer:
         with torch.cuda.device(dev):
             self.apG = AdamPack(self.ge.fp, self.G, self.mG, self.vG)
             if self.D.can_split_pack():
-                late = [self.D.a_layers[4], self.D.a_l6]
-                self.apD = AdamPack(self.de.fp, self.D, self.mD, self.vD, exclude=late)
-                self.apD_late = AdamPack(self.de.fp, self.D, self.mD, self.vD, only=late)
-                # audio_d.l5 / l6 are the last two tap-major weights of the arena: their gradients are one contiguous tail
-                self._late_off = (late[0].gwp.data_ptr() - self.de.fp.gpk.data_ptr()) // 4
+                # "late" parameters: everything the next forward reaches only after audio_d.l4 — audio_d.l5 / l6 (68 % of
+                # the critic) and the fusion MLP, weights and biases.  Their gradients are the tails of both gradient
+                # buffers (parameter order), so each side is one contiguous range for Adam and for the all-reduce.
+                fp = self.de.fp
+                late = [self.D.a_layers[4], self.D.a_l6, self.D.fc1, self.D.fc2]
+                base = fp.flat.data_ptr()
+                off = lambda t: (t.data_ptr() - base) // 4
+                self._late_plain = off(self.D.a_layers[4].b)
+                tail = {off(t) for c in late for t in (c.b,)} | {off(self.D.fc1.w), off(self.D.fc2.w)}
+                plain_offs = [off(p) for p in fp.params.values() if off(p) < fp.n_plain_padded]
+                assert {o for o in plain_offs if o >= self._late_plain} == tail and self._late_plain % 4 == 0
+                self.apD = AdamPack(fp, self.D, self.mD, self.vD, exclude=late, flat_range=(0, self._late_plain))
+                self.apD_late = AdamPack(fp, self.D, self.mD, self.vD, only=late,
+                                         flat_range=(self._late_plain, fp.n_plain_padded))
+                self._late_off = (late[0].gwp.data_ptr() - fp.gpk.data_ptr()) // 4
                 assert late[1].gwp.data_ptr() == late[0].gwp.data_ptr() + 4 * ((late[0].gwp.numel() + 3) // 4 * 4)
                 assert self._late_off % 4 == 0
             else:
@@ -155,24 +165,18 @@ class Phase3Trainer:
         return nvl
 
     def _nvl_reduce(self, eng, part):
-        """Peer-memory all-reduce of one network's gradient buffers.  part: "all"; for the critic with split tables
-        "plain" (parameter-layout gradients: biases, audio_d.l1, fusion MLP), "early" (tap-major arena without
-        audio_d.l5 / l6), "plain+early" (both in one launch), "late" (audio_d.l5 / l6)."""
+        """Peer-memory all-reduce of one network's gradient buffers.  part: "all", or for the critic with split tables
+        "early" / "late" (the ranges of the two Adam tables; each is ONE launch over both gradient buffers)."""
         plain, *rest = eng.fp.grad_buffers()
         base = 0 if eng is self.de else 4
-        gpk = rest[0] if rest else None
-        cut = self._late_off if (eng is self.de and self.apD_late is not None) else (gpk.numel() if rest else 0)
-        if part == "plain":
+        if not rest:
             self.nvl.all_reduce_sum_(plain, slot=base, blocks=4)
-        elif part == "early":
-            self.nvl.all_reduce_sum_(gpk[:cut], slot=base + 1)
-        elif part == "late":
-            self.nvl.all_reduce_sum_(gpk[cut:], slot=base + 2)
-        elif part == "plain+early" or (part == "all" and rest):
-            hi = cut if part == "plain+early" else gpk.numel()
-            self.nvl.all_reduce_sum2_(gpk[:hi], plain, slot=base + 3)
-        else:
-            self.nvl.all_reduce_sum_(plain, slot=base, blocks=4)
+        elif part == "all":
+            self.nvl.all_reduce_sum2_(rest[0], plain, slot=base)
+        elif part == "early":      # everything the early Adam table reads, in ONE launch
+            self.nvl.all_reduce_sum2_(rest[0][:self._late_off], plain[:self._late_plain], slot=base + 1)
+        else:                       # "late": audio_d.l5 / l6 + fusion MLP
+            self.nvl.all_reduce_sum2_(rest[0][self._late_off:], plain[self._late_plain:], slot=base + 2)
 
     def _all_reduce(self, eng):
         """NCCL path: sum of the gradient buffers an optimiser step reads (engine.FlatParams.grad_buffers) over the
@@ -203,11 +207,8 @@ class Phase3Trainer:
                 self.D.late_fork(late)
             else:
                 late()
-        if nvl:
-            if self.apD_late is None:
-                self._nvl_reduce(eng, "all")
-            else:
-                self._nvl_reduce(eng, "plain" if early_reduced else "plain+early")
+        if nvl and not early_reduced:
+            self._nvl_reduce(eng, "all" if self.apD_late is None else "early")
         self.apD.step(lr, gs)
         ops.mark("adam_pack")
 
