@@ -13,6 +13,9 @@ done
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 2400 -c 3600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-graphs --no-cpu-baseline --no-roofline --no-eager-gpu --no-throughput-regime --no-device-dataset > gpurun_out/ncu_bench.log 2>&1
 tail -n 2 gpurun_out/ncu_bench.log | cut -c1-300
 for k in wgrad_tc_kernel gru_fwd2_kernel gru_bwd2_kernel conv_c1_fwd_kernel conv_c1_wgrad_kernel conv_c1_dgrad4_kernel adam_pack_kernel rowconv_halo_persist_kernel rowconv_halo_kernel skinny_gemm_kernel colsum_batch_kernel; do
-  M2D_OVERLAP=0 timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k -s 30 -c 3 -f -o gpurun_out/full_$k python bench.py --steps 1 --warmup 1 --no-graphs --no-cpu-baseline --no-roofline --no-eager-gpu --no-throughput-regime --no-device-dataset > gpurun_out/ncu_full_$k.log 2>&1
-  ls -la gpurun_out/full_$k.ncu-rep 2>/dev/null | awk '{print $5, $9}'
+  # the reports stay on the box (64 MiB merge limit); their raw pages come back as CSV
+  M2D_OVERLAP=0 timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k -s 20 -c 3 -f -o /tmp/full_$k python bench.py --steps 1 --warmup 1 --no-graphs --no-cpu-baseline --no-roofline --no-eager-gpu --no-throughput-regime --no-device-dataset > gpurun_out/ncu_full_$k.log 2>&1
+  ncu -i /tmp/full_$k.ncu-rep --page raw --csv > gpurun_out/full_$k.csv 2>/dev/null
+  ls -la /tmp/full_$k.ncu-rep gpurun_out/full_$k.csv 2>/dev/null | awk '{print $5, $9}'
 done
+rm -f gpurun_out/ncu_full_*.log
