@@ -1,21 +1,24 @@
 #!/bin/bash
-# State check of the whole tree on one B200: smoke, all GPU tests, bench (both arms), batch-64 bench, launch list.
+# State check of the whole tree on one B200, the way the driver runs it: smoke, all GPU tests, both bench arms.
 set -u
 mkdir -p gpurun_out
-python -c "import __graft_entry__ as g; g.build(); g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
-timeout 1500 python -m pytest tests -m gpu -q 2>&1 | grep -E "^E  .*Error|^FAILED|passed|failed" > gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
-timeout 600 python bench.py --batch 64 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_b64.json 2>> gpurun_out/bench.err
-timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 3000 -c 4200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-graphs --no-cpu-baseline --no-roofline > gpurun_out/ncu_bench.log 2>&1
-tail -n 3 gpurun_out/smoke.log; tail -n 25 gpurun_out/pytest_gpu.log; tail -n 3 gpurun_out/bench.err; cat gpurun_out/bench_ref.json
-for f in bench bench_b64; do python - "$f" <<'PY'
-import json,sys
-try:
-    d=json.loads(open(f"gpurun_out/{sys.argv[1]}.json").read().strip().splitlines()[-1])
-    print(sys.argv[1], "value", round(d["value"],3), "ms/step", round(d["ms_per_step"],2), "e2e", round(d["e2e"]["value"],3), "launches/step", d["gpu_launches_per_step"], "roof", d.get("roofline",{}).get("kernel"), round(d.get("roofline",{}).get("frac",0),4), "cpu", d.get("cpu_baseline",{}).get("value"))
-    for k,v in sorted(d.get("kernel_families",{}).items(), key=lambda kv:-kv[1]["ms"]):
-        print("   %-14s n=%5d ms=%8.3f tflops=%7.2f gbs=%8.1f share=%.3f"%(k,v["launches"],v["ms"],v["tflops"],v["gbs"],v["share_of_eager_step"]))
-except Exception as e: print(sys.argv[1], "unreadable", e)
+python -c "import __graft_entry__ as g; g.build(); g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log; tail -n 2 gpurun_out/smoke.log | cut -c1-300
+timeout 1800 python -m pytest tests -m gpu -q 2>&1 | grep -E "^E  .*Error|^FAILED|passed|failed" | tail -n 12
+/usr/bin/time -f "reference arm wall %e s" timeout 600 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -n 1 gpurun_out/bench_ref.err
+/usr/bin/time -f "b200 arm wall %e s" timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -n 2 gpurun_out/bench.err | cut -c1-300
+python - <<'PY'
+import json
+r=json.loads(open("gpurun_out/bench_ref.json").read().strip().splitlines()[-1])
+print("reference:", {k:r.get(k) for k in ("value","steps","warmup","ms_per_step","wall_s")}, r["cpu_baseline"]["kind"], r["cpu_baseline"]["cores"])
+d=json.loads(open("gpurun_out/bench.json").read().strip().splitlines()[-1])
+print("b200: value", round(d["value"],3), "ms/step", round(d["ms_per_step"],2), "e2e", round(d["e2e"]["value"],3), "launches/step", d["gpu_launches_per_step"], "clocks", d["clocks"])
+print("roofline", {k:(round(v,4) if isinstance(v,float) else v) for k,v in d["roofline"].items() if k not in ("measured_in","peak_source","traffic_source","tf32_peak_measured")})
+print("tf32 peak", d["roofline"].get("tf32_peak_measured"))
+print("cpu_baseline", d.get("cpu_baseline"))
+print("torch_eager_gpu", json.dumps(d.get("torch_eager_gpu"))[:700])
+t=d.get("throughput_regime") or {}
+print("regime", {k:t.get(k) for k in ("batch_per_gpu","value","ms_per_step","sequences_per_s")}, {k:(round(v,4) if isinstance(v,float) else v) for k,v in (t.get("roofline") or {}).items() if k in ("kernel","achieved","peak","frac","traffic")})
+print("e2e_device_dataset", {k:d["e2e_device_dataset"].get(k) for k in ("value","ms_per_step","h2d_bytes_per_step")})
+for k,v in sorted(d.get("kernel_families",{}).items(), key=lambda kv:-kv[1]["ms"]):
+    print("   %-14s n=%5d ms=%8.3f tflops=%7.2f gbs=%8.1f share=%.3f"%(k,v["launches"],v["ms"],v["tflops"],v["gbs"],v["share_of_eager_step"]))
 PY
-done
