@@ -208,6 +208,12 @@ int m2d_bn_apply(const float* x, int ldx, float* y, int ldy, long long M, int C,
                  const double* acc, const float* gamma, const float* beta,
                  float* running_mean, float* running_var, float momentum, float eps,
                  float* mr, int act, void* stream);
+/* stats + apply in ONE launch (grid-wide rendezvous inside the kernel): acc = 2C + 1 ZEROED doubles (sums, sums of
+ * squares, rendezvous counter).  What the generator forward uses; colstats / bn_apply remain for callers that
+ * accumulate statistics over several calls. */
+int m2d_bn_train(const float* x, int ldx, float* y, int ldy, long long M, int C, double* acc,
+                 const float* gamma, const float* beta, float* running_mean, float* running_var,
+                 float momentum, float eps, float* mr, int act, void* stream);
 int m2d_bn_eval(const float* x, int ldx, float* y, int ldy, long long M, int C,
                 const float* gamma, const float* beta, const float* running_mean,
                 const float* running_var, float eps, int act, void* stream);

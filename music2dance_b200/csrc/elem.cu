@@ -154,6 +154,58 @@ bn_apply_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int
     }
 }
 
+// Train-mode BatchNorm in ONE launch: column statistics (fp64 partials, as colstats_kernel), a grid-wide rendezvous, then
+// normalisation + activation (as bn_apply_kernel).  The rendezvous is a counter in global memory that the caller zeroes
+// with the accumulators (`sync` = the slot behind the 2C sums); the grid (<= 4 x 148 blocks of 256 threads, col_grid) is
+// far below what the chip keeps resident, so every block arrives — blocks of OTHER kernels may delay that, never prevent
+// it.  A rendezvous that does not complete (a bug) traps instead of hanging the GPU.
+__global__ void __launch_bounds__(256)
+bn_train_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, long long M, int C,
+                long long rows_per, double* acc, const float* __restrict__ gamma, const float* __restrict__ beta,
+                float* running_mean, float* running_var, float momentum, float eps, float* mr, int act,
+                unsigned int* sync) {
+    col_reduce<2>(M, C, rows_per, acc, [&](long long r, int c, float* v) {
+        float t = x[r * ldx + c];
+        v[0] = t;
+        v[1] = t * t;
+    });
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(sync, 1u);
+        const unsigned int total = gridDim.x * gridDim.y;
+        unsigned int spins = 0;
+        while (*(volatile unsigned int*)sync < total)
+            if (++spins > (1u << 28)) __trap();
+        __threadfence();
+    }
+    __syncthreads();
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ry = threadIdx.x >> 5;
+    if (c >= C) return;
+    const double mean = __ldcg(acc + c) / (double)M;
+    double var = __ldcg(acc + C + c) / (double)M - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float mu = (float)mean;
+    if (blockIdx.y == 0 && ry == 0) {
+        if (mr) { mr[c] = mu; mr[C + c] = rstd; }
+        if (running_mean) {
+            double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+        }
+    }
+    if (!y) return;      // statistics-only call (dead LinearBlock branch, Q1)
+    const float g = gamma[c], bt = beta[c];
+    const long long r0 = blockIdx.y * rows_per;
+    const long long r1 = r0 + rows_per < M ? r0 + rows_per : M;
+    for (long long r = r0 + ry; r < r1; r += 8) {
+        float v = (x[r * ldx + c] - mu) * rstd * g + bt;
+        y[r * ldy + c] = apply_act(v, act);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 bn_eval_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, long long M, int C,
                long long rows_per, const float* gamma, const float* beta, const float* rm,
@@ -649,6 +701,17 @@ extern "C" int m2d_bn_apply(const float* x, int ldx, float* y, int ldy, long lon
                                                             beta, running_mean, running_var, momentum,
                                                             eps, mr, act);
     return check_launch("bn_apply");
+}
+
+extern "C" int m2d_bn_train(const float* x, int ldx, float* y, int ldy, long long M, int C, double* acc,
+                            const float* gamma, const float* beta, float* running_mean, float* running_var,
+                            float momentum, float eps, float* mr, int act, void* stream) {
+    M2D_REQUIRE(x && acc && gamma && beta && M > 0 && C > 0, "bn_train: bad args");
+    ColGrid g = col_grid(M, C);
+    bn_train_kernel<<<g.grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, M, C, g.rows_per, acc, gamma, beta,
+                                                            running_mean, running_var, momentum, eps, mr, act,
+                                                            reinterpret_cast<unsigned int*>(acc + 2 * C));
+    return check_launch("bn_train");
 }
 
 extern "C" int m2d_bn_eval(const float* x, int ldx, float* y, int ldy, long long M, int C,

@@ -265,9 +265,8 @@ class BNLayer:
         """a = act(BN(c)).  `a` None: only update running statistics (dead branch)."""
         cf = c.flat_rows()
         if train:
-            acc = wk.acc_slot(2 * self.C)
-            ops.colstats(cf, acc)
-            ops.bn_apply(cf, None if a is None else a.flat_rows(), acc, self.gamma, self.beta, self.rm,
+            acc = wk.acc_slot(2 * self.C + 1)       # sums, sums of squares, rendezvous counter (zeroed with the arena)
+            ops.bn_train(cf, None if a is None else a.flat_rows(), acc, self.gamma, self.beta, self.rm,
                          self.rv, self.mr, act)
         elif a is not None:
             ops.bn_eval(cf, a.flat_rows(), self.gamma, self.beta, self.rm, self.rv, act)

@@ -208,6 +208,13 @@ def bn_apply(x, y, acc, gamma, beta, rm, rv, mr, act, momentum=0.1, eps=1e-5):
          _p(acc), _p(gamma), _p(beta), _p(rm), _p(rv), momentum, eps, _p(mr), act, _stream())
 
 
+def bn_train(x, y, acc, gamma, beta, rm, rv, mr, act, momentum=0.1, eps=1e-5):
+    """Train-mode BatchNorm, statistics + apply in one launch; acc: 2C + 1 zeroed doubles."""
+    LAUNCHES[0] += 1
+    call("m2d_bn_train", x.ptr, x.ld, None if y is None else y.ptr, 0 if y is None else y.ld, x.M, x.cols,
+         _p(acc), _p(gamma), _p(beta), _p(rm), _p(rv), momentum, eps, _p(mr), act, _stream())
+
+
 def bn_eval(x, y, gamma, beta, rm, rv, act, eps=1e-5):
     LAUNCHES[0] += 1
     call("m2d_bn_eval", x.ptr, x.ld, y.ptr, y.ld, x.M, x.cols, _p(gamma), _p(beta), _p(rm), _p(rv),

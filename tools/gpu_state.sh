@@ -4,8 +4,10 @@ set -u
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build(); g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log; tail -n 2 gpurun_out/smoke.log | cut -c1-300
 timeout 1800 python -m pytest tests -m gpu -q 2>&1 | grep -E "^E  .*Error|^FAILED|passed|failed" | tail -n 12
-/usr/bin/time -f "reference arm wall %e s" timeout 600 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -n 1 gpurun_out/bench_ref.err
-/usr/bin/time -f "b200 arm wall %e s" timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -n 2 gpurun_out/bench.err | cut -c1-300
+T0=$SECONDS
+timeout 600 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "reference arm rc=$? wall $((SECONDS-T0)) s"
+T0=$SECONDS
+timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "b200 arm rc=$? wall $((SECONDS-T0)) s"; tail -n 2 gpurun_out/bench.err | cut -c1-300
 python - <<'PY'
 import json
 r=json.loads(open("gpurun_out/bench_ref.json").read().strip().splitlines()[-1])

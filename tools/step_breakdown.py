@@ -54,9 +54,10 @@ def timed(name, fn, reps=10):
 
 
 def ops_adam():
-    from music2dance_b200 import ops
-    n = tr.de.fp.n_live_padded
-    ops.adam(tr.de.fp.flat, tr.de.fp.grad, tr.mD, tr.vD, n, tr.stepD, 2e-4)
+    """the critic's optimiser step: both m2d_adam_pack tables inline"""
+    if tr.apD_late is not None:
+        tr.apD_late.step(2e-4)
+    tr.apD.step(2e-4)
 
 
 with torch.cuda.device(dev):
@@ -69,7 +70,7 @@ with torch.cuda.device(dev):
     from music2dance_b200.wgan import critic_forward
     tf = timed("critic forward only (3B pose rows, B audio)", lambda: critic_forward(tD, X3, tr.in_audio[0], 3 * B, B, "c", groups=3))
     ta = timed("audio branch forward only", lambda: tD.audio_fwd(tr.in_audio[0], B, "c"))
-    tp = timed("weight re-layout (pack) critic", lambda: tD.pack())
+    tp = timed("weight re-layout alone (pack_batch, init / resume path)", lambda: tD.pack())
     from music2dance_b200.wgan import gradient_penalty_pass, wasserstein_backward
     fw = critic_forward(tD, X3, tr.in_audio[0], 3 * B, B, "c", groups=3)
     timed("Wasserstein backward chain alone", lambda: wasserstein_backward(tD, fw, B, 2 * B, (-1.0, 1.0), B, "c:w", beta=0.0))
@@ -77,5 +78,5 @@ with torch.cuda.device(dev):
           lambda: gradient_penalty_pass(tD, fw, B, "c:gp", 10.0, 1.0, tr.gp_buf, tr.k0, tr.k1))
     timed("gradient-penalty dgrad only", lambda: gradient_penalty_pass(tD, fw, B, "c:gp", 10.0, 1.0, tr.gp_buf, tr.k0, tr.k1,
                                                                        weight_grads=False))
-    timed("unpack grads + Adam (no re-layout)", lambda: (tD.unpack_grads(), ops_adam()))
+    timed("optimiser step (m2d_adam_pack: Adam + re-layouts)", ops_adam)
     print(f"batch {B}: 9 x gen = {9 * tg:.2f} ms, 8 x critic = {8 * tc:.2f} ms, update = {tu:.2f} ms")
