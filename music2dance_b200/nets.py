@@ -28,6 +28,10 @@ _PRIO_ON = os.environ.get("M2D_PRIO", "0") != "0"
 PRIO_CHAIN, PRIO_LATE, PRIO_GEN, PRIO_LEAF = (-3, -2, -1, 0) if _PRIO_ON else (0, 0, 0, 0)
 
 
+# train-mode BatchNorm as ONE launch (m2d_bn_train: statistics, grid-wide rendezvous, apply); M2D_BN_FUSED=0: two launches
+_BN_ONE_LAUNCH = os.environ.get("M2D_BN_FUSED", "1") != "0"
+
+
 def make_stream(device, priority):
     return torch.cuda.Stream(device=device, priority=priority)
 ACT_CODE = {"id": ACT_ID, "relu": ACT_RELU, "tanh": ACT_TANH, "leaky": ACT_LEAKY}
@@ -264,9 +268,14 @@ class BNLayer:
     def fwd(self, c, a, act, train, wk):
         """a = act(BN(c)).  `a` None: only update running statistics (dead branch)."""
         cf = c.flat_rows()
-        if train:
+        if train and _BN_ONE_LAUNCH:
             acc = wk.acc_slot(2 * self.C + 1)       # sums, sums of squares, rendezvous counter (zeroed with the arena)
             ops.bn_train(cf, None if a is None else a.flat_rows(), acc, self.gamma, self.beta, self.rm,
+                         self.rv, self.mr, act)
+        elif train:
+            acc = wk.acc_slot(2 * self.C)
+            ops.colstats(cf, acc)
+            ops.bn_apply(cf, None if a is None else a.flat_rows(), acc, self.gamma, self.beta, self.rm,
                          self.rv, self.mr, act)
         elif a is not None:
             ops.bn_eval(cf, a.flat_rows(), self.gamma, self.beta, self.rm, self.rv, act)
