@@ -353,6 +353,14 @@ def test_batchnorm(lib, case, act):
     # eval mode
     bn.fwd(X, Y, act, False, wk)
     close(Y.t.view(M, C), f(F.batch_norm(x, rm2, rv2, gamma, beta, False, 0.1, 1e-5)), what="bn eval")
+    # the one-launch form (m2d_bn_train: statistics, grid-wide rendezvous, apply) gives the same forward
+    rm3, rv3 = rm.to(DEV), rv.to(DEV)
+    Y3 = wk.mat("y3", 1, M, C)
+    acc = torch.zeros(2 * C + 1, dtype=torch.float64, device=DEV)
+    lib.bn_train(X, Y3, acc, P["bn.weight"], P["bn.bias"], rm3, rv3, torch.empty(2 * C, device=DEV), act)
+    close(Y3.t.view(M, C), y, what="bn_train fwd")
+    close(rm3, rm2, what="bn_train running_mean")
+    close(rv3, rv2, what="bn_train running_var")
 
 
 def test_pool_upsample(lib):
