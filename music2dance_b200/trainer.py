@@ -233,8 +233,10 @@ class Phase3Trainer:
                        out=Mat.of(self.fake_g, 1, self.B * self.T, self.O))
         self._gru_side(False)
 
-    def critic_iteration(self, i, update=True, gen_inline=True):
-        """train.py:187-216 on staged batch i."""
+    def critic_iteration(self, i, update=True, gen_inline=True, fake_ready=None):
+        """train.py:187-216 on staged batch i.  fake_ready: event of the (side-stream) generator forward of this
+        iteration; the fused path waits for it only after the audio branch — which needs neither the generated poses
+        nor the interpolates — has been forked."""
         B, T, O, D, G = self.B, self.T, self.O, self.D, self.G
         real, audio = self.in_real[i], self.in_audio[i]
         if gen_inline:
@@ -246,11 +248,17 @@ class Phase3Trainer:
         n3 = 3 * B
         X3 = wk.mat("c:X3", n3, T, O)
         per = T * O
-        ops.interp_stack3(real, fake_c, self.in_alpha[i], X3, B, per)      # [interpolates; real; fake]
+        def stack():
+            if fake_ready is not None:
+                torch.cuda.current_stream(self.dev).wait_event(fake_ready)
+            ops.interp_stack3(real, fake_c, self.in_alpha[i], X3, B, per)      # [interpolates; real; fake]
         gamma = float(self.cfg["gamma"])
-        if self.fused_backward and D.act == ACT_ID:
+        fused = self.fused_backward and D.act == ACT_ID
+        if not fused:
+            stack()
+        if fused:
             # one backward sweep for the Wasserstein terms and the penalty (wgan.critic_backward_fused)
-            fw = critic_forward_fused(D, X3, None if D.ablated else audio, B, "c")
+            fw = critic_forward_fused(D, X3, None if D.ablated else audio, B, "c", before_pose=stack)
             d = fw["d"]
             aud2 = None if D.ablated else Mat(self.in_audio2[i], 2 * B, self.A, 1)
             hook = None
@@ -421,8 +429,7 @@ class Phase3Trainer:
             ev_g = torch.cuda.Event()
             ev_g.record(self.s_gen)
         for i in range(self.nc):
-            main.wait_event(evs[i])
-            self.critic_iteration(i, gen_inline=False)
+            self.critic_iteration(i, gen_inline=False, fake_ready=evs[i])
         main.wait_event(ev_g)
         self.generator_update(gen_inline=False)
 

@@ -135,9 +135,11 @@ def gradient_penalty_pass(D, fw, B, tag, scale, beta, gp_out, k0, k1, weight_gra
     return out
 
 
-def critic_forward_fused(D, X3, audio, B, tag):
+def critic_forward_fused(D, X3, audio, B, tag, before_pose=None):
     """critic_forward for the fused backward below: pose branch on the 3B rows [interpolates; real; fake], audio
-    branch once on B samples with duplicated activation buffers (CriticNet.audio_fwd(dup=True))."""
+    branch once on B samples with duplicated activation buffers (CriticNet.audio_fwd(dup=True)).
+    before_pose: called after the audio branch has been forked and before the pose branch starts — the audio branch
+    depends on neither the generated poses nor X3, so the caller waits for the generator forward / builds X3 there."""
     wk = D.wk
     n3 = 3 * B
     sa = wk.mat(f"{tag}:sa", 1, n3, D.F)
@@ -147,6 +149,8 @@ def critic_forward_fused(D, X3, audio, B, tag):
             sva = D.audio_fwd(audio, B, tag, dup=True)
             for g in range(3):
                 ops.copy2d(sva["code"], rows(sa, g * B, (g + 1) * B).cols_slice(D.code, D.F))
+    if before_pose is not None:
+        before_pose()
     svp = D.pose_fwd(X3, n3, tag)
     ops.copy2d(svp["code"], sa.cols_slice(0, D.code))
     D.join()
