@@ -305,6 +305,9 @@ class KernelTimer:
         def f_adam(p, g, m, v, n, *a, **k):
             return "adam", 0.0, 28.0 * n
 
+        def f_adam_pack(table, n, smem_floats, counters, lr, *a, nbytes=0, **k):
+            return "adam", 0.0, float(nbytes)       # Adam fused with the weight re-layouts: 28 B + 12 B per packed layout per parameter
+
         def f_dg1(dy, w, dx, *, nb, Lout, Cout, k, stride, pad, Lin):
             return "conv_dgrad_c1", 2.0 * nb * Lout * Cout * k, 4.0 * nb * (Lout * Cout + Lin)
         self._wrap("rowconv", f_rowconv)
@@ -312,6 +315,7 @@ class KernelTimer:
         self._wrap("gru_forward", f_gru_f)
         self._wrap("gru_backward", f_gru_b)
         self._wrap("adam", f_adam)
+        self._wrap("adam_pack", f_adam_pack)
         self._wrap("conv_dgrad_c1", f_dg1)
 
     def remove(self):

@@ -136,6 +136,7 @@ class AdamPack:
         assert dt.itemsize == 8 * 5 + 4 * 12 + 3 * 32
         items, flats = [], []
         self.smem_floats = 0
+        self.nparams, self.bytes = 0, 0       # parameters covered / algorithmic bytes per step (28 B Adam + 12 B per packed layout)
         ptr = lambda t: 0 if t is None else t.data_ptr()
         n_live = fp.n_live_padded
         for name, prm in fp.params.items():
@@ -176,6 +177,9 @@ class AdamPack:
                             it["pk"][j] = (ptr(e[1]), ptr(e[2]), e[7], e[6], e[8] if len(e) > 8 else 0, 0)
                         items.append(it)
                         self.smem_floats = max(self.smem_floats, nco * ((nci * nt) | 1))
+                        self.nparams += nco * nci * nt
+                        self.bytes += nco * nci * nt * (28 + sum((4 if e[1] is not None else 0) + (8 if e[2] is not None else 0)
+                                                                 for e in packs))
         # plain ranges: adjacent parameters (16-byte aligned slots, zero padding between them) merge into runs
         flats.sort()
         runs = []
@@ -192,6 +196,8 @@ class AdamPack:
                 it["p"], it["m"], it["v"] = base + 4 * c0, m.data_ptr() + 4 * c0, v.data_ptr() + 4 * c0
                 it["g"], it["flat_n"] = fp.grad.data_ptr() + 4 * c0, n
                 items.append(it)
+                self.nparams += n
+                self.bytes += 28 * n
         self.n = len(items)
         arr = np.array(items, dtype=dt) if items else np.zeros(0, dtype=dt)
         self.table = torch.from_numpy(arr.view(np.uint8).reshape(-1).copy()).to(dev) if self.n else None
@@ -200,7 +206,8 @@ class AdamPack:
 
     def step(self, lr, gscale=1.0):
         if self.n:
-            ops.adam_pack(self.table, self.n, self.smem_floats, self.counters, float(lr), gscale=gscale)
+            ops.adam_pack(self.table, self.n, self.smem_floats, self.counters, float(lr), gscale=gscale,
+                          nbytes=self.bytes)
 
 
 class Engine:

@@ -394,8 +394,9 @@ def adam(p, g, m, v, n, step, lr, b1=0.9, b2=0.999, eps=1e-8, gscale=1.0):
     call("m2d_adam", _p(p), _p(g), _p(m), _p(v), n, _p(step), lr, b1, b2, eps, gscale, _stream())
 
 
-def adam_pack(table, n, smem_floats, counters, lr, b1=0.9, b2=0.999, eps=1e-8, gscale=1.0):
-    """Adam + every weight re-layout of the table's parameters in ONE launch (m2d_adam_pack, include/m2d.h)."""
+def adam_pack(table, n, smem_floats, counters, lr, b1=0.9, b2=0.999, eps=1e-8, gscale=1.0, nbytes=0):
+    """Adam + every weight re-layout of the table's parameters in ONE launch (m2d_adam_pack, include/m2d.h).
+    nbytes: algorithmic bytes of the launch (engine.AdamPack.bytes), only read by bench.py's instrumentation."""
     LAUNCHES[0] += 1
     call("m2d_adam_pack", _p(table), n, smem_floats, _p(counters), lr, b1, b2, eps, gscale, _stream())
 

@@ -1,18 +1,17 @@
 #!/bin/bash
-# single-pass TF32 mode (parity suite + bench) and the other two audio encoders (BASELINE configs[4]: wavegan; unet)
+# other encoders (BASELINE configs[4] = wavegan; unet) at batch 7 on one GPU, long-sequence generator inference
 set -u
 mkdir -p gpurun_out
-M2D_GEMM=tf32 timeout 600 python -m pytest tests/test_parity_gpu.py -q 2>&1 | grep -E "^E  .*(Error|assert)|^FAILED|passed|failed" > gpurun_out/parity_tf32.log
-tail -n 30 gpurun_out/parity_tf32.log
-timeout 300 python bench.py --gemm tf32 --steps 20 --warmup 3 --no-cpu-baseline --no-device-dataset > gpurun_out/bench_tf32.json 2> gpurun_out/bench_var.err
-timeout 300 python bench.py --enc wavegan --steps 20 --warmup 3 --no-cpu-baseline --no-device-dataset > gpurun_out/bench_wavegan.json 2>> gpurun_out/bench_var.err
-timeout 300 python bench.py --enc unet --steps 10 --warmup 3 --no-cpu-baseline --no-device-dataset > gpurun_out/bench_unet.json 2>> gpurun_out/bench_var.err
-tail -n 5 gpurun_out/bench_var.err
-for f in bench_tf32 bench_wavegan bench_unet; do python - "$f" <<'PY'
-import json,sys
-try:
-    d=json.loads(open(f"gpurun_out/{sys.argv[1]}.json").read().strip().splitlines()[-1])
-    print(sys.argv[1], "value", round(d["value"],3), "ms/step", round(d["ms_per_step"],2), "e2e", round(d["e2e"]["value"],3), "launches/step", d["gpu_launches_per_step"], "roof", d.get("roofline",{}).get("kernel"), round(d.get("roofline",{}).get("frac",0),4))
-except Exception as e: print(sys.argv[1], "unreadable", e)
-PY
+for e in wavegan unet; do
+  timeout 600 python bench.py --enc $e --steps 10 --warmup 3 --no-eager-gpu --no-cpu-baseline --no-throughput-regime --no-device-dataset > gpurun_out/bench_b7_$e.json 2> gpurun_out/bench_$e.err
 done
+timeout 300 python tools/long_sequences.py > gpurun_out/long_sequences.jsonl 2> gpurun_out/long.err; tail -n 3 gpurun_out/long.err
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob("gpurun_out/bench_b7_*net.json"))+sorted(glob.glob("gpurun_out/bench_b7_wavegan.json")):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        print("%-40s value %8.3f ms/step %7.3f e2e %8.3f launches %d roof %.4f"%(f, d["value"], d["ms_per_step"], d["e2e"]["value"], d["gpu_launches_per_step"], d["roofline"]["frac"]))
+    except Exception as e: print(f, "unreadable", e)
+print(open("gpurun_out/long_sequences.jsonl").read()[-1500:])
+PY
