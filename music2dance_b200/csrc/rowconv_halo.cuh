@@ -41,6 +41,7 @@ struct HaloGroup {          // taps t0, t0+dt, ... (Q of them) of one residue pl
 };
 struct HaloPlan {
     int ngroups, cchunks;
+    int trigger;            // 1: griddepcontrol.launch_dependents right after this grid's own dependency wait (M2D_PDL_TRIGGER)
     HaloGroup g[HL_MAXG];
 };
 
@@ -104,6 +105,9 @@ rowconv_halo_kernel(const m2d_rowconv_args a, const HaloPlan plan, const int tpb
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    // Let the next kernel of the stream start its prologue (barrier init, TMEM allocation) on idle SMs now; its own
+    // griddepcontrol.wait still holds it until this grid has completed and flushed.
+    if (plan.trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const long long t_start = TRACE ? clock64() : 0;
 
     if (warp < HL_CW) {
@@ -397,6 +401,8 @@ static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b
 static bool halo_plan(const m2d_rowconv_args& a, HaloPlan& p) {
     p.ngroups = 0;
     p.cchunks = (int)cdiv(a.Cc, TC_BK);
+    static const int trig = halo_env("M2D_PDL_TRIGGER", 0);
+    p.trigger = trig;
     const int sr = a.sr;
     for (int r = 0; r < sr; ++r) {
         // taps of residue r are sr apart in t; the first one:

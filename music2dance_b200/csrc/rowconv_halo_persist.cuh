@@ -77,6 +77,7 @@ rowconv_halo_persist_kernel(const m2d_rowconv_args a, const HaloPlan plan, const
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (plan.trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp < HL_CW) {
         // ------------------------------------------------------------------ converters: raw -> TF32 hi / lo
