@@ -35,22 +35,68 @@ class _Holder(nn.Module):
                            "through the owning SequenceGenerator / SequenceDiscriminator")
 
 
-def _attach(root, dotted, leaf):
+_NODE_CLASSES = {}
+
+
+def _node(cls_name):
+    """Structural node that prints like the reference's module of that name (`str(module)` goes into model_gen.txt /
+    model_critic.txt, phase3/train.py:173-178): a _Holder subclass named after the reference class."""
+    cls = _NODE_CLASSES.get(cls_name)
+    if cls is None:
+        cls = _NODE_CLASSES[cls_name] = type(cls_name, (_Holder,), {})
+    return cls()
+
+
+def _node_class(path, enc_type=None):
+    """Reference class of the structural node at dotted `path` (default.py: who owns which attribute)."""
+    import re
+    table = [(r"audio_enc$", "AudioEncoder"),
+             (r"audio_enc\.model$", {"default": "DefaultAudioEncoder", "unet": "UNetAudioEncoder",
+                                     "wavegan": "WaveGANAudioEncoder"}.get(enc_type, "_Holder")),
+             (r"audio_enc\.model\.(conv_layers|activations)$", "ModuleList"),
+             (r"audio_enc\.model\.activations\.\d+$", "Sequential"),
+             (r"audio_enc\.model\.ublock$", "UBlock"),
+             (r"audio_enc\.model\.ublock\.convblock\d$", "BasisConvBlock"),
+             (r"(audio_rnn|noise_gen)$", "NoiseGen"),
+             (r"decoder$", "FrameDecoder"), (r"decoder\.blocks$", "Sequential"), (r"decoder\.blocks\.\d+$", "LinearBlock"),
+             (r"stick_d$", "StickDiscriminator"), (r"stick_d\.blocks$", "Sequential"),
+             (r"stick_d\.blocks\.\d+$", "TemporalBlock"), (r"audio_d$", "AudioDiscriminator")]
+    for pat, name in table:
+        if re.match(pat, path):
+            return name
+    return "_Holder"
+
+
+def _attach(root, dotted, leaf, enc_type=None):
     node = root
     parts = dotted.split(".")
-    for p in parts[:-1]:
+    for i, p in enumerate(parts[:-1]):
         if p not in node._modules:
-            node.add_module(p, _Holder())
+            name = _node_class(".".join(parts[:i + 1]), enc_type)
+            node.add_module(p, _Holder() if name == "_Holder" else _node(name))
         node = node._modules[p]
     node.add_module(parts[-1], leaf)
+
+
+def _code_activ(activ):
+    """default.py:71-76,98-103,133-138,308-313,336-341: the module the reference applies to a code."""
+    if activ == 'id':
+        return nn.Identity()
+    if activ == 'relu':
+        return nn.ReLU(True)
+    if activ == 'tanh':
+        return nn.Tanh()
+    raise ValueError(f"unknown activ {activ!r} (id | relu | tanh)")
 
 
 def _conv(ci, co, k, s=1, p=0):
     return nn.Conv1d(ci, co, k, stride=s, padding=p)
 
 
-def _encoder_layers(enc_type, f, out):
-    """(dotted name under audio_enc.model, layer) in the reference's creation order."""
+def _encoder_layers(enc_type, f, out, activ='id'):
+    """(dotted name under audio_enc.model, layer) in the reference's creation order; parameter-free layers (ReLU,
+    LeakyReLU, Identity / Tanh, MaxPool1d, Upsample) are listed too so that the module tree prints like the
+    reference's — they draw no random numbers and own no state."""
     L = []
     if enc_type == "default":                      # default.py:59-76
         c = [1, f, 2 * f, 4 * f, 8 * f, 16 * f, 32 * f]
@@ -60,23 +106,32 @@ def _encoder_layers(enc_type, f, out):
         L.append(("conv_layers.6", _conv(c[6], out, 2)))
         for i in range(6):
             L.append((f"activations.{i}.0", nn.BatchNorm1d(c[i + 1])))
+            L.append((f"activations.{i}.1", nn.ReLU(True)))
+        L.append(("activations.6", _code_activ(activ)))
     elif enc_type == "wavegan":                    # default.py:114-135
         c = [1, f, 2 * f, 4 * f, 8 * f]
         for i in range(1, 5):
             L.append((f"l{i}", _conv(c[i - 1], c[i], 25, 4)))
             L.append((f"bn{i}", nn.BatchNorm1d(c[i])))
         L.append(("l5", _conv(c[4], out, 5)))
+        L.append(("relu", nn.ReLU(True)))
+        L.append(("activ", _code_activ(activ)))
     elif enc_type == "unet":                       # default.py:85-104,213-239
         L.append(("conv_layers.0", _conv(1, f, 160, 4, 79)))
         L.append(("conv_layers.1", _conv(f, 2 * f, 4, 2, 1)))
         L.append(("conv_layers.2", _conv(2 * f, 4 * f, 4, 2, 1)))
         for i, ch in enumerate((f, 2 * f, 4 * f)):
             L.append((f"activations.{i}.0", nn.BatchNorm1d(ch)))
+            L.append((f"activations.{i}.1", nn.LeakyReLU(0.2)))
         ch = 4 * f
         for i in range(1, 8):
             L.append((f"ublock.convblock{i}.conv", _conv(ch if i <= 4 else 2 * ch, ch, 3, 1, 1)))
             L.append((f"ublock.convblock{i}.bn", nn.BatchNorm1d(ch)))
+            L.append((f"ublock.convblock{i}.relu", nn.LeakyReLU(0.2)))
+        L.append(("ublock.downsample", nn.MaxPool1d(2, 2)))
+        L.append(("ublock.upsample", nn.Upsample(scale_factor=2, mode="linear", align_corners=False)))
         L.append(("fc", _conv(ch, out, 200)))
+        L.append(("activ", _code_activ(activ)))
     else:
         raise ValueError(f"unknown enc_type {enc_type!r} (default | unet | wavegan)")
     return L
@@ -122,18 +177,22 @@ class SequenceGenerator(nn.Module):
         self.output_size = output_size
         self.device = device
         self.n_blocks, self.n_cells, self.enc_type, self.activ = n_blocks, n_cells, enc_type, activ
-        for name, layer in _encoder_layers(enc_type, 32, input_size):
-            _attach(self, "audio_enc.model." + name, layer)
+        for name, layer in _encoder_layers(enc_type, 32, input_size, activ):
+            _attach(self, "audio_enc.model." + name, layer, enc_type)
         _attach(self, "audio_rnn.rnn", nn.GRU(input_size, latent_size - noise_size, n_cells, batch_first=True))
         _attach(self, "noise_gen.rnn", nn.GRU(noise_size, noise_size, 1, batch_first=True))
         _attach(self, "decoder.fc1", nn.Linear(latent_size, size))
         _attach(self, "decoder.bn1", nn.BatchNorm1d(size, eps=1e-5, momentum=0.1))
+        _attach(self, "decoder.relu", nn.ReLU(inplace=True))
+        if n_blocks == 0:
+            self._modules["decoder"].add_module("blocks", _node("Sequential"))
         for b in range(n_blocks):
             q = f"decoder.blocks.{b}."
             _attach(self, q + "fc1", nn.Linear(size, size))
             _attach(self, q + "fc2", nn.Linear(size, size))
             _attach(self, q + "bn1", nn.BatchNorm1d(size, eps=1e-5, momentum=0.1))
             _attach(self, q + "bn2", nn.BatchNorm1d(size, eps=1e-5, momentum=0.1))
+            _attach(self, q + "relu", nn.ReLU(inplace=True))
         _attach(self, "decoder.lastfc", nn.Linear(size, output_size))
         dec = self._modules["decoder"]
         dec.latent_size, dec.size, dec.output_size, dec.nblocks = latent_size, size, output_size, n_blocks
@@ -236,12 +295,15 @@ def _critic_cfg(self):
                 audio_length=k6 * 4 ** 5)
 
 
-def _build_stick_d(root, channels_in, channels_h, output_code, seqlen, init_ker, n_blocks=2):
+def _build_stick_d(root, channels_in, channels_h, output_code, seqlen, init_ker, n_blocks=2, activ='id'):
     _attach(root, "stick_d.conv1", _conv(channels_in, channels_h, init_ker, 1, int((init_ker - 1) / 2)))
     for b in range(n_blocks):
         _attach(root, f"stick_d.blocks.{b}.conv1", _conv(channels_h, channels_h, 7, 1, 3))
         _attach(root, f"stick_d.blocks.{b}.conv2", _conv(channels_h, channels_h, 7, 1, 3))
+        _attach(root, f"stick_d.blocks.{b}.relu", nn.ReLU(inplace=True))
     _attach(root, "stick_d.fconv", _conv(channels_h, output_code, seqlen))
+    _attach(root, "stick_d.relu", nn.ReLU(inplace=True))
+    _attach(root, "stick_d.activ", _code_activ(activ))
 
 
 class SequenceDiscriminator(nn.Module):
@@ -252,13 +314,16 @@ class SequenceDiscriminator(nn.Module):
         super().__init__()
         self.channels_in, self.channels_h, self.output_code, self.seqlen = channels_in, channels_h, output_code, seqlen
         self.activ = activ
-        _build_stick_d(self, channels_in, channels_h, output_code, seqlen, init_ker)
+        _build_stick_d(self, channels_in, channels_h, output_code, seqlen, init_ker, activ=activ)
         ch = [1, 32, 64, 128, 256, 512]
         for i in range(1, 6):                                    # default.py:298-302
             _attach(self, f"audio_d.l{i}", _conv(ch[i - 1], ch[i], 25, 4, 11))
         _attach(self, "audio_d.l6", _conv(512, output_code, 75))
+        _attach(self, "audio_d.relu", nn.ReLU(True))
+        _attach(self, "audio_d.activ", _code_activ(activ))
         self.fc1 = nn.Linear(2 * output_code, 128)
         self.fc2 = nn.Linear(128, 1)
+        self.relu = nn.ReLU(True)
         initialize_weights(self)
         self.to(device)
 
@@ -282,9 +347,10 @@ class AblatedSequenceDiscriminator(nn.Module):
         super().__init__()
         self.channels_in, self.channels_h, self.output_code, self.seqlen = channels_in, channels_h, output_code, seqlen
         self.activ = activ
-        _build_stick_d(self, channels_in, channels_h, output_code, seqlen, 9)
+        _build_stick_d(self, channels_in, channels_h, output_code, seqlen, 9, activ=activ)
         self.fc1 = nn.Linear(output_code, 128)
         self.fc2 = nn.Linear(128, 1)
+        self.relu = nn.ReLU(True)
         initialize_weights(self)
         self.to(device)
 

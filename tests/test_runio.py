@@ -6,6 +6,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from music2dance_b200 import runio
@@ -94,6 +95,28 @@ def test_scalars_from_trainer_logs_structure():
                       ("l1_loss_train", 0.75, 8)]
 
 
+@pytest.mark.parametrize("variant", ["default", "wavegan", "unet", "ablated", "tanh", "relu", "tv", "noise_enhanced"])
+def test_module_text_matches_reference(variant):
+    """phase3/train.py:173-178 writes `str(gen)` / `str(critic)` to model_gen.txt / model_critic.txt: the drop-in
+    modules print EXACTLY what the reference's modules print (fixture: tests/golden/make_golden_repr.py ran the
+    unmodified reference) — structural nodes named after the reference's classes, parameter-free layers included."""
+    import json
+    from music2dance_b200.archis.default import (AblatedSequenceDiscriminator, SequenceDiscriminator,
+                                                 SequenceGenerator)
+    from oracle import phase3_oracle as O
+    from tests.parity import VARIANTS
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "module_repr.json")))[variant]
+    cfg = O.make_cfg(**VARIANTS[variant])
+    gen = SequenceGenerator(cfg["audio_feat_samples"], cfg["input_vector_size"], cfg["latent_vector_size"], cfg["size"],
+                            cfg["output_size"], cfg["noise_size"], cfg["nblocks_gen"], cfg["n_cells"], cfg["enc_type"],
+                            cfg["activ"], "cpu")
+    cls = AblatedSequenceDiscriminator if cfg["ablated"] else SequenceDiscriminator
+    critic = cls(cfg["output_size"], cfg["channels"], cfg["code_size"], cfg["stick_length"],
+                 init_ker=cfg["init_kernel"], activ=cfg["activ"], device="cpu")
+    assert str(gen) == gold["gen"]
+    assert str(critic) == gold["critic"]
+
+
 def test_checkpoint_files_round_trip_with_reference_keys(tmp_path):
     """Files written at the reference cadence hold the drop-in modules' state_dict (= the reference's keys, SURVEY
     Appendix A) and load back strictly."""
@@ -120,4 +143,4 @@ def test_checkpoint_files_round_trip_with_reference_keys(tmp_path):
     assert list(torch.load(paths[1])) == list(critic.state_dict())
     runio.write_model_descriptions(str(tmp_path), gen, critic)
     assert open(tmp_path / "model_gen.txt").read() == str(gen)
-    assert open(tmp_path / "model_critic.txt").read().startswith("SequenceDiscriminator(")
+    assert open(tmp_path / "model_critic.txt").read().startswith("SequenceDiscriminator(\n  (stick_d): StickDiscriminator(")
