@@ -228,13 +228,17 @@ __device__ __forceinline__ void gru_mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void gru_mbar_expect(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Default semantics (.acquire at CTA scope): everything the waiter reads after the phase completes is SHARED memory
+// written by st.async / st.shared + complete_tx on this very barrier.  The cluster-scope acquire used before made ptxas
+// emit CCTL.IVALL (invalidate the whole L1) after every successful wait — 10 % of the kernel's stall samples (ncu source
+// page, round 2) and a cold L1 for the input-projection loads of every step.
 __device__ __forceinline__ void gru_mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0, spins = 0;
     while (true) {
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t"
             "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
         if (ok) break;
@@ -314,12 +318,23 @@ gru_fwd2_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, co
     const bool sender = lane < nb && (u0 + 4 * (tid >> 5)) < H && 4 * (tid >> 5) < nu;
     float bhr = 0.f, bhz = 0.f, bhn = 0.f;
     long long row0 = 0;
-    float gir = 0.f, giz = 0.f, gin = 0.f, hprev = 0.f;
+    float hprev = 0.f;
+    // input projections of the next GI_D steps live in registers: one step ahead is not enough — the load (L2 / HBM
+    // latency, 700+ cycles) would be waited for at the end of EVERY step of a chain whose own work is ~500 cycles
+    constexpr int GI_D = 4;
+    float pr[GI_D], pz[GI_D], pn[GI_D];
+#pragma unroll
+    for (int d = 0; d < GI_D; ++d) { pr[d] = 0.f; pz[d] = 0.f; pn[d] = 0.f; }
     if (fin) {
         bhr = b_hh[uu]; bhz = b_hh[H + uu]; bhn = b_hh[2 * H + uu];
         row0 = (long long)(b0 + kp) * T;
-        const float* g0 = gi + row0 * 3 * H;
-        gir = g0[uu]; giz = g0[H + uu]; gin = g0[2 * H + uu];
+#pragma unroll
+        for (int d = 0; d < GI_D; ++d) {
+            if (d < T) {
+                const float* g0 = gi + (row0 + d) * 3 * H;
+                pr[d] = g0[uu]; pz[d] = g0[H + uu]; pn[d] = g0[2 * H + uu];
+            }
+        }
     }
     const uint32_t hs_addr = gru_smem_u32(&hs[0][0][0]);
     __syncthreads();
@@ -332,10 +347,12 @@ gru_fwd2_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, co
             gru_mbar_wait(bar0 + 8 * cur, parity);
             if (tid == 0 && t + 2 <= T - 1) gru_mbar_expect(bar0 + 8 * cur, tx_bytes);
         }
-        float nr = 0.f, nz = 0.f, nn = 0.f;
-        if (fin && t + 1 < T) {                          // prefetch next step's input projection
-            const float* g1 = gi + (row0 + t + 1) * 3 * H;
-            nr = g1[uu]; nz = g1[H + uu]; nn = g1[2 * H + uu];
+        const float gir = pr[0], giz = pz[0], gin = pn[0];
+#pragma unroll
+        for (int d = 0; d + 1 < GI_D; ++d) { pr[d] = pr[d + 1]; pz[d] = pz[d + 1]; pn[d] = pn[d + 1]; }
+        if (fin && t + GI_D < T) {                       // input projection of step t + GI_D
+            const float* g1 = gi + (row0 + t + GI_D) * 3 * H;
+            pr[GI_D - 1] = g1[uu]; pz[GI_D - 1] = g1[H + uu]; pn[GI_D - 1] = g1[2 * H + uu];
         }
         float ar = 0.f, az = 0.f, an = 0.f;
         for (int b = 0; b < nb; ++b) {                   // every lane takes part (full-mask shuffles)
@@ -372,7 +389,6 @@ gru_fwd2_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, co
                 float* sv = save + row * 4 * H;
                 sv[uu] = r; sv[H + uu] = z; sv[2 * H + uu] = n; sv[3 * H + uu] = ghn;
             }
-            gir = nr; giz = nz; gin = nn;
         }
         // gather the warp's four units of batch entry (lane & 7) into one 16-byte message
         float4 h4;
