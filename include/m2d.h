@@ -208,6 +208,15 @@ int m2d_bn_apply(const float* x, int ldx, float* y, int ldy, long long M, int C,
                  const double* acc, const float* gamma, const float* beta,
                  float* running_mean, float* running_var, float momentum, float eps,
                  float* mr, int act, void* stream);
+/* The same over `groups` consecutive row blocks of M rows each, one launch: block z is normalised with its OWN batch
+ * statistics (acc + z*2C; mr + z*2C when given) and the running statistics advance block by block in order — i.e.
+ * `groups` train-mode forwards of the same module on `groups` batches (the generator forwards of several critic
+ * iterations, train.py:193-196, evaluated as one batched pass; the generator's weights do not change in between). */
+int m2d_colstats_groups(const float* x, int ld, long long M, int C, int groups, double* acc, void* stream);
+int m2d_bn_apply_groups(const float* x, int ldx, float* y, int ldy, long long M, int C, int groups,
+                        const double* acc, const float* gamma, const float* beta,
+                        float* running_mean, float* running_var, float momentum, float eps,
+                        float* mr, int act, void* stream);
 /* stats + apply in ONE launch (grid-wide rendezvous inside the kernel): acc = 2C + 1 ZEROED doubles (sums, sums of
  * squares, rendezvous counter).  What the generator forward uses; colstats / bn_apply remain for callers that
  * accumulate statistics over several calls. */

@@ -74,6 +74,8 @@ SIGNATURES = {
     "m2d_gru_backward": [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _P],
     "m2d_colstats": [_P, _I, _L, _I, _P, _P],
     "m2d_bn_apply": [_P, _I, _P, _I, _L, _I, _P, _P, _P, _P, _P, _F, _F, _P, _I, _P],
+    "m2d_colstats_groups": [_P, _I, _L, _I, _I, _P, _P],
+    "m2d_bn_apply_groups": [_P, _I, _P, _I, _L, _I, _I, _P, _P, _P, _P, _P, _F, _F, _P, _I, _P],
     "m2d_bn_train": [_P, _I, _P, _I, _L, _I, _P, _P, _P, _P, _P, _F, _F, _P, _I, _P],
     "m2d_bn_eval": [_P, _I, _P, _I, _L, _I, _P, _P, _P, _P, _F, _I, _P],
     "m2d_bn_bwd_reduce": [_P, _I, _P, _I, _P, _I, _L, _I, _P, _I, _P, _P],

@@ -60,6 +60,9 @@ __device__ __forceinline__ void col_reduce(long long M, int C, long long rows_pe
 
 __global__ void __launch_bounds__(256)
 colstats_kernel(const float* __restrict__ x, int ld, long long M, int C, long long rows_per, double* acc) {
+    // blockIdx.z = group: M rows each, statistics of group z at acc + z*2C (m2d_colstats_groups)
+    x += (long long)blockIdx.z * M * ld;
+    acc += (long long)blockIdx.z * 2 * C;
     col_reduce<2>(M, C, rows_per, acc, [&](long long r, int c, float* v) {
         float t = x[r * ld + c];
         v[0] = t;
@@ -131,18 +134,34 @@ bn_apply_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     const int ry = threadIdx.x >> 5;
     if (c >= C) return;
+    // blockIdx.z = group (m2d_bn_apply_groups): M rows each, normalised with the group's own statistics; the running
+    // statistics advance group by group in order, exactly as gridDim.z separate calls would
+    if (blockIdx.y == 0 && blockIdx.z == 0 && ry == 0 && running_mean) {
+        float rm = running_mean[c], rv = running_var[c];
+        for (unsigned z = 0; z < gridDim.z; ++z) {
+            const double* a = acc + (long long)z * 2 * C;
+            const double mean = a[c] / (double)M;
+            double var = a[C + c] / (double)M - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
+            rm = (1.f - momentum) * rm + momentum * (float)mean;
+            rv = (1.f - momentum) * rv + momentum * (float)unb;
+        }
+        running_mean[c] = rm;
+        running_var[c] = rv;
+    }
+    acc += (long long)blockIdx.z * 2 * C;
+    x += (long long)blockIdx.z * M * ldx;
+    if (y) y += (long long)blockIdx.z * M * ldy;
     const double mean = acc[c] / (double)M;
     double var = acc[C + c] / (double)M - mean * mean;
     if (var < 0.0) var = 0.0;
     const float rstd = (float)(1.0 / sqrt(var + (double)eps));
     const float mu = (float)mean;
-    if (blockIdx.y == 0 && ry == 0) {
-        if (mr) { mr[c] = mu; mr[C + c] = rstd; }
-        if (running_mean) {
-            double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
-            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
-            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
-        }
+    if (blockIdx.y == 0 && ry == 0 && mr) {
+        float* o = mr + (long long)blockIdx.z * 2 * C;
+        o[c] = mu;
+        o[C + c] = rstd;
     }
     if (!y) return;      // statistics-only call (dead LinearBlock branch, Q1)
     const float g = gamma[c], bt = beta[c];
@@ -684,23 +703,36 @@ __global__ void timestamp_kernel(unsigned long long* slot) {
 
 using namespace m2d;
 
-extern "C" int m2d_colstats(const float* x, int ld, long long M, int C, double* acc, void* stream) {
-    M2D_REQUIRE(x && acc && M > 0 && C > 0, "colstats: bad args");
+extern "C" int m2d_colstats_groups(const float* x, int ld, long long M, int C, int groups, double* acc, void* stream) {
+    M2D_REQUIRE(x && acc && M > 0 && C > 0 && groups > 0 && groups <= 65535, "colstats: bad args");
     ColGrid g = col_grid(M, C);
+    g.grid.z = (unsigned)groups;
     colstats_kernel<<<g.grid, 256, 0, (cudaStream_t)stream>>>(x, ld, M, C, g.rows_per, acc);
     return check_launch("colstats");
 }
+extern "C" int m2d_colstats(const float* x, int ld, long long M, int C, double* acc, void* stream) {
+    return m2d_colstats_groups(x, ld, M, C, 1, acc, stream);
+}
 
-extern "C" int m2d_bn_apply(const float* x, int ldx, float* y, int ldy, long long M, int C,
-                            const double* acc, const float* gamma, const float* beta,
-                            float* running_mean, float* running_var, float momentum, float eps,
-                            float* mr, int act, void* stream) {
-    M2D_REQUIRE(x && acc && gamma && beta && M > 0 && C > 0, "bn_apply: bad args");
+extern "C" int m2d_bn_apply_groups(const float* x, int ldx, float* y, int ldy, long long M, int C, int groups,
+                                   const double* acc, const float* gamma, const float* beta,
+                                   float* running_mean, float* running_var, float momentum, float eps,
+                                   float* mr, int act, void* stream) {
+    M2D_REQUIRE(x && acc && gamma && beta && M > 0 && C > 0 && groups > 0 && groups <= 65535, "bn_apply: bad args");
+    M2D_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "bn_apply: running_mean / running_var go together");
     ColGrid g = col_grid(M, C);
+    g.grid.z = (unsigned)groups;
     bn_apply_kernel<<<g.grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, M, C, g.rows_per, acc, gamma,
                                                             beta, running_mean, running_var, momentum,
                                                             eps, mr, act);
     return check_launch("bn_apply");
+}
+extern "C" int m2d_bn_apply(const float* x, int ldx, float* y, int ldy, long long M, int C,
+                            const double* acc, const float* gamma, const float* beta,
+                            float* running_mean, float* running_var, float momentum, float eps,
+                            float* mr, int act, void* stream) {
+    return m2d_bn_apply_groups(x, ldx, y, ldy, M, C, 1, acc, gamma, beta, running_mean, running_var, momentum, eps,
+                               mr, act, stream);
 }
 
 extern "C" int m2d_bn_train(const float* x, int ldx, float* y, int ldy, long long M, int C, double* acc,

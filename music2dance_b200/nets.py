@@ -270,7 +270,15 @@ class BNLayer:
     def fwd(self, c, a, act, train, wk):
         """a = act(BN(c)).  `a` None: only update running statistics (dead branch)."""
         cf = c.flat_rows()
-        if train and _BN_ONE_LAUNCH:
+        groups = getattr(wk, "groups", 1)
+        if train and groups > 1:
+            # `groups` forwards of this module in one pass (GeneratorNet.forward groups=): per-block statistics, the
+            # running statistics advance block by block; no backward follows, so mean / rstd are not kept
+            acc = wk.acc_slot(2 * self.C * groups)
+            ops.colstats(cf, acc, groups=groups)
+            ops.bn_apply(cf, None if a is None else a.flat_rows(), acc, self.gamma, self.beta, self.rm,
+                         self.rv, None, act, groups=groups)
+        elif train and _BN_ONE_LAUNCH:
             acc = wk.acc_slot(2 * self.C + 1)       # sums, sums of squares, rendezvous counter (zeroed with the arena)
             ops.bn_train(cf, None if a is None else a.flat_rows(), acc, self.gamma, self.beta, self.rm,
                          self.rv, self.mr, act)
@@ -646,10 +654,17 @@ class GeneratorNet:
         pad = cfg["pad_samples"]
         return (T, cfg["cutting_stride"], pad // 2, None, cfg["audio_feat_samples"])
 
-    def forward(self, audio, noise, B, T, train=True, out=None, slices=None):
+    def forward(self, audio, noise, B, T, train=True, out=None, slices=None, wk=None, groups=1):
         """audio [B, A] raw (fused windowing) or, if `slices` [B,T,W] is given, explicit
-        windows (the drop-in module path).  noise [B,T,Nz].  Returns Mat [1,B*T,O]."""
-        wk, cfg = self.wk, self.cfg
+        windows (the drop-in module path).  noise [B,T,Nz].  Returns Mat [1,B*T,O].
+        groups > 1 (train mode, forward only): the B sequences are `groups` consecutive batches of B / groups — the
+        result, BatchNorm batch statistics and running-statistic updates are those of `groups` successive forwards
+        (the generator's weights do not change between the critic iterations of a train step, train.py:187-216), in
+        one pass over `wk`, a Workspace of its own; nothing is kept for a backward."""
+        assert groups == 1 or (train and wk is not None and wk is not self.wk and B % groups == 0)
+        save = groups == 1
+        wk, cfg = (self.wk if wk is None else wk), self.cfg
+        wk.groups = groups
         wk.acc_reset()
         nb = B * T
         if slices is not None:
@@ -667,16 +682,16 @@ class GeneratorNet:
         if side is not None:
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                self.nrnn.fwd(nz, z.cols_slice(self.H, self.Lat), B, T, wk, save=True)
+                self.nrnn.fwd(nz, z.cols_slice(self.H, self.Lat), B, T, wk, save=save)
         ops.mark("g:start")
         self.enc.fwd(src, nb, win, wk, train, enc_out)
         ops.mark("g:enc")
-        self.rnn.fwd(enc_out.as_rows(1, nb), z.cols_slice(0, self.H), B, T, wk, save=True)
+        self.rnn.fwd(enc_out.as_rows(1, nb), z.cols_slice(0, self.H), B, T, wk, save=save)
         ops.mark("g:rnn")
         if side is not None:
             cur.wait_stream(side)
         else:
-            self.nrnn.fwd(nz, z.cols_slice(self.H, self.Lat), B, T, wk, save=True)
+            self.nrnn.fwd(nz, z.cols_slice(self.H, self.Lat), B, T, wk, save=save)
         c = wk.mat("g:dec_c0", 1, nb, self.S)
         self.fc1.fwd(z, c, ws=wk.scratch)
         d = wk.mat("g:dec_d0", 1, nb, self.S)
@@ -700,10 +715,10 @@ class GeneratorNet:
         self.d_last = d
         if train:
             if self.nbt_flat is not None:
-                self.nbt_flat.add_(1)            # every num_batches_tracked is a view of this buffer
+                self.nbt_flat.add_(groups)       # every num_batches_tracked is a view of this buffer
             else:
                 for t in self.nbt:
-                    t.add_(1)
+                    t.add_(groups)
         return fake
 
     def backward(self, dfake):

@@ -197,15 +197,20 @@ def gru_backward(dh_out, ldd, h_out, ldh, save, w_hh, dgi, dgh, B, T, H):
          B, T, H, _stream())
 
 
-def colstats(x, acc):
+def colstats(x, acc, groups=1):
+    """acc[z*2C : (z+1)*2C] += column sums / sums of squares of row block z (x.M / groups rows each)."""
+    assert x.M % groups == 0
     LAUNCHES[0] += 1
-    call("m2d_colstats", x.ptr, x.ld, x.M, x.cols, _p(acc), _stream())
+    call("m2d_colstats_groups", x.ptr, x.ld, x.M // groups, x.cols, groups, _p(acc), _stream())
 
 
-def bn_apply(x, y, acc, gamma, beta, rm, rv, mr, act, momentum=0.1, eps=1e-5):
+def bn_apply(x, y, acc, gamma, beta, rm, rv, mr, act, momentum=0.1, eps=1e-5, groups=1):
+    """Train-mode BatchNorm of `groups` consecutive row blocks, each with its own statistics; the running statistics
+    advance block by block (groups separate forwards in one launch)."""
+    assert x.M % groups == 0
     LAUNCHES[0] += 1
-    call("m2d_bn_apply", x.ptr, x.ld, None if y is None else y.ptr, 0 if y is None else y.ld, x.M, x.cols,
-         _p(acc), _p(gamma), _p(beta), _p(rm), _p(rv), momentum, eps, _p(mr), act, _stream())
+    call("m2d_bn_apply_groups", x.ptr, x.ld, None if y is None else y.ptr, 0 if y is None else y.ld, x.M // groups,
+         x.cols, groups, _p(acc), _p(gamma), _p(beta), _p(rm), _p(rv), momentum, eps, _p(mr), act, _stream())
 
 
 def bn_train(x, y, acc, gamma, beta, rm, rv, mr, act, momentum=0.1, eps=1e-5):

@@ -24,10 +24,12 @@ import torch
 from . import dp, ops
 from .engine import AdamPack
 from .ops import Mat
-from .nets import ACT_ID, PRIO_CHAIN, PRIO_GEN, make_stream
+from .nets import ACT_ID, PRIO_CHAIN, PRIO_GEN, Workspace, make_stream
 from .wgan import (critic_backward_fused, critic_forward, critic_forward_fused, gradient_penalty_pass, rows,
                    wasserstein_backward)
 
+# one batched generator pass serves at most this many sequences (trainer.gen_groups)
+GEN_GROUP_SEQUENCES = 64
 LOG_CRITIC = ("loss_critic", "gp", "w_dist", "err_real", "err_fake")
 LOG_GEN = ("loss_gen", "l1", "tv", "err_real", "err_fake")
 
@@ -127,6 +129,13 @@ class Phase3Trainer:
         self.overlap = os.environ.get("M2D_OVERLAP", "1") != "0"
         self.s_gen = make_stream(dev, PRIO_GEN)
         self.s_main = make_stream(dev, PRIO_CHAIN)          # capture stream of the step graph(s)
+        # ... and because the weights are constant, several of these forwards can be ONE batched pass with per-batch
+        # BatchNorm statistics (GeneratorNet.forward groups=): gen_groups maps the first iteration of a pass to the
+        # number of iterations it serves.  Small batches only (the kernels of a batch-7 forward are latency-bound; from
+        # 64 sequences on they fill the machine anyway).  M2D_GEN_GROUPS="1,7" style lists override the default.
+        self.gen_groups = self._plan_gen_groups(os.environ.get("M2D_GEN_GROUPS"))
+        self.gen_wk = {g: Workspace(dev, scratch_floats=1 << 25) for g in set(self.gen_groups.values()) if g > 1}
+        self.gen_audio = torch.zeros(nc * B, A, **f) if self.gen_wk else None
         # measured on B200 at batch 7: 0 -> 57.0, 4 -> 55.8, 8 -> 50.3 train steps/s: under contention a generator
         # forward takes about as long as a critic iteration, so its latency matters as much as its SM footprint
         self.gru_bg = int(os.environ.get("M2D_GRU_BG", "0"))
@@ -219,11 +228,40 @@ class Phase3Trainer:
         if self.overlap and self.gru_bg:
             ops.set_gru_forward_batch_group(self.gru_bg if on else 0)
 
+    def _plan_gen_groups(self, spec):
+        nc, B = self.nc, self.B
+        if spec:
+            sizes = [int(x) for x in spec.split(",")]
+            assert all(g >= 1 for g in sizes) and sum(sizes) == nc, f"M2D_GEN_GROUPS={spec!r} must sum to n_critic={nc}"
+        else:
+            gmax = max(1, GEN_GROUP_SEQUENCES // B)
+            sizes, left = [1], nc - 1            # the first iteration's poses are needed at once: a pass of its own
+            while left > 0:
+                sizes.append(min(gmax, left))
+                left -= sizes[-1]
+        plan, i = {}, 0
+        for g in sizes:
+            plan[i] = g
+            i += g
+        return plan
+
     def _gen_forward(self, i):
-        """Generator forward of critic iteration i (train-mode BatchNorm, no graph kept)."""
+        """Generator forward(s) of critic iteration i (train-mode BatchNorm, nothing kept for a backward): the pass
+        that STARTS at iteration i serves gen_groups[i] iterations; for the others the poses are already there."""
+        g = self.gen_groups.get(i)
+        if g is None:
+            return
+        B, T = self.B, self.T
         self._gru_side(True)
-        self.G.forward(self.in_audio[i], self.in_noise[i], self.B, self.T, train=True,
-                       out=Mat.of(self.fake_c[i], 1, self.B * self.T, self.O))
+        if g == 1:
+            self.G.forward(self.in_audio[i], self.in_noise[i], B, T, train=True,
+                           out=Mat.of(self.fake_c[i], 1, B * T, self.O))
+        else:
+            # audio of the g iterations, contiguous (it is staged as the first half of [2B, A] blocks): one 2-D copy
+            dst = self.gen_audio[i * B:(i + g) * B]
+            ops.copy2d(Mat(self.in_audio2[i:i + g], 1, g, B * self.A, 2 * B * self.A), Mat(dst, 1, g, B * self.A))
+            self.G.forward(dst, self.in_noise[i:i + g], g * B, T, train=True,
+                           out=Mat.of(self.fake_c[i:i + g], 1, g * B * T, self.O), wk=self.gen_wk[g], groups=g)
         self._gru_side(False)
 
     def _gen_forward_update(self):
@@ -370,7 +408,7 @@ class Phase3Trainer:
                 self.s_gen.wait_stream(main)
                 with torch.cuda.stream(self.s_gen):
                     if i + 1 < self.nc:
-                        self._gen_forward(i + 1)
+                        self._gen_forward(i + 1)         # no-op unless a (batched) pass starts at iteration i + 1
                     else:
                         self._gen_forward_update()
                 self.critic_iteration(i, update=False, gen_inline=False)

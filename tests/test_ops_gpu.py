@@ -363,6 +363,50 @@ def test_batchnorm(lib, case, act):
     close(rv3, rv2, what="bn_train running_var")
 
 
+@pytest.mark.parametrize("case", [(840, 256, 7), (53760, 32, 4), (77, 250, 3)])
+def test_batchnorm_groups(lib, case):
+    """m2d_colstats_groups / m2d_bn_apply_groups: `groups` row blocks in one launch = `groups` successive train-mode
+    forwards (own batch statistics per block, running statistics advanced block by block in order)."""
+    from music2dance_b200.ops import Mat
+    Mg, C, Gn = case
+    g = torch.Generator().manual_seed(18)
+    x = (torch.randn(Gn, Mg, C, generator=g) * torch.arange(1, Gn + 1).view(Gn, 1, 1) + 3).to(DEV)   # blocks differ
+    gamma, beta = (torch.rand(C, generator=g) + 0.5).to(DEV), torch.randn(C, generator=g).to(DEV)
+    rm0, rv0 = torch.randn(C, generator=g).to(DEV), (torch.rand(C, generator=g) + 0.5).to(DEV)
+    # one call per block
+    rm1, rv1 = rm0.clone(), rv0.clone()
+    y1 = torch.empty_like(x)
+    mr1 = torch.empty(Gn, 2 * C, device=DEV)
+    for z in range(Gn):
+        acc = torch.zeros(2 * C, dtype=torch.float64, device=DEV)
+        X = Mat.of(x[z], 1, Mg, C)
+        lib.colstats(X, acc)
+        lib.bn_apply(X, Mat.of(y1[z], 1, Mg, C), acc, gamma, beta, rm1, rv1, mr1[z], 1)
+    # all blocks in one launch pair
+    rm2, rv2 = rm0.clone(), rv0.clone()
+    y2 = torch.empty_like(x)
+    mr2 = torch.empty(Gn, 2 * C, device=DEV)
+    acc = torch.zeros(Gn * 2 * C, dtype=torch.float64, device=DEV)
+    X = Mat.of(x, 1, Gn * Mg, C)
+    lib.colstats(X, acc, groups=Gn)
+    lib.bn_apply(X, Mat.of(y2, 1, Gn * Mg, C), acc, gamma, beta, rm2, rv2, mr2, 1, groups=Gn)
+    torch.cuda.synchronize()
+    # same arithmetic; the fp64 partial sums may be added in a different order (atomics): far below float resolution
+    close(y2, y1, tol=1e-6, what="grouped bn forward")
+    close(mr2, mr1, tol=1e-6, what="grouped bn mean / rstd")
+    close(rm2, rm1, tol=1e-6, what="grouped bn running_mean")
+    close(rv2, rv1, tol=1e-6, what="grouped bn running_var")
+    # statistics-only form (dead LinearBlock branch)
+    rm3, rv3 = rm0.clone(), rv0.clone()
+    acc.zero_()
+    lib.colstats(X, acc, groups=Gn)
+    lib.bn_apply(X, None, acc, gamma, beta, rm3, rv3, None, 1, groups=Gn)
+    close(rm3, rm1, tol=1e-6, what="grouped bn (stats only) running_mean")
+    close(rv3, rv1, tol=1e-6, what="grouped bn (stats only) running_var")
+    ref = F.batch_norm(x[Gn - 1].cpu(), None, None, gamma.cpu(), beta.cpu(), True, 0.1, 1e-5).relu()
+    close(y2[Gn - 1], ref, what="grouped bn vs torch (last block)")
+
+
 def test_pool_upsample(lib):
     from music2dance_b200.ops import Mat
     g = torch.Generator().manual_seed(9)

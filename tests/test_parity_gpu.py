@@ -314,6 +314,45 @@ def test_trainer_every_iteration_vs_oracle_resynced(variant, B, nc):
         _sync_trainer_from_oracle(tr, gen, critic, G, D, ad, ag)
 
 
+@pytest.mark.parametrize("variant,groups", [("default", "4"), ("default", "1,3"), ("unet", "2,2"), ("wavegan", "4"),
+                                            ("noise_enhanced", "1,1,2")])
+def test_batched_generator_passes_match_one_pass_per_iteration(variant, groups, monkeypatch):
+    """trainer.gen_groups: the generator forwards of several critic iterations as ONE pass (per-batch BatchNorm
+    statistics, running statistics advanced batch by batch) against one pass per iteration — generated poses of every
+    iteration, the generator's BatchNorm buffers after the step, and the step's logs."""
+    from music2dance_b200.trainer import Phase3Trainer
+    nc, B = 4, 2
+    cfg = O.make_cfg(n_critic_steps=nc, **VARIANTS[variant])
+    res = []
+    for spec in (",".join(["1"] * nc), groups):
+        monkeypatch.setenv("M2D_GEN_GROUPS", spec)
+        gen, critic = build(cfg)
+        tr = Phase3Trainer(gen, critic, cfg, B, use_graphs=False)
+        assert sorted(tr.gen_groups.values()) == sorted(int(x) for x in spec.split(","))
+        bs = [O.synthetic_batch(cfg, B, 9100 + i) for i in range(nc)]
+        tr.load_batches(*[torch.stack([b[j] for b in bs]) for j in range(4)], bs[-1][4])
+        tr.train_step()
+        logs = tr.logs()
+        bufs = {k: v.detach().cpu().clone() for k, v in gen.named_buffers()}
+        res.append((tr.fake_c.cpu().clone(), bufs, logs))
+    (f0, b0, l0), (f1, b1, l1) = res
+    for i in range(nc):
+        e = float((f1[i] - f0[i]).abs().max() / f0[i].abs().max())
+        assert e < 2e-5, f"{variant} {groups}: generated poses of iteration {i} differ by {e:.2e}"
+    for k, v in b0.items():
+        if v.is_floating_point():
+            e = float((b1[k] - v).abs().max() / max(float(v.abs().max()), 0.1))
+            assert e < 1e-5, f"{variant} {groups}: {k} differs by {e:.2e}"
+        else:
+            assert torch.equal(b1[k], v), k                       # num_batches_tracked: nc + 1 forwards either way
+    for i in range(nc):
+        for k in ("loss_critic", "gp", "w_dist"):
+            scalar_check(l1["critic"][i][k], l0["critic"][i][k], TOL_NORTH_STAR if i == 0 else TOL_CHAINED,
+                         f"{variant} {groups} it{i} {k}")
+    for k in ("loss_gen", "l1"):
+        scalar_check(l1["gen"][k], l0["gen"][k], TOL_CHAINED, f"{variant} {groups} gen {k}")
+
+
 @pytest.mark.parametrize("variant,B", [("default", 7), ("ablated", 4), ("tanh", 2)])
 def test_critic_gradients_full_tensor_vs_oracle(variant, B):
     """Every critic gradient of one iteration compared over ALL its elements (the fixture checks are 64-sample digests):
