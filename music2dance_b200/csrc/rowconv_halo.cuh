@@ -515,8 +515,9 @@ static int rowconv_halo_dispatch(const m2d_rowconv_args& a, int M, int mode, cud
     const int nunits = plan.ngroups * plan.cchunks;
     const long long tiles = tiles_m * cdiv(a.N, TC_BNMAX);
     int splits = 1;
-    if (tiles < kNumSMs && nunits >= 2) {
-        long long want = kNumSMs / tiles;                    // keep the launch inside ONE wave of CTAs
+    static const int split_target = halo_env("M2D_SPLIT_CTAS", kNumSMs);
+    if (tiles < split_target && nunits >= 2) {
+        long long want = split_target / tiles;               // keep the launch inside ONE wave of CTAs
         splits = (int)(want < nunits ? want : nunits);
         if (splits < 1) splits = 1;
     }

@@ -546,8 +546,9 @@ int rowconv_tc_dispatch(const m2d_rowconv_args& a, int M, int mode, cudaStream_t
     const int nsteps = c1 ? (int)cdiv(a.T, TC_BK) : a.T * cchunks;
     const long long tiles = cdiv(M, TC_BM) * cdiv(a.N, TC_BNMAX);
     int splits = 1;
-    if (tiles < kNumSMs && nsteps >= 8) {          // few tiles, long K: split K over a cluster
-        long long want = cdiv(kNumSMs, tiles);
+    static const int split_target = getenv("M2D_SPLIT_CTAS") ? atoi(getenv("M2D_SPLIT_CTAS")) : kNumSMs;
+    if (tiles < split_target && nsteps >= 8) {          // few tiles, long K: split K over a cluster
+        long long want = cdiv(split_target, tiles);
         splits = (int)(want < nsteps / 4 ? want : nsteps / 4);
         if (splits < 1) splits = 1;
     }
@@ -846,7 +847,11 @@ int wgrad_tc_dispatch(const m2d_wgrad_args& a, int Ktot, int Ncols, int mode, cu
     if (!ok || (long long)a.Cout * Ncols * Ktot < (1ll << 18)) return 1;
     const int nsteps = (int)cdiv(Ktot, TC_BK);
     const long long tiles = cdiv(a.Cout, TC_BM) * cdiv(Ncols, TC_BNMAX);
-    long long want = cdiv(2 * kNumSMs, tiles);
+    // split K until the launch fills ONE wave of SMs: weight gradients are leaves of the step's dependency graph and
+    // run next to the tangent chain, so their SM footprint counts, not their latency (measured on B200, batch 7,
+    // train steps/s by target CTAs: 74 -> 60.4, 120 -> 62.4, 148 -> 62.6, 185 -> 62.3, 296 -> 61.6, 592 -> 61.0)
+    static const int target = getenv("M2D_WGRAD_CTAS") ? atoi(getenv("M2D_WGRAD_CTAS")) : kNumSMs;
+    long long want = cdiv(target, tiles);
     int splits = (int)(want < nsteps / 2 ? want : nsteps / 2);
     if (splits < 1) splits = 1;
     // TF32_BF16 applies to the row convolutions only: weight gradients (MN-major operands) stay 3xTF32

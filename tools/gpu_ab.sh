@@ -3,8 +3,9 @@
 set -u
 mkdir -p gpurun_out
 V=$1; A=$2; B=$3; BATCH=${4:-7}
+EXTRA=${M2D_AB_EXTRA:-}
 for rep in 1 2; do for val in $A $B; do
-  env $V=$val timeout 400 python bench.py --batch $BATCH --steps 15 --warmup 3 --no-eager-gpu --no-cpu-baseline --no-throughput-regime --no-device-dataset --no-roofline > gpurun_out/ab_${val}_$rep.json 2> gpurun_out/ab.err
+  env $EXTRA $V=$val timeout 400 python bench.py --batch $BATCH --steps 15 --warmup 3 --no-eager-gpu --no-cpu-baseline --no-throughput-regime --no-device-dataset --no-roofline > gpurun_out/ab_${val}_$rep.json 2> gpurun_out/ab.err
   python - $V $val $rep <<'PY'
 import json,sys
 try:
