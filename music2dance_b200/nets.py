@@ -31,6 +31,7 @@ PRIO_CHAIN, PRIO_LATE, PRIO_GEN, PRIO_LEAF = (-3, -2, -1, 0) if _PRIO_ON else (0
 # M2D_BN_FUSED=1: train-mode BatchNorm as ONE launch (m2d_bn_train: statistics, grid-wide rendezvous, apply) instead of
 # two (colstats + bn_apply).  Measured on B200 at batch 7: 99 launches fewer per step (1163 -> 1064) but 56.9 vs 57.5 train
 # steps/s — blocks spinning at the rendezvous hold SM slots the concurrent streams could use — hence opt-in.
+_NOISE_BWD_SIDE = os.environ.get("M2D_NOISE_BWD_SIDE", "1") != "0"
 _BN_ONE_LAUNCH = os.environ.get("M2D_BN_FUSED", "0") != "0"
 
 
@@ -759,7 +760,15 @@ class GeneratorNet:
         e_z = wk.mat("g:e_z", 1, nb, self.Lat)
         self.fc1.dgrad(dc, e_z, ws=wk.scratch)
         ops.mark("gb:dec")
-        self.nrnn.bwd(e_z.cols_slice(self.H, self.Lat), B, T, wk, leaf=leaf)
+        # the noise GRU's BPTT (120 dependent steps on B CTAs) shares nothing with the audio path below e_z: side
+        # stream, like its forward; its parameter gradients follow it there
+        noise = self.s_noise if (self.par and _NOISE_BWD_SIDE) else None
+        if noise is not None:
+            noise.wait_stream(cur)
+            with torch.cuda.stream(noise):
+                self.nrnn.bwd(e_z.cols_slice(self.H, self.Lat), B, T, wk)
+        else:
+            self.nrnn.bwd(e_z.cols_slice(self.H, self.Lat), B, T, wk, leaf=leaf)
         e_enc = wk.mat("g:e_enc", 1, nb, self.I)
         self.rnn.bwd(e_z.cols_slice(0, self.H), B, T, wk, e_x=e_enc, leaf=leaf)
         ops.mark("gb:rnn")
@@ -767,6 +776,8 @@ class GeneratorNet:
         ops.mark("gb:enc")
         if side is not None:
             cur.wait_stream(side)
+        if noise is not None:
+            cur.wait_stream(noise)
 
 
 # ===========================================================================
