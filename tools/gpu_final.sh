@@ -1,20 +1,14 @@
 #!/bin/bash
-# Round-end state check sized for a small GPU budget: all GPU tests, the default bench line, one large-batch line,
-# then (if time remains) the ncu launch list of the same bench command.
+# Evidence refresh on the final tree (batch 7): DRAM traffic of the rowconv / wgrad launches of ONE train step (feeds
+# roofline.traffic), the ncu launch list of the bench command, the in-graph timeline.  Results -> gpurun_out/.
 set -u
 mkdir -p gpurun_out
-timeout 150 python -m pytest tests -m gpu -q 2>&1 | grep -E "^E  .*Error|^FAILED|passed|failed" > gpurun_out/pytest_gpu.log
-tail -n 5 gpurun_out/pytest_gpu.log
-timeout 120 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
-timeout 80 python bench.py --batch 512 --steps 3 --warmup 3 --no-cpu-baseline --no-device-dataset > gpurun_out/bench_b512.json 2>> gpurun_out/bench.err; echo "b512 rc=$?" >> gpurun_out/bench.err
-tail -n 4 gpurun_out/bench.err | cut -c1-300
-for f in bench bench_b512; do python - "$f" <<'PY'
-import json,sys
-try:
-    d=json.loads(open(f"gpurun_out/{sys.argv[1]}.json").read().strip().splitlines()[-1])
-    print(sys.argv[1], "value", round(d["value"],3), "ms/step", round(d["ms_per_step"],2), "e2e", round(d["e2e"]["value"],3), "launches/step", d["gpu_launches_per_step"], "roof", d.get("roofline",{}).get("kernel"), round(d.get("roofline",{}).get("frac",0),4), "cpu", d.get("cpu_baseline",{}).get("value"))
-except Exception as e: print(sys.argv[1], "unreadable", e)
-PY
+cp profiles/r02_traffic.json gpurun_out/r02_traffic.json
+M="dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"
+for fam in rowconv wgrad; do
+  timeout 900 ncu --profile-from-start off --nvtx --nvtx-include "$fam/" --metrics $M --clock-control none --csv --log-file gpurun_out/traffic_${fam}_b7.csv python tools/traffic_step.py 7 > gpurun_out/traffic_${fam}_b7.log 2>&1
+  python tools/summarize_traffic2.py $fam 7 default tf32x3 gpurun_out/traffic_${fam}_b7.csv gpurun_out/traffic_counts_b7.json gpurun_out/r02_traffic.json | tail -n 12
 done
-timeout 100 ncu --metrics gpu__time_duration.sum --clock-control none -s 3000 -c 4200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-graphs --no-cpu-baseline --no-roofline --no-device-dataset > gpurun_out/ncu_bench.log 2>&1
-echo "ncu rc=$?"; wc -l gpurun_out/launches.csv
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1800 -c 2600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-graphs --no-cpu-baseline --no-roofline --no-eager-gpu --no-throughput-regime --no-device-dataset > gpurun_out/ncu_bench.log 2>&1
+tail -n 2 gpurun_out/ncu_bench.log | cut -c1-300
+python tools/step_timeline.py 7 gpurun_out/timeline_b7.json > gpurun_out/timeline_b7.txt 2>&1; tail -n 3 gpurun_out/timeline_b7.txt
