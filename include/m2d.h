@@ -316,6 +316,26 @@ int m2d_upsample2_bwd(const float* dy, int lddy, float* dx, int lddx, int nb, in
 /* strided 2-D copy / transpose helpers for the (B,C,L) <-> channels-last boundary */
 int m2d_copy2d(const float* x, int ldx, float* y, int ldy, long long M, int C, int accumulate, void* stream);
 int m2d_transpose_bcl(const float* x, float* y, int nb, int R, int C, void* stream); /* [b,R,C]->[b,C,R] */
+/* n <= M2D_COPY2D_MAX strided copies in one launch, applied in order (`descs` is a HOST array, passed by value to the
+ * kernel): the code halves going in and out of the critic's concatenated fusion input (default.py:331-337, torch.cat
+ * and its backward), e.g. the audio code of B samples into the three row groups [interpolates; real; fake]. */
+#define M2D_COPY2D_MAX 4
+typedef struct m2d_copy2d_desc {
+    const float* x;     /* source, row stride ldx */
+    float* y;           /* destination, row stride ldy */
+    long long M;        /* rows */
+    int ldx, ldy, C;    /* row strides (floats), columns */
+    int accumulate;     /* y += x instead of y = x */
+} m2d_copy2d_desc;
+int m2d_copy2d_batch(const m2d_copy2d_desc* descs, int n, void* stream);
+
+/* The critic's fusion MLP on n rows (default.py:339-345: fc1 = Linear(F,H) + ReLU, fc2 = Linear(H,1)), one launch:
+ *   u[n,H] = relu(W1 x + b1), d[n] = W2 u + b2, and — if dd (upstream of the scores, n floats) is given — the
+ *   backward-data dh[n,H] = dd * W2 * [u > 0], dx[n, lddx] = W1^T dh.  w1 (H,F) and w2 (1,H) in the parameter layout.
+ *   fp32 CUDA-core arithmetic (the reference's own precision); H <= 256, F <= 8192. */
+int m2d_fusion_mlp(const float* x, int ldx, int n, int F, int H, const float* w1, const float* b1,
+                   const float* w2, const float* b2, const float* dd, float* u, float* d, float* dh,
+                   float* dx, int lddx, void* stream);
 
 /* Scalar losses (train.py:207-214 critic, :226-235 generator).  sums = fp64 {sum D(real),
  * sum D(fake), sum|real-fake|, sum|tv diffs|}.  mode 0: out = {err_fake-err_real+c0*gp, gp,

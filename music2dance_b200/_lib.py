@@ -101,6 +101,8 @@ SIGNATURES = {
     "m2d_upsample2": [_P, _I, _P, _I, _I, _I, _I, _P],
     "m2d_upsample2_bwd": [_P, _I, _P, _I, _I, _I, _I, _I, _P],
     "m2d_copy2d": [_P, _I, _P, _I, _L, _I, _I, _P],
+    "m2d_copy2d_batch": [_P, _I, _P],
+    "m2d_fusion_mlp": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "m2d_embed_rows": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
     "m2d_embed_grad": [_P, _I, _P, _P, _I, _I, _I, _I, _F, _F, _P],
     "m2d_transpose_bcl": [_P, _P, _I, _I, _I, _P],

@@ -602,6 +602,74 @@ __global__ void copy2d_kernel(const float* __restrict__ x, int ldx, float* y, in
     }
 }
 
+// up to M2D_COPY2D_MAX strided copies in ONE launch, applied in table order (thread t touches the same element index
+// of every entry, so an accumulating entry may follow the copy that initialises its destination)
+struct Copy2dBatch { m2d_copy2d_desc e[M2D_COPY2D_MAX]; int n; };
+__global__ void copy2d_batch_kernel(const Copy2dBatch b) {
+    for (int k = 0; k < b.n; ++k) {
+        const m2d_copy2d_desc d = b.e[k];
+        const long long total = d.M * d.C;
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+             i += (long long)gridDim.x * blockDim.x) {
+            const int c = (int)(i % d.C);
+            const long long r = i / d.C;
+            const float v = d.x[r * d.ldx + c];
+            float* o = d.y + r * d.ldy + c;
+            *o = d.accumulate ? *o + v : v;
+        }
+    }
+}
+
+// The critic's fusion MLP (default.py:339-345: Linear(F,H) + ReLU, Linear(H,1)) on a handful of rows, forward and —
+// when the upstream of the scores is known in advance (dd != null: the WGAN-GP critic step, where it is a constant) —
+// its backward-data in the same launch: one block per row, fp32 CUDA-core arithmetic (0.1 MFLOP per row).
+//   u = relu(W1 x + b1), d = W2 u + b2;   dh = dd * W2 * [u > 0],  dx = W1^T dh
+constexpr int FUSION_MAXH = 256;
+__global__ void __launch_bounds__(256)
+fusion_mlp_kernel(const float* __restrict__ x, int ldx, int F, int H, const float* __restrict__ w1,
+                  const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                  const float* __restrict__ dd, float* __restrict__ u, float* __restrict__ d, float* __restrict__ dh,
+                  float* __restrict__ dx, int lddx) {
+    extern __shared__ float fus_x[];                       // F floats
+    __shared__ float us[FUSION_MAXH], dhs[FUSION_MAXH];
+    const int row = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int f = tid; f < F; f += 256) fus_x[f] = x[(long long)row * ldx + f];
+    __syncthreads();
+    for (int j = warp; j < H; j += 8) {
+        const float* wr = w1 + (long long)j * F;
+        float a = 0.f;
+        for (int f = lane; f < F; f += 32) a = fmaf(wr[f], fus_x[f], a);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) {
+            const float v = fmaxf(a + b1[j], 0.f);
+            us[j] = v;
+            u[(long long)row * H + j] = v;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float a = 0.f;
+        for (int j = lane; j < H; j += 32) a = fmaf(w2[j], us[j], a);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) d[row] = a + b2[0];
+    }
+    if (!dd) return;
+    const float up = dd[row];
+    for (int j = tid; j < H; j += 256) {
+        const float g = us[j] > 0.f ? up * w2[j] : 0.f;
+        dhs[j] = g;
+        dh[(long long)row * H + j] = g;
+    }
+    __syncthreads();
+    for (int f = tid; f < F; f += 256) {
+        float a = 0.f;
+        for (int j = 0; j < H; ++j) a = fmaf(dhs[j], w1[(long long)j * F + f], a);
+        dx[(long long)row * lddx + f] = a;
+    }
+}
+
 __global__ void transpose_kernel(const float* __restrict__ x, float* y, int R, int C) {
     __shared__ float tile[32][33];
     const float* xb = x + (long long)blockIdx.z * R * C;
@@ -952,6 +1020,32 @@ extern "C" int m2d_copy2d(const float* x, int ldx, float* y, int ldy, long long 
     M2D_REQUIRE(x && y && M > 0 && C > 0, "copy2d: bad args");
     copy2d_kernel<<<grid1d(M * C), 256, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, M, C, accumulate);
     return check_launch("copy2d");
+}
+
+extern "C" int m2d_copy2d_batch(const m2d_copy2d_desc* descs, int n, void* stream) {
+    M2D_REQUIRE(descs && n > 0 && n <= M2D_COPY2D_MAX, "copy2d_batch: 1..M2D_COPY2D_MAX entries");
+    Copy2dBatch b;
+    long long most = 0;
+    for (int k = 0; k < n; ++k) {
+        M2D_REQUIRE(descs[k].x && descs[k].y && descs[k].M > 0 && descs[k].C > 0, "copy2d_batch: bad entry");
+        b.e[k] = descs[k];
+        const long long t = descs[k].M * descs[k].C;
+        most = t > most ? t : most;
+    }
+    b.n = n;
+    copy2d_batch_kernel<<<grid1d(most), 256, 0, (cudaStream_t)stream>>>(b);
+    return check_launch("copy2d_batch");
+}
+
+extern "C" int m2d_fusion_mlp(const float* x, int ldx, int n, int F, int H, const float* w1, const float* b1,
+                              const float* w2, const float* b2, const float* dd, float* u, float* d, float* dh,
+                              float* dx, int lddx, void* stream) {
+    M2D_REQUIRE(x && w1 && b1 && w2 && b2 && u && d && n > 0 && F > 0 && F <= 8192 && H > 0 && H <= FUSION_MAXH,
+                "fusion_mlp: bad args (H <= 256, F <= 8192)");
+    M2D_REQUIRE(!dd || (dh && dx), "fusion_mlp: backward needs dh and dx");
+    fusion_mlp_kernel<<<n, 256, (size_t)F * sizeof(float), (cudaStream_t)stream>>>(x, ldx, F, H, w1, b1, w2, b2, dd, u, d,
+                                                                                 dh, dx, lddx);
+    return check_launch("fusion_mlp");
 }
 
 extern "C" int m2d_transpose_bcl(const float* x, float* y, int nb, int R, int C, void* stream) {

@@ -32,6 +32,7 @@ PRIO_CHAIN, PRIO_LATE, PRIO_GEN, PRIO_LEAF = (-3, -2, -1, 0) if _PRIO_ON else (0
 # two (colstats + bn_apply).  Measured on B200 at batch 7: 99 launches fewer per step (1163 -> 1064) but 56.9 vs 57.5 train
 # steps/s — blocks spinning at the rendezvous hold SM slots the concurrent streams could use — hence opt-in.
 _NOISE_BWD_SIDE = os.environ.get("M2D_NOISE_BWD_SIDE", "1") != "0"
+_FUSION_ONE_LAUNCH = os.environ.get("M2D_FUSION_FUSED", "1") != "0"
 _BN_ONE_LAUNCH = os.environ.get("M2D_BN_FUSED", "0") != "0"
 
 
@@ -1111,14 +1112,24 @@ class CriticNet:
         return {"X": x0, "q": tq}
 
     # ---------------------------------------------------------------- fusion MLP
-    def fusion_fwd(self, sa, n, tag):
-        """sa Mat [1,n,F] -> scores Mat [1,n,1]; keeps u = relu(fc1(sa))."""
+    def fusion_fwd(self, sa, n, tag, dd=None):
+        """sa Mat [1,n,F] -> scores Mat [1,n,1]; keeps u = relu(fc1(sa)).  One launch (m2d_fusion_mlp); with dd (the
+        upstream of the scores, known in advance in the critic step) the same launch also does fusion_bwd and the
+        result is returned as (u, d, dh, dsa)."""
         wk = self.wk
         u = wk.mat(f"{tag}:u", 1, n, 128)
-        self.fc1.fwd(sa, u, act=ACT_RELU, ws=wk.scratch)
         d = wk.mat(f"{tag}:d", 1, n, 1)
-        self.fc2.fwd(u, d, ws=wk.scratch)
-        return u, d
+        if not _FUSION_ONE_LAUNCH:
+            self.fc1.fwd(sa, u, act=ACT_RELU, ws=wk.scratch)
+            self.fc2.fwd(u, d, ws=wk.scratch)
+            return (u, d) if dd is None else (u, d) + self.fusion_bwd(dd, u, n, tag)
+        if dd is None:
+            ops.fusion_mlp(sa, self.fc1.w, self.fc1.b, self.fc2.w, self.fc2.b, u, d)
+            return u, d
+        dh = wk.mat(f"{tag}:dh", 1, n, 128)
+        dsa = wk.mat(f"{tag}:dsa", 1, n, self.F)
+        ops.fusion_mlp(sa, self.fc1.w, self.fc1.b, self.fc2.w, self.fc2.b, u, d, dd=dd, dh=dh, dx=dsa)
+        return u, d, dh, dsa
 
     def fusion_bwd(self, dd, u, n, tag):
         """dd Mat [1,n,1] -> (dh [1,n,128] masked, dsa [1,n,F])."""

@@ -356,6 +356,35 @@ def copy2d(x, y, accumulate=False):
     call("m2d_copy2d", x.ptr, x.ld, y.ptr, y.ld, x.M, x.cols, int(accumulate), _stream())
 
 
+def fusion_mlp(x, w1, b1, w2, b2, u, d, dd=None, dh=None, dx=None):
+    """u = relu(fc1(x)), d = fc2(u) on the rows of x [1,n,F]; with dd (n floats) also dh / dx (see m2d_fusion_mlp)."""
+    H = w1.shape[0]
+    assert x.nb == 1 and w1.shape[1] == x.cols and u.cols == H and u.ld == H and (dh is None or dh.ld == H)
+    LAUNCHES[0] += 1
+    call("m2d_fusion_mlp", x.ptr, x.ld, x.rows, x.cols, H, _p(w1), _p(b1), _p(w2), _p(b2),
+         None if dd is None else dd.ptr, u.ptr, d.ptr, None if dh is None else dh.ptr,
+         None if dx is None else dx.ptr, 0 if dx is None else dx.ld, _stream())
+
+
+class Copy2dDesc(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("y", C.c_void_p), ("M", C.c_longlong), ("ldx", C.c_int), ("ldy", C.c_int),
+                ("C", C.c_int), ("accumulate", C.c_int)]
+
+
+COPY2D_MAX = 4
+
+
+def copy2d_batch(entries):
+    """entries: up to 4 (x Mat, y Mat, accumulate) strided copies, ONE launch, applied in order."""
+    assert 0 < len(entries) <= COPY2D_MAX
+    arr = (Copy2dDesc * len(entries))()
+    for i, (x, y, accumulate) in enumerate(entries):
+        assert (x.M, x.cols) == (y.M, y.cols)
+        arr[i] = Copy2dDesc(x.ptr, y.ptr, x.M, x.ld, y.ld, x.cols, int(accumulate))
+    LAUNCHES[0] += 1
+    call("m2d_copy2d_batch", C.cast(arr, C.c_void_p), len(entries), _stream())
+
+
 def embed_rows(table, labels, y, B, T, n_classes, err=None):
     """y[(b*T+t), :E] = table[labels[b]] for a Mat `y` that is the label-column slice of a concatenated operand
     (conditional.py:19-21,45-46); labels int64 on the device."""

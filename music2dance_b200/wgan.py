@@ -50,8 +50,8 @@ def critic_forward(D, X, audio, nS, nA, tag, groups=1):
     if not D.ablated:
         with D.fork():                                   # audio branch: side stream
             sva = D.audio_fwd(audio, nA, tag)
-            for g in range(groups):
-                ops.copy2d(sva["code"], rows(sa, g * nA, (g + 1) * nA).cols_slice(D.code, D.F))
+            ops.copy2d_batch([(sva["code"], rows(sa, g * nA, (g + 1) * nA).cols_slice(D.code, D.F), False)
+                              for g in range(groups)])
     svp = D.pose_fwd(X, nS, tag)
     ops.copy2d(svp["code"], sa.cols_slice(0, D.code))
     D.join()
@@ -147,16 +147,33 @@ def critic_forward_fused(D, X3, audio, B, tag, before_pose=None):
     if not D.ablated:
         with D.fork():
             sva = D.audio_fwd(audio, B, tag, dup=True)
-            for g in range(3):
-                ops.copy2d(sva["code"], rows(sa, g * B, (g + 1) * B).cols_slice(D.code, D.F))
+            ops.copy2d_batch([(sva["code"], rows(sa, g * B, (g + 1) * B).cols_slice(D.code, D.F), False)
+                              for g in range(3)])
     if before_pose is not None:
         before_pose()
     svp = D.pose_fwd(X3, n3, tag)
     ops.copy2d(svp["code"], sa.cols_slice(0, D.code))
     D.join()
-    u, d = D.fusion_fwd(sa, n3, tag)
+    # the upstream of the scores is a constant of the step, so the fusion MLP's backward-data rides in its forward launch
+    ddm = score_upstream(D, B)
+    u, d, dh, dsa = D.fusion_fwd(sa, n3, "f", dd=ddm)
     ops.mark(f"{tag}:fwd_end")
-    return dict(svp=svp, sva=sva, sa=sa, u=u, d=d)
+    return dict(svp=svp, sva=sva, sa=sa, u=u, d=d, ddm=ddm, dh=dh, dsa=dsa)
+
+
+def score_upstream(D, B):
+    """d(err_fake - err_real + gamma*gp) / d(scores) over the rows [interpolates; real; fake] up to the penalty's
+    kappa (applied later): 1, -1/B, +1/B — a constant vector, written once."""
+    wk = D.wk
+    n3 = 3 * B
+    dd = wk.vec("f:dd", n3)
+    consts = D.__dict__.setdefault("_consts", set())
+    if ("f", "dd", B) not in consts:
+        ops.fill(dd[:B], B, 1.0)
+        ops.fill(dd[B:2 * B], B, -1.0 / B)
+        ops.fill(dd[2 * B:], B, 1.0 / B)
+        consts.add(("f", "dd", B))
+    return Mat(dd, 1, n3, 1)
 
 
 def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f", aud2=None, early_reduce=None):
@@ -178,16 +195,9 @@ def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f", aud2=
     wk, T, O, code = D.wk, D.T, D.O, D.code
     n3 = 3 * B
     A1 = lambda c: wk.acc_slot(c)
-    dd = wk.vec(f"{tag}:dd", n3)                                  # upstream of the scores: a constant, written once
-    consts = D.__dict__.setdefault("_consts", set())
-    if (tag, "dd", B) not in consts:
-        ops.fill(dd[:B], B, 1.0)
-        ops.fill(dd[B:2 * B], B, -1.0 / B)
-        ops.fill(dd[2 * B:], B, 1.0 / B)
-        consts.add((tag, "dd", B))
-    ddm = Mat(dd, 1, n3, 1)
+    ddm = fw["ddm"]                                               # upstream of the scores: a constant (score_upstream)
     u, sa = fw["u"], fw["sa"]
-    dh, dsa = D.fusion_bwd(ddm, u, n3, tag)                       # the branches' upstreams first: they start at once
+    dh, dsa = fw["dh"], fw["dsa"]                                 # fusion MLP backward-data: done by the forward launch
     ops.mark(f"{tag}:fusion_bwd")
     g1 = ss1 = None
     sva = fw["sva"]
@@ -197,9 +207,9 @@ def critic_backward_fused(D, fw, B, audio, gamma, gp_out, k0, k1, tag="f", aud2=
         g1 = aud2 if aud2 is not None else wk.mat(f"{tag}:aud2", 2 * B, Alen, 1)   # [audio; v1]: stacked input of l1
         with D.fork():
             d_a2 = wk.mat(f"{tag}:d_a2", 1, 2 * B, code)
-            ops.copy2d(rows(dsa, B, 2 * B).cols_slice(code, D.F), rows(d_a2, 0, B))
-            ops.copy2d(rows(dsa, 2 * B, n3).cols_slice(code, D.F), rows(d_a2, 0, B), accumulate=True)
-            ops.copy2d(rows(dsa, 0, B).cols_slice(code, D.F), rows(d_a2, B, 2 * B))
+            ops.copy2d_batch([(rows(dsa, B, 2 * B).cols_slice(code, D.F), rows(d_a2, 0, B), False),
+                              (rows(dsa, 2 * B, n3).cols_slice(code, D.F), rows(d_a2, 0, B), True),
+                              (rows(dsa, 0, B).cols_slice(code, D.F), rows(d_a2, B, 2 * B), False)])
             sv2 = {"q": sva["q2"], "code": None, "X": None}
             dla = D.audio_bwd(sv2, d_a2, 2 * B, tag, wgrads=False, dX=None)
             gv = g1.batch_slice(B, 2 * B)

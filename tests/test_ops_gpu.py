@@ -407,6 +407,75 @@ def test_batchnorm_groups(lib, case):
     close(y2[Gn - 1], ref, what="grouped bn vs torch (last block)")
 
 
+@pytest.mark.parametrize("n,F,H", [(21, 200, 128), (6, 100, 128), (14, 37, 50)])
+def test_fusion_mlp(lib, n, F, H):
+    """m2d_fusion_mlp: Linear(F,H) + ReLU + Linear(H,1) forward and backward-data in one launch vs torch autograd."""
+    from music2dance_b200.ops import Mat
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(n, F + 8, generator=g)                     # padded rows: ld > F
+    w1, b1 = torch.randn(H, F, generator=g) / F ** 0.5, torch.randn(H, generator=g) * 0.1
+    w2, b2 = torch.randn(1, H, generator=g) / H ** 0.5, torch.randn(1, generator=g)
+    dd = torch.randn(n, generator=g)
+    xr = x[:, :F].clone().requires_grad_(True)
+    u_ref = F_relu(xr @ w1.T + b1)
+    d_ref = (u_ref @ w2.T + b2).squeeze(1)
+    u_ref.retain_grad()
+    d_ref.backward(dd)
+    xd = x.to(DEV)
+    X = Mat(xd, 1, n, F, F + 8)
+    dev = lambda t: t.to(DEV).contiguous()
+    W1, B1, W2, B2, DD = dev(w1), dev(b1), dev(w2), dev(b2), dev(dd)
+    u, d = torch.empty(n, H, device=DEV), torch.empty(n, device=DEV)
+    dh, dx = torch.empty(n, H, device=DEV), torch.full((n, F + 4), 5.0, device=DEV)
+    lib.fusion_mlp(X, W1, B1, W2, B2, Mat.of(u, 1, n, H), Mat.of(d, 1, n, 1), dd=Mat.of(DD, 1, n, 1),
+                   dh=Mat.of(dh, 1, n, H), dx=Mat(dx, 1, n, F, F + 4))
+    torch.cuda.synchronize()
+    close(u, u_ref, tol=2e-6, what="fusion u")
+    close(d, d_ref, tol=2e-6, what="fusion d")
+    close(dh, u_ref.grad * (u_ref > 0), tol=2e-6, what="fusion dh")
+    close(dx[:, :F], xr.grad, tol=2e-6, what="fusion dx")
+    assert float((dx[:, F:] - 5.0).abs().max()) == 0.0          # columns beyond F untouched
+    # forward only
+    u2, d2 = torch.empty(n, H, device=DEV), torch.empty(n, device=DEV)
+    lib.fusion_mlp(X, W1, B1, W2, B2, Mat.of(u2, 1, n, H), Mat.of(d2, 1, n, 1))
+    assert torch.equal(u2, u) and torch.equal(d2, d)
+
+
+def F_relu(t):
+    return torch.relu(t)
+
+
+def test_copy2d_batch(lib):
+    """m2d_copy2d_batch: several strided copies in one launch, in table order (accumulate after initialise)."""
+    from music2dance_b200.ops import Mat
+    g = torch.Generator().manual_seed(21)
+    B, code = 7, 50
+    dsa = torch.randn(3 * B, 2 * code, generator=g).to(DEV)
+    d_a2 = torch.full((2 * B, code), 7.0, device=DEV)
+    src = Mat.of(dsa, 1, 3 * B, 2 * code)
+    dst = Mat.of(d_a2, 1, 2 * B, code)
+    lib.copy2d_batch([(_rows(src, B, 2 * B).cols_slice(code, 2 * code), _rows(dst, 0, B), False),
+                      (_rows(src, 2 * B, 3 * B).cols_slice(code, 2 * code), _rows(dst, 0, B), True),
+                      (_rows(src, 0, B).cols_slice(code, 2 * code), _rows(dst, B, 2 * B), False)])
+    torch.cuda.synchronize()
+    assert torch.equal(d_a2[:B], dsa[B:2 * B, code:] + dsa[2 * B:, code:])
+    assert torch.equal(d_a2[B:], dsa[:B, code:])
+    # broadcast of one block into three row groups of a wider matrix; the other columns stay untouched
+    c = torch.randn(B, code, generator=g).to(DEV)
+    sa = torch.zeros(3 * B, 2 * code, device=DEV)
+    S = Mat.of(sa, 1, 3 * B, 2 * code)
+    lib.copy2d_batch([(Mat.of(c, 1, B, code), _rows(S, k * B, (k + 1) * B).cols_slice(code, 2 * code), False)
+                      for k in range(3)])
+    assert torch.equal(sa[:, code:], c.repeat(3, 1)) and float(sa[:, :code].abs().max()) == 0.0
+    with pytest.raises((AssertionError, RuntimeError)):
+        lib.copy2d_batch([(Mat.of(c, 1, B, code), Mat.of(c.clone(), 1, B, code), False)] * 5)
+
+
+def _rows(m, a, b):
+    from music2dance_b200.wgan import rows
+    return rows(m, a, b)
+
+
 def test_pool_upsample(lib):
     from music2dance_b200.ops import Mat
     g = torch.Generator().manual_seed(9)
