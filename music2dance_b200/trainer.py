@@ -30,6 +30,29 @@ from .wgan import (critic_backward_fused, critic_forward, critic_forward_fused, 
 
 # one batched generator pass serves at most this many sequences (trainer.gen_groups)
 GEN_GROUP_SEQUENCES = 64
+
+
+def plan_gen_groups(nc, B, spec=None):
+    """{first iteration of a pass: iterations it serves} for the generator forwards of the nc critic iterations of a
+    train step (host logic, no device).  spec: "8", "1,7", ... (sizes in order, summing to nc); default: consecutive
+    passes of at most GEN_GROUP_SEQUENCES // B iterations (at least one)."""
+    if spec:
+        sizes = [int(x) for x in spec.split(",")]
+        if not (all(g >= 1 for g in sizes) and sum(sizes) == nc):
+            raise ValueError(f"M2D_GEN_GROUPS={spec!r}: positive sizes that sum to n_critic_steps={nc} expected")
+    else:
+        gmax = max(1, GEN_GROUP_SEQUENCES // B)
+        sizes, left = [], nc
+        while left > 0:
+            sizes.append(min(gmax, left))
+            left -= sizes[-1]
+    plan, i = {}, 0
+    for g in sizes:
+        plan[i] = g
+        i += g
+    return plan
+
+
 LOG_CRITIC = ("loss_critic", "gp", "w_dist", "err_real", "err_fake")
 LOG_GEN = ("loss_gen", "l1", "tv", "err_real", "err_fake")
 
@@ -231,21 +254,7 @@ class Phase3Trainer:
             ops.set_gru_forward_batch_group(self.gru_bg if on else 0)
 
     def _plan_gen_groups(self, spec):
-        nc, B = self.nc, self.B
-        if spec:
-            sizes = [int(x) for x in spec.split(",")]
-            assert all(g >= 1 for g in sizes) and sum(sizes) == nc, f"M2D_GEN_GROUPS={spec!r} must sum to n_critic={nc}"
-        else:
-            gmax = max(1, GEN_GROUP_SEQUENCES // B)
-            sizes, left = [], nc
-            while left > 0:
-                sizes.append(min(gmax, left))
-                left -= sizes[-1]
-        plan, i = {}, 0
-        for g in sizes:
-            plan[i] = g
-            i += g
-        return plan
+        return plan_gen_groups(self.nc, self.B, spec)
 
     def _gen_forward(self, i):
         """Generator forward(s) of critic iteration i (train-mode BatchNorm, nothing kept for a backward): the pass

@@ -328,7 +328,7 @@ def test_batched_generator_passes_match_one_pass_per_iteration(variant, groups, 
         monkeypatch.setenv("M2D_GEN_GROUPS", spec)
         gen, critic = build(cfg)
         tr = Phase3Trainer(gen, critic, cfg, B, use_graphs=False)
-        assert sorted(tr.gen_groups.values()) == sorted(int(x) for x in spec.split(","))
+        assert [tr.gen_groups[i] for i in sorted(tr.gen_groups)] == [int(x) for x in spec.split(",")]
         bs = [O.synthetic_batch(cfg, B, 9100 + i) for i in range(nc)]
         tr.load_batches(*[torch.stack([b[j] for b in bs]) for j in range(4)], bs[-1][4])
         tr.train_step()
