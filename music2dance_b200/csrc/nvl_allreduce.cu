@@ -68,22 +68,49 @@ struct NvlPtrs {
 };
 
 // reduce + broadcast this block's share of rank `rank`'s slice of one segment
-__device__ __forceinline__ void nvl_segment(float* const* buf, float* mc, int rank, int world, long long off, long long n4) {
+__device__ __forceinline__ void nvl_segment(float* const* buf, float* mc, int rank, int world, long long off, long long n4,
+                                            bool unroll) {
     const long long per_rank = (n4 + world - 1) / world;
     const long long r0 = rank * per_rank, r1 = r0 + per_rank < n4 ? r0 + per_rank : n4;
     const long long base4 = off >> 2;
+    // four independent 16-byte transactions in flight per thread: one ld_reduce -> st round trip over the switch takes
+    // a few microseconds, so the kernel is bound by bytes in flight, not by the links (one vector per thread and 32
+    // blocks = 256 KiB in flight moved ~150 GB/s)
+    const long long stride = (long long)gridDim.x * NVL_THREADS;
+    long long i = r0 + (long long)blockIdx.x * NVL_THREADS + threadIdx.x;
     if (mc) {
         float4* m4 = reinterpret_cast<float4*>(mc) + base4;
-        for (long long i = r0 + (long long)blockIdx.x * NVL_THREADS + threadIdx.x; i < r1;
-             i += (long long)gridDim.x * NVL_THREADS) {
+        for (; unroll && i + 3 * stride < r1; i += 4 * stride) {
+            const float4 v0 = mc_ld_reduce(reinterpret_cast<const float*>(m4 + i));
+            const float4 v1 = mc_ld_reduce(reinterpret_cast<const float*>(m4 + i + stride));
+            const float4 v2 = mc_ld_reduce(reinterpret_cast<const float*>(m4 + i + 2 * stride));
+            const float4 v3 = mc_ld_reduce(reinterpret_cast<const float*>(m4 + i + 3 * stride));
+            mc_st(reinterpret_cast<float*>(m4 + i), v0);
+            mc_st(reinterpret_cast<float*>(m4 + i + stride), v1);
+            mc_st(reinterpret_cast<float*>(m4 + i + 2 * stride), v2);
+            mc_st(reinterpret_cast<float*>(m4 + i + 3 * stride), v3);
+        }
+        for (; i < r1; i += stride) {
             const float4 v = mc_ld_reduce(reinterpret_cast<const float*>(m4 + i));
             mc_st(reinterpret_cast<float*>(m4 + i), v);
         }
     } else {
-        for (long long i = r0 + (long long)blockIdx.x * NVL_THREADS + threadIdx.x; i < r1;
-             i += (long long)gridDim.x * NVL_THREADS) {
-            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (; unroll && i + stride < r1; i += 2 * stride) {
+            float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
             for (int p = 0; p < world; ++p) {                    // fixed order: identical sums on every rank
+                const float4 a = __ldcg(reinterpret_cast<const float4*>(buf[p]) + base4 + i);
+                const float4 b = __ldcg(reinterpret_cast<const float4*>(buf[p]) + base4 + i + stride);
+                s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+                s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
+            }
+            for (int p = 0; p < world; ++p) {
+                __stcg(reinterpret_cast<float4*>(buf[p]) + base4 + i, s0);
+                __stcg(reinterpret_cast<float4*>(buf[p]) + base4 + i + stride, s1);
+            }
+        }
+        for (; i < r1; i += stride) {
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int p = 0; p < world; ++p) {
                 const float4 v = __ldcg(reinterpret_cast<const float4*>(buf[p]) + base4 + i);
                 s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
             }
@@ -95,10 +122,10 @@ __device__ __forceinline__ void nvl_segment(float* const* buf, float* mc, int ra
 __global__ void __launch_bounds__(NVL_THREADS)
 nvl_allreduce_kernel(const NvlPtrs P, float* mc, const int rank, const int world, const long long off,
                      const long long n4 /* 16-byte vectors */, float* mc2, const long long off2, const long long n4_2,
-                     const int slot0, int* status, const unsigned long long timeout_ns) {
+                     const int slot0, int* status, const unsigned long long timeout_ns, const int unroll) {
     meet_peers(P.pad, rank, world, slot0, status, timeout_ns);
-    nvl_segment(P.buf, mc, rank, world, off, n4);
-    if (n4_2 > 0) nvl_segment(P.buf2, mc2, rank, world, off2, n4_2);
+    nvl_segment(P.buf, mc, rank, world, off, n4, unroll != 0);
+    if (n4_2 > 0) nvl_segment(P.buf2, mc2, rank, world, off2, n4_2, unroll != 0);
     __threadfence_system();
     meet_peers(P.pad, rank, world, slot0, status, timeout_ns);
 }
@@ -124,8 +151,10 @@ static int nvl_launch(float* const* bufs, float* mc, long long off, long long n,
         P.pad[r] = signal_pads[r];
     }
     M2D_REQUIRE((!mc || aligned16(mc)) && (!mc2 || aligned16(mc2)), "nvl_allreduce: unaligned multicast pointer");
+    static const int unroll = getenv("M2D_NVL_UNROLL") ? atoi(getenv("M2D_NVL_UNROLL")) : 1;   // 0: one vector in flight per thread
     nvl_allreduce_kernel<<<blocks, NVL_THREADS, 0, (cudaStream_t)stream>>>(P, mc, rank, world, off, n >> 2, mc2, off2,
-                                                                          n2 >> 2, slot0, status, 2000000000ull /* 2 s */);
+                                                                          n2 >> 2, slot0, status, 2000000000ull /* 2 s */,
+                                                                          unroll);
     return check_launch("nvl_allreduce");
 }
 

@@ -8,6 +8,8 @@ step, with the 1/world factor folded into the fused Adam kernel (`gscale`).  Gen
 uses per-replica statistics (standard DDP semantics)."""
 from __future__ import annotations
 
+import os
+
 import torch
 
 
@@ -67,7 +69,7 @@ class NvlAllReduce:
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.blocks = blocks
+        self.blocks = int(os.environ.get("M2D_NVL_BLOCKS", blocks))
         if symm.get_signal_pad_size() < pad_bytes:
             symm.set_signal_pad_size(pad_bytes)
         self.pad_slots = symm.get_signal_pad_size() // 4
